@@ -1,0 +1,129 @@
+/* yume_b200.h — C ABI of libyume_b200.so: the B200 (sm_100a) kernels behind YUME's denoise hot path.
+ *
+ * The reference (stdstu12/YUME) has no FFI: its extension seam is Python method re-binding on the
+ * WanModel instance (wan23/textimage2video.py:190-194) plus the module-level function
+ * `flash_attention` (wan23/modules/attention.py:24-38). This C ABI sits *under* those seams: the Python
+ * host side (yume_b200/*.py) keeps the reference's call signatures and hands raw device pointers to the
+ * entry points below. Each entry point names the reference code it replaces.
+ *
+ * Conventions: every pointer is a CUDA device pointer unless stated; `stream` is a cudaStream_t passed as
+ * void*; functions never allocate device memory, never synchronise, never throw; they return 0 on
+ * success or a negative YB_ERR_* code. Row-major everywhere, strides in elements.
+ */
+#ifndef YUME_B200_H_
+#define YUME_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YB_OK 0
+#define YB_ERR_ARG (-1)        /* null pointer / out-of-range enum / non-positive size */
+#define YB_ERR_SHAPE (-2)      /* shape not supported by the kernel (see each function) */
+#define YB_ERR_ALIGNMENT (-3)  /* pointer or stride not 16-byte aligned */
+#define YB_ERR_NO_DRIVER (-4)  /* cuTensorMapEncodeTiled not available (no CUDA driver) */
+#define YB_ERR_TENSORMAP (-5)  /* driver rejected a TMA descriptor */
+#define YB_ERR_LAUNCH (-6)     /* kernel launch failed (message on stderr) */
+
+/* ABI version: bump on any signature change. */
+int yb_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM with fused epilogue: out = epi(A[M,K] * B[N,K]^T + bias[N]); A, B bf16; fp32 accumulate (tcgen05).
+ * Replaces nn.Linear q/k/v/o (wan23/modules/model.py:171-174,190-192,206), ffn (:265-267,309-312),
+ * text_embedding (:455-457), cross-attn projections (:222-224,231) and the patch-embedding Conv3d
+ * (kernel==stride, :453-454) after yb_patchify has gathered the patches.
+ * Constraints: N % 32 == 0, K % 8 == 0, lda/ldb % 8 == 0, ldo % 8 == 0; A, B, out 16-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+#define YB_EPI_BF16 0      /* out bf16 = acc + bias */
+#define YB_EPI_GELU_BF16 1 /* out bf16 = gelu_tanh(acc + bias)            (nn.GELU(approximate='tanh')) */
+#define YB_EPI_F32 2       /* out f32  = acc + bias */
+#define YB_EPI_GATE_RES 3  /* out f32 += (acc + bias) * gate[tok_idx[m]][n]   (model.py:304,308,312) */
+
+typedef struct yb_gemm_args {
+  const void* A;   /* bf16 [M, K], row stride lda */
+  const void* B;   /* bf16 [N, K], row stride ldb  (nn.Linear.weight layout) */
+  const void* bias;/* f32 [N] or NULL */
+  void* out;       /* bf16/f32 [M, N] row stride ldo; for YB_EPI_GATE_RES the fp32 residual stream, updated in place */
+  const void* gate;    /* YB_EPI_GATE_RES: f32 [U, gate_ld] gate table or NULL (gate == 1, cross-attention) */
+  const void* tok_idx; /* YB_EPI_GATE_RES: int32 [M] row of `gate` per token, or NULL (all tokens use row 0) */
+  long long lda, ldb, ldo, gate_ld;
+  int M, N, K;
+  int epilogue;    /* YB_EPI_* */
+  int block_n;     /* 0 = auto, or 128 / 256 */
+} yb_gemm_args;
+int yb_gemm_bf16(const yb_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused LayerNorm (no affine, eps) + adaLN modulate -> bf16:  h = LN(x) * (1 + scale) + shift
+ * Replaces WanLayerNorm.forward + `norm1(x).float() * (1 + e[1]) + e[0]` (wan23/modules/model.py:140-150,
+ * 301,310; 14B: wan/modules/model.py:470-476). With `weight`/`lnbias` non-NULL and scale/shift NULL it is
+ * the affine norm3 in front of cross-attention (:259-261,308).
+ *   x      f32 [L, C]            scale/shift: f32 rows of a [U, mod_ld] table, selected per token by tok_idx
+ *   out    bf16 [L, ldo] (out_f32 == 0) or f32 [L, ldo] (out_f32 == 1, used by Head: model.py:343-347)
+ * Constraints: C % 8 == 0, C <= 8192.
+ * ------------------------------------------------------------------------------------------- */
+int yb_ln_modulate(const void* x, long long ldx, void* out, long long ldo, int out_f32, const void* scale,
+                   const void* shift, long long mod_ld, const void* tok_idx, const void* weight, const void* lnbias,
+                   int L, int C, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused WanRMSNorm (over the full C row, fp32 math) + weight + 3-axis RoPE, in place on bf16 rows.
+ * Replaces WanRMSNorm.forward (wan23/modules/model.py:121-137) and rope_apply (:38-118) for q and k.
+ *   qk     bf16, rows of C elements at qk + t*ld (t < L); normalised, scaled by weight[C] (f32) and,
+ *          when `rope` != NULL, rotated: pair j of every head uses (cos,sin) = rope[t][j] (f32 [L, D/2, 2]);
+ *          tokens t >= rope_len are left un-rotated (model.py:73).
+ * Constraints: C % 8 == 0, head_dim D even, C % D == 0.
+ * ------------------------------------------------------------------------------------------- */
+int yb_rmsnorm_rope(void* qk, long long ld, const void* weight, const void* rope, int rope_len, int L, int C, int D,
+                    float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Non-causal softmax(Q K^T * scale) V, head_dim 128, bf16 in / bf16 out, fp32 softmax + accumulate.
+ * Replaces flash_attention(q, k, v, k_lens=...) (wan23/modules/attention.py:24-130) for B == 1.
+ *   q: bf16 [Lq, heads*128] at row stride ldq (head h = columns [h*128, h*128+128)); k, v likewise with Lk rows.
+ *   Keys >= Lk are masked (the k_lens contract, attention.py:74-81). out: bf16 [Lq, heads*128] stride ldo.
+ * Constraints: head_dim == 128; strides % 8 == 0; pointers 16-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+int yb_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
+                 long long ldo, int Lq, int Lk, int heads, float scale, int variant, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * patchify gather (bit-exact index op): x f32 [Cin, F, H, W] -> bf16 [F*(Hp)*(Wp), Cin*ph*pw] rows in
+ * (f, h, w) token order, columns in Conv3d weight order (cin, ph, pw); H, W zero-padded up to a multiple
+ * of the patch (convpadd, wan23/modules/model.py:918-931). Replaces the data movement of
+ * `patch_embedding(u).flatten(2).transpose(1, 2)` (:750-753); the contraction itself is yb_gemm_bf16.
+ * ------------------------------------------------------------------------------------------- */
+int yb_patchify(const void* x, void* out, long long ldo, int Cin, int F, int H, int W, int ph, int pw, void* stream);
+
+/* unpatchify (bit-exact): y f32 [L, ph*pw*Cout] (row stride ldy) -> out f32 [Cout, F, Hp*ph, Wp*pw]
+ * (einsum 'fhwpqrc->cfphqwr', wan23/modules/model.py:867-890; patch_t == 1). */
+int yb_unpatchify(const void* y, long long ldy, void* out, int Cout, int F, int Hp, int Wp, int ph, int pw,
+                  void* stream);
+
+/* Sinusoidal timestep embedding in fp64 -> f32 [n, dim] = [cos | sin] (wan23/modules/model.py:14-24). t: f32 [n]. */
+int yb_sinusoidal(const void* t, void* out, int n, int dim, void* stream);
+
+/* Small-M fp32 linear: out[M,N] = act(in[M,K]) * W[N,K]^T + bias, act = SiLU if silu_in (M <= 16).
+ * Replaces time_embedding / time_projection under autocast(fp32) (wan23/modules/model.py:459-461,805-812). */
+int yb_linear_f32_small(const void* in, const void* W, const void* bias, void* out, int M, int N, int K, int silu_in,
+                        void* stream);
+
+/* General fp32 linear (SIMT, exact fp32): out[M,N] = in[M,K] * W[N,K]^T + bias. Replaces Head.head
+ * (wan23/modules/model.py:331,346) which the reference runs under autocast(fp32). N % 4 == 0, K % 4 == 0. */
+int yb_linear_f32(const void* in, long long ldi, const void* W, const void* bias, void* out, long long ldo, int M,
+                  int N, int K, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Self-test of the tcgen05 building blocks on one 128x128x128 tile (used by tests/, not by the product path).
+ *   mode 0: A smem K-major, B smem K-major        D = A[128,128] * Bk[128(n),128(k)]^T
+ *   mode 1: A smem K-major, B smem MN-major       D = A * Bmn[128(k),128(n)]
+ *   mode 2: A in TMEM (bf16x2 packed), B MN-major D = A * Bmn
+ * A, B bf16 [128,128] row-major; D f32 [128,128].
+ * ------------------------------------------------------------------------------------------- */
+int yb_umma_probe(const void* A, const void* B, void* D, int mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YUME_B200_H_ */

@@ -1,0 +1,80 @@
+"""ctypes binding of libyume_b200.so (include/yume_b200.h). The library is mandatory: there is no Python /
+PyTorch / CPU fallback for any op — a missing library is a hard error."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libyume_b200.so"
+
+YB_EPI_BF16, YB_EPI_GELU_BF16, YB_EPI_F32, YB_EPI_GATE_RES = 0, 1, 2, 3
+
+_ERRORS = {
+    -1: "YB_ERR_ARG (null pointer / bad enum / non-positive size)",
+    -2: "YB_ERR_SHAPE (shape not supported by the kernel)",
+    -3: "YB_ERR_ALIGNMENT (pointer or stride not 16-byte aligned)",
+    -4: "YB_ERR_NO_DRIVER (cuTensorMapEncodeTiled unavailable: no CUDA driver)",
+    -5: "YB_ERR_TENSORMAP (driver rejected a TMA descriptor)",
+    -6: "YB_ERR_LAUNCH (kernel launch failed)",
+}
+
+
+class YumeB200Error(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    """Mirror of `struct yb_gemm_args` (include/yume_b200.h)."""
+
+    _fields_ = [
+        ("A", C.c_void_p), ("B", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p),
+        ("gate", C.c_void_p), ("tok_idx", C.c_void_p),
+        ("lda", C.c_longlong), ("ldb", C.c_longlong), ("ldo", C.c_longlong), ("gate_ld", C.c_longlong),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("epilogue", C.c_int), ("block_n", C.c_int),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/yume_b200.h declares
+_vp, _ll, _i, _f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+SIGNATURES = {
+    "yb_abi_version": (_i, []),
+    "yb_gemm_bf16": (_i, [C.POINTER(GemmArgs), _vp]),
+    "yb_ln_modulate": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp, _ll, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "yb_rmsnorm_rope": (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "yb_attention": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _f, _i, _vp]),
+    "yb_patchify": (_i, [_vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
+    "yb_unpatchify": (_i, [_vp, _ll, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "yb_sinusoidal": (_i, [_vp, _vp, _i, _i, _vp]),
+    "yb_linear_f32_small": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "yb_linear_f32": (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
+    "yb_umma_probe": (_i, [_vp, _vp, _vp, _i, _vp]),
+}
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (once). Raises YumeB200Error if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise YumeB200Error(
+            f"{_LIB_PATH} is missing: build it with `python -m yume_b200.build` (or __graft_entry__.build()). "
+            "yume_b200 has no fallback path.")
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise YumeB200Error(f"{what} failed: {_ERRORS.get(rc, rc)}")

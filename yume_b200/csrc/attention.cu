@@ -1,0 +1,345 @@
+// attention.cu — FlashAttention-style forward for sm_100a: TMA-staged Q/K/V tiles, tcgen05.mma with fp32
+// accumulators in TMEM, online softmax in registers (one thread per query row), P fed back to the tensor
+// core from TMEM (or shared memory, variant 1).
+//
+// Replaces flash_attention(q, k, v, k_lens) as used by WanSelfAttention / WanCrossAttention
+// (reference: wan23/modules/attention.py:24-130 -> flash_attn_varlen_func; call sites
+//  wan23/modules/model.py:197-202 self, :227 cross; wan/modules/model.py:306-311, 380-383).
+// Contract kept: non-causal, softmax scale 1/sqrt(D), keys >= k_len dropped, bf16 inputs, fp32 accumulate,
+// output in [L, heads, D] layout (so the o-projection GEMM reads it directly). Batch is 1 on every Yume path.
+//
+// CTA = 2 query tiles of 128 rows (ping-pong), one head. 384 threads:
+//   warp 0        TMA producer (Q once; K_j / V_j through an smem ring)
+//   warp 1        MMA issuer (single thread): S_X = Q_X K_j^T  and  O_X += P_X V_j
+//   warps 4-7     softmax for query tile 0: thread t owns row t (TMEM lane t)
+//   warps 8-11    softmax for query tile 1
+// TMEM columns: [0,128) S_0 / P_0, [128,256) S_1 / P_1, [256,384) O_0, [384,512) O_1.
+// Issue order per KV tile j: PV_0(j), S_0(j+1), PV_1(j), S_1(j+1) — while the tensor core works on tile X
+// the softmax warps of tile 1-X run. O is rescaled lazily (only when a row max grows by > 2^8).
+#include "yb_host.h"
+#include "yb_ptx.cuh"
+
+namespace yb {
+
+constexpr int ATT_THREADS = 384;
+constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // one 128x128 bf16 tile = 2 swizzled slabs of 16 KB
+
+struct AttParams {
+  __nv_bfloat16* out;
+  long long ldo;
+  int Lq, Lk;
+  int nkv;
+  float scale_log2;  // softmax scale * log2(e)
+};
+
+template <bool P_TMEM>
+struct AttCfg {
+  static constexpr int NS = P_TMEM ? 5 : 3;  // KV ring slots
+  static constexpr int Q_OFF = 0;
+  static constexpr int P_OFF = 2 * ATT_TILE_BYTES;
+  static constexpr int KV_OFF = P_TMEM ? 2 * ATT_TILE_BYTES : 4 * ATT_TILE_BYTES;
+  static constexpr int BAR_OFF = KV_OFF + NS * ATT_TILE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256;
+};
+
+template <bool P_TMEM>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttParams p) {
+  using Cfg = AttCfg<P_TMEM>;
+  constexpr int NS = Cfg::NS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* kv_full = q_full + 1;
+  uint64_t* kv_empty = kv_full + NS;
+  uint64_t* s_full = kv_empty + NS;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* o_done = p_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * 256;
+  const int nkv = p.nkv;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < 4) {
+    setmaxnreg_dec<80>();
+    if (warp == 0 && lane == 0) {
+      // ------------------------------- TMA producer -------------------------------
+      mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+      for (int x = 0; x < 2; ++x)
+        for (int s = 0; s < 2; ++s)
+          tma_load_2d(smem + Cfg::Q_OFF + x * ATT_TILE_BYTES + s * 16384, &tmQ, q_full, head * 128 + s * 64,
+                      q0 + x * 128);
+      for (int it = 0; it < 2 * nkv; ++it) {
+        const int slot = it % NS;
+        const uint32_t ph = (it / NS) & 1;
+        mbar_wait(&kv_empty[slot], ph ^ 1);
+        mbar_arrive_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
+        const CUtensorMap* tm = (it & 1) ? &tmV : &tmK;
+        uint8_t* dst = smem + Cfg::KV_OFF + slot * ATT_TILE_BYTES;
+        const int j = it >> 1;
+        tma_load_2d(dst, tm, &kv_full[slot], head * 128, j * 128);
+        tma_load_2d(dst + 16384, tm, &kv_full[slot], head * 128 + 64, j * 128);
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ------------------------------- MMA issuer -------------------------------
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);
+      const uint32_t sQ = smem_u32(smem + Cfg::Q_OFF);
+      const uint32_t sP = smem_u32(smem + Cfg::P_OFF);
+      const uint32_t sKV = smem_u32(smem + Cfg::KV_OFF);
+      auto issue_S = [&](int X, uint32_t kbase) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+          umma_ss(tmem_base + X * 128, make_smem_desc_sw128(sQ + X * ATT_TILE_BYTES + off, 16, 1024),
+                  make_smem_desc_sw128(kbase + off, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
+        }
+      };
+      auto issue_PV = [&](int X, uint32_t vbase, bool acc) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t bdesc = make_smem_desc_sw128(vbase + kk * 2048, 16384, 1024);  // MN-major V tile
+          if (P_TMEM) {
+            umma_ts(tmem_base + 256 + X * 128, tmem_base + X * 128 + kk * 8, bdesc, idesc_pv,
+                    (acc || kk != 0) ? 1u : 0u);
+          } else {
+            const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+            umma_ss(tmem_base + 256 + X * 128, make_smem_desc_sw128(sP + X * ATT_TILE_BYTES + off, 16, 1024), bdesc,
+                    idesc_pv, (acc || kk != 0) ? 1u : 0u);
+          }
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_S(0, sKV);
+      umma_commit(&s_full[0]);
+      issue_S(1, sKV);
+      umma_commit(&s_full[1]);
+      umma_commit(&kv_empty[0]);
+      for (int j = 0; j < nkv; ++j) {
+        const int iv = 2 * j + 1, ik = 2 * j + 2;
+        const int slot_v = iv % NS, slot_k = ik % NS;
+        const bool has_next = (j + 1 < nkv);
+        mbar_wait(&kv_full[slot_v], (iv / NS) & 1);
+        if (has_next) mbar_wait(&kv_full[slot_k], (ik / NS) & 1);
+        tc_fence_after();
+        const uint32_t vbase = sKV + slot_v * ATT_TILE_BYTES;
+        const uint32_t kbase = sKV + slot_k * ATT_TILE_BYTES;
+        for (int X = 0; X < 2; ++X) {
+          mbar_wait(&p_full[X], j & 1);
+          tc_fence_after();
+          issue_PV(X, vbase, j > 0);
+          if (has_next) {
+            issue_S(X, kbase);
+            umma_commit(&s_full[X]);
+          } else {
+            umma_commit(&o_done[X]);
+          }
+        }
+        umma_commit(&kv_empty[slot_v]);
+        if (has_next) umma_commit(&kv_empty[slot_k]);
+      }
+    }
+  } else {
+    // ------------------------------- softmax / correction / epilogue -------------------------------
+    setmaxnreg_inc<216>();
+    const int X = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + X * 128;
+    const uint32_t tO = tmem_base + lane_off + 256 + X * 128;
+    const float sc = p.scale_log2;
+    float m_used = -INFINITY;
+    float l = 0.f;
+
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&s_full[X], j & 1);
+      tc_fence_after();
+      uint32_t s[4][32];
+      tmem_ld32(tS + 0, s[0]);
+      tmem_ld32(tS + 32, s[1]);
+      tmem_ld32(tS + 64, s[2]);
+      tmem_ld32(tS + 96, s[3]);
+      tmem_ld_wait();
+      const int kv_rem = p.Lk - j * 128;
+      if (kv_rem < 128) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= kv_rem) s[c][i] = 0xff800000u;  // -inf
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[c][i]));
+      const float ms = mx * sc;
+      if (j == 0) {
+        m_used = ms;
+      } else {
+        const bool need = ms > m_used + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = fmaxf(m_used, ms);
+          const float alpha = fast_exp2(m_used - m_new);
+          l *= alpha;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tO + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tO + c * 32, o);
+          }
+          tmem_st_wait();
+          m_used = m_new;
+        }
+      }
+      float lsum = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c0 = h * 64 + 2 * i;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(s[c0 >> 5][c0 & 31]), sc, -m_used));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31]), sc, -m_used));
+          lsum += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        if (P_TMEM) {
+          tmem_st32(tS + h * 32, pk);
+        } else {
+          // K-major 128B-swizzled slab h of the P tile: row r, 16-byte chunk c -> r*128 + ((c ^ (r & 7)) << 4)
+          uint8_t* slab = smem + Cfg::P_OFF + X * ATT_TILE_BYTES + h * 16384 + row_in_tile * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 w = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            *reinterpret_cast<uint4*>(slab + ((c ^ (row_in_tile & 7)) << 4)) = w;
+          }
+        }
+      }
+      l += lsum;
+      if (P_TMEM) {
+        tmem_st_wait();
+      } else {
+        fence_proxy_async_smem();
+      }
+      tc_fence_before();
+      mbar_arrive(&p_full[X]);
+    }
+
+    // epilogue: O / l -> bf16 -> global [Lq, heads*128]
+    mbar_wait(&o_done[X], 0);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    const int q_row = q0 + X * 128 + row_in_tile;
+    __nv_bfloat16* orow = p.out + static_cast<long long>(q_row) * p.ldo + head * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tO + c * 32, o);
+      tmem_ld_wait();
+      if (q_row < p.Lq) {
+        uint4* o4 = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+          o4[i] = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <bool P_TMEM>
+static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                            const AttParams& p, int heads, cudaStream_t stream) {
+  using Cfg = AttCfg<P_TMEM>;
+  auto kern = attention_kernel<P_TMEM>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      fprintf(stderr, "yume_b200: attention smem attribute failed: %s\n", cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return YB_ERR_LAUNCH;
+    }
+    attr_set = true;
+  }
+  dim3 grid((p.Lq + 255) / 256, heads);
+  kern<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  return check_launch("attention");
+}
+
+}  // namespace yb
+
+extern "C" int yb_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                            void* out, long long ldo, int Lq, int Lk, int heads, float scale, int variant,
+                            void* stream_) {
+  using namespace yb;
+  if (!q || !k || !v || !out) return YB_ERR_ARG;
+  if (Lq <= 0 || Lk <= 0 || heads <= 0) return YB_ERR_ARG;
+  if ((ldo % 8) != 0 || (reinterpret_cast<uintptr_t>(out) & 0xF)) return YB_ERR_ALIGNMENT;
+  CUtensorMap tmQ, tmK, tmV;
+  const uint64_t cols = static_cast<uint64_t>(heads) * 128;
+  int rc = make_tmap_bf16_2d(&tmQ, q, Lq, cols, ldq, 128, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmK, k, Lk, cols, ldk, 128, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmV, v, Lk, cols, ldv, 128, 64);
+  if (rc) return rc;
+  AttParams p;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.Lq = Lq;
+  p.Lk = Lk;
+  p.nkv = (Lk + 127) / 128;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (variant == 1) return launch_attention<false>(tmQ, tmK, tmV, p, heads, stream);
+  return launch_attention<true>(tmQ, tmK, tmV, p, heads, stream);
+}

@@ -1,0 +1,391 @@
+// elementwise.cu — the HBM-bound glue of the denoise path, each fused so the fp32 residual stream is read once
+// per use: LayerNorm+adaLN modulate, RMSNorm+RoPE, patchify / unpatchify gathers, timestep embedding pieces
+// and the small fp32 linears the reference keeps in fp32 (time MLP, head).
+#include "yb_host.h"
+#include "yb_ptx.cuh"
+
+namespace yb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum for blockDim.x == 256 (8 warps); `red` is 8 floats of smem. Result broadcast to all threads.
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();  // protect `red` from the previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < 8) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (+ optional affine) + adaLN modulate. One CTA (256 threads) per token row; the row lives in
+// registers (C <= 8192 -> at most 8 float4 per thread), two-pass mean/variance in fp32 like
+// nn.LayerNorm (reference: wan23/modules/model.py:140-150, 301, 310, 343-347).
+// Algorithmic bytes per token: 4*C read + 2*C (bf16) or 4*C (f32) written.
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_THREADS = 256;
+constexpr int LN_MAX_VEC = 8;
+
+template <bool OUT_F32>
+__global__ void __launch_bounds__(LN_THREADS)
+ln_modulate_kernel(const float* __restrict__ x, long long ldx, void* __restrict__ out, long long ldo,
+                   const float* __restrict__ scale, const float* __restrict__ shift, long long mod_ld,
+                   const int* __restrict__ tok_idx, const float* __restrict__ weight,
+                   const float* __restrict__ lnbias, int C, float eps) {
+  __shared__ float red[8];
+  const int row = blockIdx.x;
+  const int nvec = C >> 2;  // float4 per row
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
+  float4 v[LN_MAX_VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int idx = threadIdx.x + i * LN_THREADS;
+    if (idx < nvec) {
+      v[i] = xr[idx];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = block_sum_256(s, red) / static_cast<float>(C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int idx = threadIdx.x + i * LN_THREADS;
+    if (idx < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float var = block_sum_256(q, red) / static_cast<float>(C);
+  const float rstd = rsqrtf(var + eps);
+  const long long u = tok_idx ? tok_idx[row] : 0;
+  const float4* sc4 = scale ? reinterpret_cast<const float4*>(scale + u * mod_ld) : nullptr;
+  const float4* sh4 = shift ? reinterpret_cast<const float4*>(shift + u * mod_ld) : nullptr;
+  const float4* w4 = weight ? reinterpret_cast<const float4*>(weight) : nullptr;
+  const float4* b4 = lnbias ? reinterpret_cast<const float4*>(lnbias) : nullptr;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int idx = threadIdx.x + i * LN_THREADS;
+    if (idx < nvec) {
+      float4 y;
+      y.x = (v[i].x - mean) * rstd;
+      y.y = (v[i].y - mean) * rstd;
+      y.z = (v[i].z - mean) * rstd;
+      y.w = (v[i].w - mean) * rstd;
+      if (w4) {
+        const float4 w = __ldg(w4 + idx);
+        y.x *= w.x; y.y *= w.y; y.z *= w.z; y.w *= w.w;
+      }
+      if (b4) {
+        const float4 b = __ldg(b4 + idx);
+        y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w;
+      }
+      if (sc4) {
+        const float4 c = __ldg(sc4 + idx);
+        y.x *= (1.f + c.x); y.y *= (1.f + c.y); y.z *= (1.f + c.z); y.w *= (1.f + c.w);
+      }
+      if (sh4) {
+        const float4 h = __ldg(sh4 + idx);
+        y.x += h.x; y.y += h.y; y.z += h.z; y.w += h.w;
+      }
+      if (OUT_F32) {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + static_cast<long long>(row) * ldo)[idx] = y;
+      } else {
+        uint2 w;
+        w.x = pack_bf16x2(y.x, y.y);
+        w.y = pack_bf16x2(y.z, y.w);
+        reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + static_cast<long long>(row) * ldo)[idx] = w;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// WanRMSNorm over the full C row + weight + RoPE, in place on bf16 (reference: wan23/modules/model.py:121-137,
+// 38-118). One CTA (256 threads) per token; thread handles 8-element (16 B) chunks, i.e. 4 RoPE pairs.
+// rope table: float2 (cos, sin) [L, D/2]; pair j of each head = elements (2j, 2j+1)  (view_as_complex, :62-63).
+// Algorithmic bytes per token: 2*C read + 2*C written (+ D*4 of table).
+// ------------------------------------------------------------------------------------------------
+constexpr int RR_THREADS = 256;
+constexpr int RR_MAX_CHUNK = 4;  // C <= 8192
+
+__global__ void __launch_bounds__(RR_THREADS)
+rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ qk, long long ld, const float* __restrict__ weight,
+                    const float2* __restrict__ rope, int rope_len, int C, int D, float eps) {
+  __shared__ float red[8];
+  const int row = blockIdx.x;
+  uint4* xr = reinterpret_cast<uint4*>(qk + static_cast<long long>(row) * ld);
+  const int nchunk = C >> 3;
+  uint4 raw[RR_MAX_CHUNK];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < RR_MAX_CHUNK; ++i) {
+    const int idx = threadIdx.x + i * RR_THREADS;
+    if (idx < nchunk) {
+      raw[i] = xr[idx];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h[k]);
+        ss += f.x * f.x + f.y * f.y;
+      }
+    }
+  }
+  const float rstd = rsqrtf(block_sum_256(ss, red) / static_cast<float>(C) + eps);
+  const bool rot = (rope != nullptr) && (row < rope_len);
+  const int half = D >> 1;
+#pragma unroll
+  for (int i = 0; i < RR_MAX_CHUNK; ++i) {
+    const int idx = threadIdx.x + i * RR_THREADS;
+    if (idx < nchunk) {
+      const int col = idx << 3;
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(weight + col));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(weight + col + 4));
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const int pair0 = (col % D) >> 1;
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h[k]);
+        float a = f.x * rstd * wv[2 * k];
+        float b = f.y * rstd * wv[2 * k + 1];
+        if (rot) {
+          const float2 cs = __ldg(rope + static_cast<long long>(row) * half + pair0 + k);
+          const float ra = a * cs.x - b * cs.y;
+          const float rb = a * cs.y + b * cs.x;
+          a = ra;
+          b = rb;
+        }
+        o[k] = pack_bf16x2(a, b);
+      }
+      xr[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// patchify gather: x f32 [Cin, F, H, W] -> bf16 [L, Cin*ph*pw], token order (f, hp, wp), column order
+// (cin, i, j) = Conv3d weight.flatten(1) order for kernel (1, ph, pw). Out-of-range H/W read as zero (convpadd).
+// ------------------------------------------------------------------------------------------------
+__global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long ldo, int Cin,
+                                int F, int H, int W, int ph, int pw, int Hp, int Wp) {
+  const int Kc = Cin * ph * pw;
+  const long long total = static_cast<long long>(F) * Hp * Wp * Kc;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kc = static_cast<int>(t % Kc);
+    const long long tok = t / Kc;
+    const int wp = static_cast<int>(tok % Wp);
+    const int hp = static_cast<int>((tok / Wp) % Hp);
+    const int f = static_cast<int>(tok / (static_cast<long long>(Wp) * Hp));
+    const int j = kc % pw;
+    const int i = (kc / pw) % ph;
+    const int c = kc / (pw * ph);
+    const int h = hp * ph + i, w = wp * pw + j;
+    float v = 0.f;
+    if (h < H && w < W) v = x[((static_cast<long long>(c) * F + f) * H + h) * W + w];
+    out[tok * ldo + kc] = __float2bfloat16_rn(v);
+  }
+}
+
+// unpatchify: y f32 [L, ph*pw*Cout] -> out f32 [Cout, F, Hp*ph, Wp*pw]  ('fhwpqrc->cfphqwr', p == 1)
+__global__ void unpatchify_kernel(const float* __restrict__ y, long long ldy, float* __restrict__ out, int Cout, int F,
+                                  int Hp, int Wp, int ph, int pw) {
+  const int Ho = Hp * ph, Wo = Wp * pw;
+  const long long total = static_cast<long long>(Cout) * F * Ho * Wo;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(t % Wo);
+    const int h = static_cast<int>((t / Wo) % Ho);
+    const int f = static_cast<int>((t / (static_cast<long long>(Wo) * Ho)) % F);
+    const int c = static_cast<int>(t / (static_cast<long long>(Wo) * Ho * F));
+    const int hp = h / ph, q = h % ph, wp = w / pw, r = w % pw;
+    const long long tok = (static_cast<long long>(f) * Hp + hp) * Wp + wp;
+    out[t] = y[tok * ldy + (static_cast<long long>(q) * pw + r) * Cout + c];
+  }
+}
+
+// sinusoidal embedding in fp64 (reference: wan23/modules/model.py:14-24): out[n, :half] = cos, [half:] = sin
+__global__ void sinusoidal_kernel(const float* __restrict__ t, float* __restrict__ out, int n, int dim) {
+  const int half = dim >> 1;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * half) return;
+  const int r = idx / half, i = idx % half;
+  const double pos = static_cast<double>(t[r]);
+  const double freq = pow(10000.0, -static_cast<double>(i) / static_cast<double>(half));
+  const double a = pos * freq;
+  out[static_cast<long long>(r) * dim + i] = static_cast<float>(cos(a));
+  out[static_cast<long long>(r) * dim + half + i] = static_cast<float>(sin(a));
+}
+
+// small-M fp32 linear: one warp per output column n, all M (<= 16) rows at once. Weight-read bound.
+constexpr int LS_MAX_M = 16;
+__global__ void __launch_bounds__(256)
+linear_f32_small_kernel(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
+                        float* __restrict__ out, int M, int N, int K, int silu_in) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float acc[LS_MAX_M];
+#pragma unroll
+  for (int m = 0; m < LS_MAX_M; ++m) acc[m] = 0.f;
+  const float* wr = W + static_cast<long long>(n) * K;
+  for (int k = lane; k < K; k += 32) {
+    const float w = __ldg(wr + k);
+#pragma unroll
+    for (int m = 0; m < LS_MAX_M; ++m) {
+      if (m < M) {
+        float a = in[static_cast<long long>(m) * K + k];
+        if (silu_in) a = a / (1.f + expf(-a));
+        acc[m] = fmaf(a, w, acc[m]);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < LS_MAX_M; ++m) {
+    if (m < M) {
+      const float s = warp_sum(acc[m]);
+      if (lane == 0) out[static_cast<long long>(m) * N + n] = s + (bias ? bias[n] : 0.f);
+    }
+  }
+}
+
+// general fp32 linear (SIMT): 64x64 output tile per CTA of 256 threads, 4x4 per thread, K step 16.
+__global__ void __launch_bounds__(256)
+linear_f32_kernel(const float* __restrict__ in, long long ldi, const float* __restrict__ W,
+                  const float* __restrict__ bias, float* __restrict__ out, long long ldo, int M, int N, int K) {
+  __shared__ float sa[16][64 + 4];
+  __shared__ float sb[16][64 + 4];
+  const int tm = blockIdx.y * 64, tn = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  const int lr = threadIdx.x >> 2;        // 0..63: row within the tile
+  const int lk = (threadIdx.x & 3) << 2;  // 0,4,8,12: k offset
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (tm + lr < M && k0 + lk < K) a = *reinterpret_cast<const float4*>(in + static_cast<long long>(tm + lr) * ldi + k0 + lk);
+    if (tn + lr < N && k0 + lk < K) b = __ldg(reinterpret_cast<const float4*>(W + static_cast<long long>(tn + lr) * K + k0 + lk));
+    __syncthreads();
+    sa[lk + 0][lr] = a.x; sa[lk + 1][lr] = a.y; sa[lk + 2][lr] = a.z; sa[lk + 3][lr] = a.w;
+    sb[lk + 0][lr] = b.x; sb[lk + 1][lr] = b.y; sb[lk + 2][lr] = b.z; sb[lk + 3][lr] = b.w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&sa[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&sb[k][tx * 4]);
+      const float ar[4] = {av.x, av.y, av.z, av.w};
+      const float br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = tm + ty * 4 + i;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = tn + tx * 4 + j;
+      if (c < N) out[static_cast<long long>(r) * ldo + c] = acc[i][j] + (bias ? bias[c] : 0.f);
+    }
+  }
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+extern "C" int yb_abi_version(void) { return 1; }
+
+extern "C" int yb_ln_modulate(const void* x, long long ldx, void* out, long long ldo, int out_f32, const void* scale,
+                              const void* shift, long long mod_ld, const void* tok_idx, const void* weight,
+                              const void* lnbias, int L, int C, float eps, void* stream_) {
+  if (!x || !out || L <= 0 || C <= 0) return YB_ERR_ARG;
+  if (C % 8 != 0 || C > LN_THREADS * LN_MAX_VEC * 4) return YB_ERR_SHAPE;
+  if ((ldx % 4) || (ldo % 8) || (mod_ld % 4)) return YB_ERR_ALIGNMENT;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  if (out_f32)
+    ln_modulate_kernel<true><<<L, LN_THREADS, 0, s>>>(static_cast<const float*>(x), ldx, out, ldo,
+                                                      static_cast<const float*>(scale), static_cast<const float*>(shift),
+                                                      mod_ld, static_cast<const int*>(tok_idx),
+                                                      static_cast<const float*>(weight), static_cast<const float*>(lnbias),
+                                                      C, eps);
+  else
+    ln_modulate_kernel<false><<<L, LN_THREADS, 0, s>>>(static_cast<const float*>(x), ldx, out, ldo,
+                                                       static_cast<const float*>(scale), static_cast<const float*>(shift),
+                                                       mod_ld, static_cast<const int*>(tok_idx),
+                                                       static_cast<const float*>(weight), static_cast<const float*>(lnbias),
+                                                       C, eps);
+  return check_launch("ln_modulate");
+}
+
+extern "C" int yb_rmsnorm_rope(void* qk, long long ld, const void* weight, const void* rope, int rope_len, int L,
+                               int C, int D, float eps, void* stream_) {
+  if (!qk || !weight || L <= 0 || C <= 0 || D <= 0) return YB_ERR_ARG;
+  if (C % 8 != 0 || C > RR_THREADS * RR_MAX_CHUNK * 8 || D % 8 != 0 || C % D != 0) return YB_ERR_SHAPE;
+  if ((ld % 8) || (reinterpret_cast<uintptr_t>(qk) & 0xF)) return YB_ERR_ALIGNMENT;
+  rmsnorm_rope_kernel<<<L, RR_THREADS, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<__nv_bfloat16*>(qk), ld, static_cast<const float*>(weight), static_cast<const float2*>(rope), rope_len,
+      C, D, eps);
+  return check_launch("rmsnorm_rope");
+}
+
+extern "C" int yb_patchify(const void* x, void* out, long long ldo, int Cin, int F, int H, int W, int ph, int pw,
+                           void* stream_) {
+  if (!x || !out || Cin <= 0 || F <= 0 || H <= 0 || W <= 0 || ph <= 0 || pw <= 0) return YB_ERR_ARG;
+  const int Hp = (H + ph - 1) / ph, Wp = (W + pw - 1) / pw;
+  const long long total = static_cast<long long>(F) * Hp * Wp * Cin * ph * pw;
+  const int blocks = static_cast<int>(total / 256 + 1 < 148LL * 16 ? total / 256 + 1 : 148LL * 16);
+  patchify_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), ldo, Cin, F, H, W, ph, pw, Hp, Wp);
+  return check_launch("patchify");
+}
+
+extern "C" int yb_unpatchify(const void* y, long long ldy, void* out, int Cout, int F, int Hp, int Wp, int ph, int pw,
+                             void* stream_) {
+  if (!y || !out || Cout <= 0 || F <= 0 || Hp <= 0 || Wp <= 0 || ph <= 0 || pw <= 0) return YB_ERR_ARG;
+  const long long total = static_cast<long long>(Cout) * F * Hp * ph * Wp * pw;
+  const int blocks = static_cast<int>(total / 256 + 1 < 148LL * 16 ? total / 256 + 1 : 148LL * 16);
+  unpatchify_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const float*>(y), ldy, static_cast<float*>(out), Cout, F, Hp, Wp, ph, pw);
+  return check_launch("unpatchify");
+}
+
+extern "C" int yb_sinusoidal(const void* t, void* out, int n, int dim, void* stream_) {
+  if (!t || !out || n <= 0 || dim <= 0 || (dim & 1)) return YB_ERR_ARG;
+  const int total = n * (dim / 2);
+  sinusoidal_kernel<<<(total + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const float*>(t), static_cast<float*>(out), n, dim);
+  return check_launch("sinusoidal");
+}
+
+extern "C" int yb_linear_f32_small(const void* in, const void* W, const void* bias, void* out, int M, int N, int K,
+                                   int silu_in, void* stream_) {
+  if (!in || !W || !out || M <= 0 || N <= 0 || K <= 0) return YB_ERR_ARG;
+  if (M > LS_MAX_M) return YB_ERR_SHAPE;
+  linear_f32_small_kernel<<<(N + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const float*>(in), static_cast<const float*>(W), static_cast<const float*>(bias),
+      static_cast<float*>(out), M, N, K, silu_in);
+  return check_launch("linear_f32_small");
+}
+
+extern "C" int yb_linear_f32(const void* in, long long ldi, const void* W, const void* bias, void* out, long long ldo,
+                             int M, int N, int K, void* stream_) {
+  if (!in || !W || !out || M <= 0 || N <= 0 || K <= 0) return YB_ERR_ARG;
+  if ((K % 4) || (ldi % 4)) return YB_ERR_SHAPE;
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  linear_f32_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const float*>(in), ldi, static_cast<const float*>(W), static_cast<const float*>(bias),
+      static_cast<float*>(out), ldo, M, N, K);
+  return check_launch("linear_f32");
+}

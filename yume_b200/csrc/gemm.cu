@@ -1,0 +1,320 @@
+// gemm.cu — persistent, warp-specialised tcgen05 GEMM for sm_100a with fused epilogues.
+//
+//   out[M,N] = epilogue( A[M,K] (bf16, row-major) x B[N,K]^T (bf16, row-major, i.e. nn.Linear.weight) + bias[N] )
+//
+// This is the B200-native replacement for every nn.Linear on the reference's denoise path
+// (reference: wan23/modules/model.py:171-174 q/k/v/o, :265-267 ffn, :455-457 text_embedding;
+//  wan/modules/model.py:282-287, 358-361, 436-438), with the elementwise work the reference runs as
+// separate eager kernels folded into the epilogue:
+//   YB_EPI_BF16       out_bf16 = acc + bias                        (q/k/v projections)
+//   YB_EPI_GELU_BF16  out_bf16 = gelu_tanh(acc + bias)             (ffn.0 + nn.GELU(approximate='tanh'))
+//   YB_EPI_F32        out_f32  = acc + bias                        (patch embedding -> fp32 residual stream)
+//   YB_EPI_GATE_RES   resid_f32 += (acc + bias) * gate[tok[m], n]  (o-proj / ffn.2 + adaLN gate + residual add:
+//                                                                   model.py:304, 308, 312)
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0      TMA producer: A tile 128x64 and B tile BLOCK_Nx64 (128B-swizzled) into a 4..6-stage smem ring
+//   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16 x4 per stage, fp32
+//               accumulators in TMEM, double-buffered (2 x BLOCK_N columns) so the epilogue of tile i overlaps
+//               the main loop of tile i+1
+//   warps 2..5  epilogue: tcgen05.ld 32x32b -> registers -> fused math -> global
+#include "yb_host.h"
+#include "yb_ptx.cuh"
+
+namespace yb {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_GROUP_N = 8;   // rasterisation: n-tiles per group (keeps A and B footprints L2 resident)
+
+struct GemmParams {
+  int M, N, K;
+  const float* bias;      // [N] or null
+  void* out;              // bf16 / f32 output, or fp32 residual stream for GATE_RES
+  long long ldo;          // row stride of out (elements)
+  const float* gate;      // GATE_RES: [U, gate_ld] fp32 table (null => gate = 1)
+  long long gate_ld;      // row stride of the gate table
+  const int* tok_idx;     // GATE_RES: [M] token -> row of gate table (null => row 0)
+  int num_m_tiles, num_n_tiles;
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 512 or 256: power of two
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int num_m_tiles, int num_n_tiles, int& m_tile, int& n_tile) {
+  const int per_group = GEMM_GROUP_N * num_m_tiles;
+  const int g = tile / per_group;
+  const int r = tile - g * per_group;
+  const int n_first = g * GEMM_GROUP_N;
+  const int n_in_group = min(GEMM_GROUP_N, num_n_tiles - n_first);
+  m_tile = r / n_in_group;
+  n_tile = n_first + (r - m_tile * n_in_group);
+}
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_tile, n_tile;
+        tile_coords(tile, p.num_m_tiles, p.num_n_tiles, m_tile, n_tile);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BLOCK_K, m_tile * GEMM_BLOCK_M);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BLOCK_K, n_tile * BLOCK_N);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer -------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr>>4) field
+            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps -------------------------------
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      int m_tile, n_tile;
+      tile_coords(tile, p.num_m_tiles, p.num_n_tiles, m_tile, n_tile);
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_tile * GEMM_BLOCK_M + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+      const float* gate_row = nullptr;
+      if (EPI == YB_EPI_GATE_RES && p.gate != nullptr && row_ok) {
+        const int u = p.tok_idx ? p.tok_idx[row] : 0;
+        gate_row = p.gate + static_cast<long long>(u) * p.gate_ld;
+      }
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n_tile * BLOCK_N + c * 32;
+        if (row_ok && col0 < p.N) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 b = __ldg(b4 + i);
+              v[4 * i + 0] += b.x;
+              v[4 * i + 1] += b.y;
+              v[4 * i + 2] += b.z;
+              v[4 * i + 3] += b.w;
+            }
+          }
+          if (EPI == YB_EPI_BF16 || EPI == YB_EPI_GELU_BF16) {
+            if (EPI == YB_EPI_GELU_BF16) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+            }
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+            uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 w;
+              w.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+              w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+              w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+              w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+              o4[i] = w;
+            }
+          } else if (EPI == YB_EPI_F32) {
+            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
+                                                   static_cast<long long>(row) * p.ldo + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {  // YB_EPI_GATE_RES
+            float4* x4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
+                                                   static_cast<long long>(row) * p.ldo + col0);
+            if (gate_row) {
+              const float4* g4 = reinterpret_cast<const float4*>(gate_row + col0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 g = __ldg(g4 + i);
+                float4 x = x4[i];
+                x.x += v[4 * i + 0] * g.x;
+                x.y += v[4 * i + 1] * g.y;
+                x.z += v[4 * i + 2] * g.z;
+                x.w += v[4 * i + 3] * g.w;
+                x4[i] = x;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 x = x4[i];
+                x.x += v[4 * i + 0];
+                x.y += v[4 * i + 1];
+                x.z += v[4 * i + 2];
+                x.w += v[4 * i + 3];
+                x4[i] = x;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BLOCK_N, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  auto kern = gemm_kernel<BLOCK_N, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      fprintf(stderr, "yume_b200: gemm smem attribute failed: %s\n", cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return YB_ERR_LAUNCH;
+    }
+    attr_set = true;
+  }
+  p.num_m_tiles = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  return check_launch("gemm");
+}
+
+}  // namespace yb
+
+extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
+  using namespace yb;
+  if (!a || !a->A || !a->B || !a->out) return YB_ERR_ARG;
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return YB_ERR_ARG;
+  if (a->N % 32 != 0 || a->K % 8 != 0) return YB_ERR_SHAPE;
+  if (a->epilogue < 0 || a->epilogue > YB_EPI_GATE_RES) return YB_ERR_ARG;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int block_n = (a->block_n == 128 || a->block_n == 256) ? a->block_n : ((a->N % 256 == 0 || a->N > 1024) ? 256 : 128);
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_2d(&tmA, a->A, a->M, a->K, a->lda, GEMM_BLOCK_M, GEMM_BLOCK_K);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, a->B, a->N, a->K, a->ldb, block_n, GEMM_BLOCK_K);
+  if (rc) return rc;
+  GemmParams p;
+  p.M = a->M;
+  p.N = a->N;
+  p.K = a->K;
+  p.bias = static_cast<const float*>(a->bias);
+  p.out = a->out;
+  p.ldo = a->ldo;
+  p.gate = static_cast<const float*>(a->gate);
+  p.gate_ld = a->gate_ld;
+  p.tok_idx = static_cast<const int*>(a->tok_idx);
+#define YB_DISPATCH(BN)                                                                  \
+  switch (a->epilogue) {                                                                 \
+    case YB_EPI_BF16: return launch_gemm<BN, YB_EPI_BF16>(tmA, tmB, p, stream);           \
+    case YB_EPI_GELU_BF16: return launch_gemm<BN, YB_EPI_GELU_BF16>(tmA, tmB, p, stream); \
+    case YB_EPI_F32: return launch_gemm<BN, YB_EPI_F32>(tmA, tmB, p, stream);             \
+    default: return launch_gemm<BN, YB_EPI_GATE_RES>(tmA, tmB, p, stream);                \
+  }
+  if (block_n == 256) {
+    YB_DISPATCH(256)
+  } else {
+    YB_DISPATCH(128)
+  }
+#undef YB_DISPATCH
+}

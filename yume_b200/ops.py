@@ -1,0 +1,210 @@
+"""Tensor-level wrappers over the C ABI. torch is used only for device memory and the current stream;
+every function requires CUDA tensors and calls straight into libyume_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (YB_EPI_BF16, YB_EPI_F32, YB_EPI_GATE_RES, YB_EPI_GELU_BF16, GemmArgs, YumeB200Error, check)
+
+__all__ = [
+    "gemm", "ln_modulate", "rmsnorm_rope", "attention", "patchify", "unpatchify", "sinusoidal",
+    "linear_f32_small", "linear_f32", "umma_probe", "launch_count", "reset_launch_count",
+    "YB_EPI_BF16", "YB_EPI_GELU_BF16", "YB_EPI_F32", "YB_EPI_GATE_RES",
+]
+
+_launches = 0
+
+
+def launch_count() -> int:
+    """Number of yume_b200 kernels launched since the last reset (bench.py reports it as gpu_launches)."""
+    return _launches
+
+
+def reset_launch_count() -> None:
+    global _launches
+    _launches = 0
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise YumeB200Error(f"{name} must be a CUDA tensor (yume_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise YumeB200Error(f"{name} must be {dtype}, got {t.dtype}")
+    if t.stride(-1) != 1:
+        raise YumeB200Error(f"{name} must be contiguous in its last dimension")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, epilogue: int,
+         gate: Optional[torch.Tensor] = None, tok_idx: Optional[torch.Tensor] = None, block_n: int = 0) -> torch.Tensor:
+    """out = epi(a[M,K] @ w[N,K]^T + bias). a, w bf16 (2-D, row stride arbitrary); see include/yume_b200.h."""
+    global _launches
+    _need(a, torch.bfloat16, "a")
+    _need(w, torch.bfloat16, "w")
+    M, K = a.shape
+    N, K2 = w.shape
+    if K2 != K:
+        raise YumeB200Error(f"gemm K mismatch: {K} vs {K2}")
+    want = torch.bfloat16 if epilogue in (YB_EPI_BF16, YB_EPI_GELU_BF16) else torch.float32
+    _need(out, want, "out")
+    if out.shape[0] != M or out.shape[1] != N:
+        raise YumeB200Error(f"gemm out shape {tuple(out.shape)} != ({M}, {N})")
+    if bias is not None:
+        _need(bias, torch.float32, "bias")
+    if gate is not None:
+        _need(gate, torch.float32, "gate")
+    if tok_idx is not None:
+        _need(tok_idx, torch.int32, "tok_idx")
+    args = GemmArgs(
+        A=a.data_ptr(), B=w.data_ptr(), bias=_ptr(bias), out=out.data_ptr(), gate=_ptr(gate), tok_idx=_ptr(tok_idx),
+        lda=a.stride(0), ldb=w.stride(0), ldo=out.stride(0), gate_ld=(gate.stride(0) if gate is not None else 0),
+        M=M, N=N, K=K, epilogue=epilogue, block_n=block_n)
+    check(_lib.load().yb_gemm_bf16(C.byref(args), _stream()), "yb_gemm_bf16")
+    _launches += 1
+    return out
+
+
+def ln_modulate(x: torch.Tensor, out: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
+                tok_idx: Optional[torch.Tensor] = None, weight: Optional[torch.Tensor] = None,
+                bias: Optional[torch.Tensor] = None, eps: float = 1e-6) -> torch.Tensor:
+    """out = LN(x) [* weight + bias] [* (1 + scale[tok]) + shift[tok]]; x f32 [L, C]; out bf16 or f32 [L, C]."""
+    global _launches
+    _need(x, torch.float32, "x")
+    L, Cdim = x.shape
+    out_f32 = 1 if out.dtype == torch.float32 else 0
+    _need(out, torch.float32 if out_f32 else torch.bfloat16, "out")
+    mod_ld = 0
+    for name, t in (("scale", scale), ("shift", shift)):
+        if t is not None:
+            _need(t, torch.float32, name)
+            mod_ld = t.stride(0) if t.dim() == 2 else 0
+    if scale is not None and shift is not None and scale.dim() == 2 and scale.stride(0) != shift.stride(0):
+        raise YumeB200Error("scale and shift must share their row stride")
+    check(_lib.load().yb_ln_modulate(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), out_f32, _ptr(scale),
+                                     _ptr(shift), mod_ld, _ptr(tok_idx), _ptr(weight), _ptr(bias), L, Cdim, eps,
+                                     _stream()), "yb_ln_modulate")
+    _launches += 1
+    return out
+
+
+def rmsnorm_rope(qk: torch.Tensor, weight: torch.Tensor, rope: Optional[torch.Tensor], head_dim: int,
+                 eps: float = 1e-6, rope_len: Optional[int] = None) -> torch.Tensor:
+    """In place on bf16 rows qk [L, C] (row stride arbitrary): RMSNorm over C, * weight, RoPE with rope f32 [L, D/2, 2]."""
+    global _launches
+    _need(qk, torch.bfloat16, "qk")
+    _need(weight, torch.float32, "weight")
+    L, Cdim = qk.shape
+    if rope is not None:
+        _need(rope, torch.float32, "rope")
+        if not rope.is_contiguous() or rope.shape[-1] != 2 or rope.shape[-2] != head_dim // 2:
+            raise YumeB200Error("rope must be contiguous f32 [L, D/2, 2]")
+        if rope_len is None:
+            rope_len = rope.shape[0]
+    check(_lib.load().yb_rmsnorm_rope(qk.data_ptr(), qk.stride(0), weight.data_ptr(), _ptr(rope), rope_len or 0, L,
+                                      Cdim, head_dim, eps, _stream()), "yb_rmsnorm_rope")
+    _launches += 1
+    return qk
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, heads: int,
+              scale: Optional[float] = None, variant: int = 0) -> torch.Tensor:
+    """softmax(q k^T * scale) v, non-causal. q [Lq, heads*128], k/v [Lk, heads*128] bf16 (row strides arbitrary)."""
+    global _launches
+    for n, t in (("q", q), ("k", k), ("v", v), ("out", out)):
+        _need(t, torch.bfloat16, n)
+    Lq, Lk = q.shape[0], k.shape[0]
+    if q.shape[1] != heads * 128 or k.shape[1] != heads * 128 or v.shape[1] != heads * 128:
+        raise YumeB200Error("attention supports head_dim 128 only")
+    if scale is None:
+        scale = 1.0 / math.sqrt(128.0)
+    check(_lib.load().yb_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                   out.data_ptr(), out.stride(0), Lq, Lk, heads, scale, variant, _stream()),
+          "yb_attention")
+    _launches += 1
+    return out
+
+
+def patchify(x: torch.Tensor, out: torch.Tensor, ph: int, pw: int) -> torch.Tensor:
+    """x f32 [Cin, F, H, W] (contiguous) -> out bf16 [F*ceil(H/ph)*ceil(W/pw), >= Cin*ph*pw]."""
+    global _launches
+    _need(x, torch.float32, "x")
+    _need(out, torch.bfloat16, "out")
+    if not x.is_contiguous():
+        raise YumeB200Error("patchify input must be contiguous")
+    Cin, F, H, W = x.shape
+    check(_lib.load().yb_patchify(x.data_ptr(), out.data_ptr(), out.stride(0), Cin, F, H, W, ph, pw, _stream()),
+          "yb_patchify")
+    _launches += 1
+    return out
+
+
+def unpatchify(y: torch.Tensor, out: torch.Tensor, F: int, Hp: int, Wp: int, ph: int, pw: int) -> torch.Tensor:
+    """y f32 [L, ph*pw*Cout] -> out f32 [Cout, F, Hp*ph, Wp*pw] (contiguous)."""
+    global _launches
+    _need(y, torch.float32, "y")
+    _need(out, torch.float32, "out")
+    Cout = out.shape[0]
+    check(_lib.load().yb_unpatchify(y.data_ptr(), y.stride(0), out.data_ptr(), Cout, F, Hp, Wp, ph, pw, _stream()),
+          "yb_unpatchify")
+    _launches += 1
+    return out
+
+
+def sinusoidal(t: torch.Tensor, dim: int) -> torch.Tensor:
+    global _launches
+    _need(t, torch.float32, "t")
+    out = torch.empty(t.numel(), dim, device=t.device, dtype=torch.float32)
+    check(_lib.load().yb_sinusoidal(t.data_ptr(), out.data_ptr(), t.numel(), dim, _stream()), "yb_sinusoidal")
+    _launches += 1
+    return out
+
+
+def linear_f32_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], silu_in: bool = False) -> torch.Tensor:
+    global _launches
+    _need(x, torch.float32, "x")
+    _need(w, torch.float32, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    if not (x.is_contiguous() and w.is_contiguous()):
+        raise YumeB200Error("linear_f32_small needs contiguous operands")
+    out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    check(_lib.load().yb_linear_f32_small(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K,
+                                          1 if silu_in else 0, _stream()), "yb_linear_f32_small")
+    _launches += 1
+    return out
+
+
+def linear_f32(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+    global _launches
+    _need(x, torch.float32, "x")
+    _need(w, torch.float32, "w")
+    _need(out, torch.float32, "out")
+    M, K = x.shape
+    N = w.shape[0]
+    if not w.is_contiguous():
+        raise YumeB200Error("linear_f32 weight must be contiguous")
+    check(_lib.load().yb_linear_f32(x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(bias), out.data_ptr(),
+                                    out.stride(0), M, N, K, _stream()), "yb_linear_f32")
+    _launches += 1
+    return out
+
+
+def umma_probe(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
+    """tcgen05 self-test (tests only). a, b bf16 [128,128] contiguous -> f32 [128,128]."""
+    _need(a, torch.bfloat16, "a")
+    _need(b, torch.bfloat16, "b")
+    d = torch.empty(128, 128, device=a.device, dtype=torch.float32)
+    check(_lib.load().yb_umma_probe(a.data_ptr(), b.data_ptr(), d.data_ptr(), mode, _stream()), "yb_umma_probe")
+    return d
