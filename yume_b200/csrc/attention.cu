@@ -172,7 +172,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else {
     // ------------------------------- softmax / correction / epilogue -------------------------------
-    setmaxnreg_inc<216>();
+    setmaxnreg_inc<208>();  // 128*80 + 256*208 = 63488 <= 384*168 (the CTA's register pool)
     const int X = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int row_in_tile = quad * 32 + lane;
