@@ -144,7 +144,9 @@ def main():
     xb = torch.randn(1, Lb, C, generator=g)
     eb = 0.5 * torch.randn(1, Lb, 6, C, generator=g)
     cb = torch.randn(1, cfg["text_len"], C, generator=g)
-    freqs = torch.cat(list(model.freqs.split([22, 21, 21], dim=1)), dim=1) if False else model.freqs
+    d = cfg["dim"] // cfg["num_heads"]  # the [1024, d/2] grid table of model.py:475-480 (model.freqs was overwritten
+    freqs = torch.cat([mod23.rope_params(1024, d - 4 * (d // 6)), mod23.rope_params(1024, 2 * (d // 6)),  # by forward)
+                       mod23.rope_params(1024, 2 * (d // 6))], dim=1)
     yb = model.blocks[0](xb, eb, torch.tensor([Lb]), torch.tensor([[2, 8, 8]]), freqs, cb, None, flag=False)
     gold["block"] = dict(seed=7, L=Lb, grid=(2, 8, 8), out=yb.clone())
     torch.save(gold, out_dir / "wan23_tiny.pt")
