@@ -39,6 +39,7 @@ int yb_abi_version(void);
 #define YB_EPI_GELU_BF16 1 /* out bf16 = gelu_tanh(acc + bias)            (nn.GELU(approximate='tanh')) */
 #define YB_EPI_F32 2       /* out f32  = acc + bias */
 #define YB_EPI_GATE_RES 3  /* out f32 += (acc + bias) * gate[tok_idx[m]][n]   (model.py:304,308,312) */
+#define YB_EPI_GELU_ERF_BF16 4 /* out bf16 = gelu_erf(acc + bias)         (nn.GELU() in MLPProj, wan/modules/model.py:536) */
 
 typedef struct yb_gemm_args {
   const void* A;   /* bf16 [M, K], row stride lda */
@@ -86,20 +87,27 @@ int yb_rmsnorm_rope(void* qk, long long ld, const void* weight, const void* rope
  * Constraints: head_dim == 128; strides % 8 == 0; pointers 16-byte aligned.
  * ------------------------------------------------------------------------------------------- */
 int yb_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
-                 long long ldo, int Lq, int Lk, int heads, float scale, int variant, void* stream);
+                 long long ldo, int Lq, int Lk, int heads, float scale, int flags, void* stream);
+#define YB_ATT_P_SMEM 1     /* flags bit 0: stage P through shared memory instead of TMEM (debug variant) */
+#define YB_ATT_ACCUMULATE 2 /* flags bit 1: out += result (WanI2VCrossAttention sums the text and image branches,
+                               wan/modules/model.py:380-387) */
 
 /* ---------------------------------------------------------------------------------------------
- * patchify gather (bit-exact index op): x f32 [Cin, F, H, W] -> bf16 [F*(Hp)*(Wp), Cin*ph*pw] rows in
+ * patchify gather (bit-exact index op): x f32 [Cin, F, H, W] (element strides sc, sf, sh, sw) -> bf16 [F*(Hp)*(Wp), Cin*ph*pw] rows in
  * (f, h, w) token order, columns in Conv3d weight order (cin, ph, pw); H, W zero-padded up to a multiple
  * of the patch (convpadd, wan23/modules/model.py:918-931). Replaces the data movement of
  * `patch_embedding(u).flatten(2).transpose(1, 2)` (:750-753); the contraction itself is yb_gemm_bf16.
  * ------------------------------------------------------------------------------------------- */
-int yb_patchify(const void* x, void* out, long long ldo, int Cin, int F, int H, int W, int ph, int pw, void* stream);
+int yb_patchify(const void* x, long long sc, long long sf, long long sh, long long sw, void* out, long long ldo,
+                int Cin, int F, int H, int W, int ph, int pw, void* stream);
 
 /* unpatchify (bit-exact): y f32 [L, ph*pw*Cout] (row stride ldy) -> out f32 [Cout, F, Hp*ph, Wp*pw]
  * (einsum 'fhwpqrc->cfphqwr', wan23/modules/model.py:867-890; patch_t == 1). */
 int yb_unpatchify(const void* y, long long ldy, void* out, int Cout, int F, int Hp, int Wp, int ph, int pw,
                   void* stream);
+
+/* out[r1][r2][:] = a[r1][:] + b[r2][:] (f32): per-block adaLN tables `modulation + e0` (wan23/modules/model.py:296,344). */
+int yb_bcast_add(const void* a, const void* b, void* out, int R1, int R2, int n, void* stream);
 
 /* Sinusoidal timestep embedding in fp64 -> f32 [n, dim] = [cos | sin] (wan23/modules/model.py:14-24). t: f32 [n]. */
 int yb_sinusoidal(const void* t, void* out, int n, int dim, void* stream);

@@ -7,7 +7,8 @@ from pathlib import Path
 
 _LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libyume_b200.so"
 
-YB_EPI_BF16, YB_EPI_GELU_BF16, YB_EPI_F32, YB_EPI_GATE_RES = 0, 1, 2, 3
+YB_EPI_BF16, YB_EPI_GELU_BF16, YB_EPI_F32, YB_EPI_GATE_RES, YB_EPI_GELU_ERF_BF16 = 0, 1, 2, 3, 4
+YB_ATT_P_SMEM, YB_ATT_ACCUMULATE = 1, 2
 
 _ERRORS = {
     -1: "YB_ERR_ARG (null pointer / bad enum / non-positive size)",
@@ -42,7 +43,8 @@ SIGNATURES = {
     "yb_ln_modulate": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp, _ll, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "yb_rmsnorm_rope": (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "yb_attention": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _f, _i, _vp]),
-    "yb_patchify": (_i, [_vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
+    "yb_patchify": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
+    "yb_bcast_add": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "yb_unpatchify": (_i, [_vp, _ll, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "yb_sinusoidal": (_i, [_vp, _vp, _i, _i, _vp]),
     "yb_linear_f32_small": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

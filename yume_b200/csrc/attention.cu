@@ -29,6 +29,7 @@ struct AttParams {
   long long ldo;
   int Lq, Lk;
   int nkv;
+  int accumulate;    // out += result (sum of two attention branches)
   float scale_log2;  // softmax scale * log2(e)
 };
 
@@ -274,6 +275,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tmem_ld_wait();
       if (q_row < p.Lq) {
         uint4* o4 = reinterpret_cast<uint4*>(orow + c * 32);
+        if (p.accumulate) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 prev = o4[i];
+            const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&prev);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __bfloat1622float2(ph[k]);
+              o[8 * i + 2 * k] = __float_as_uint(__uint_as_float(o[8 * i + 2 * k]) + f.x * l);
+              o[8 * i + 2 * k + 1] = __float_as_uint(__uint_as_float(o[8 * i + 2 * k + 1]) + f.y * l);
+            }
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 w;
@@ -318,7 +332,7 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, cons
 }  // namespace yb
 
 extern "C" int yb_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
-                            void* out, long long ldo, int Lq, int Lk, int heads, float scale, int variant,
+                            void* out, long long ldo, int Lq, int Lk, int heads, float scale, int flags,
                             void* stream_) {
   using namespace yb;
   if (!q || !k || !v || !out) return YB_ERR_ARG;
@@ -338,8 +352,9 @@ extern "C" int yb_attention(const void* q, long long ldq, const void* k, long lo
   p.Lq = Lq;
   p.Lk = Lk;
   p.nkv = (Lk + 127) / 128;
+  p.accumulate = (flags & YB_ATT_ACCUMULATE) ? 1 : 0;
   p.scale_log2 = scale * 1.4426950408889634f;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (variant == 1) return launch_attention<false>(tmQ, tmK, tmV, p, heads, stream);
+  if (flags & YB_ATT_P_SMEM) return launch_attention<false>(tmQ, tmK, tmV, p, heads, stream);
   return launch_attention<true>(tmQ, tmK, tmV, p, heads, stream);
 }

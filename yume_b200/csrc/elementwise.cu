@@ -175,8 +175,9 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ qk, long long ld, const float* _
 // patchify gather: x f32 [Cin, F, H, W] -> bf16 [L, Cin*ph*pw], token order (f, hp, wp), column order
 // (cin, i, j) = Conv3d weight.flatten(1) order for kernel (1, ph, pw). Out-of-range H/W read as zero (convpadd).
 // ------------------------------------------------------------------------------------------------
-__global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long ldo, int Cin,
-                                int F, int H, int W, int ph, int pw, int Hp, int Wp) {
+__global__ void patchify_kernel(const float* __restrict__ x, long long sc, long long sf, long long sh, long long sw,
+                                __nv_bfloat16* __restrict__ out, long long ldo, int Cin, int F, int H, int W, int ph,
+                                int pw, int Hp, int Wp) {
   const int Kc = Cin * ph * pw;
   const long long total = static_cast<long long>(F) * Hp * Wp * Kc;
   for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
@@ -191,7 +192,7 @@ __global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __re
     const int c = kc / (pw * ph);
     const int h = hp * ph + i, w = wp * pw + j;
     float v = 0.f;
-    if (h < H && w < W) v = x[((static_cast<long long>(c) * F + f) * H + h) * W + w];
+    if (h < H && w < W) v = x[c * sc + f * sf + h * sh + w * sw];
     out[tok * ldo + kc] = __float2bfloat16_rn(v);
   }
 }
@@ -301,9 +302,31 @@ linear_f32_kernel(const float* __restrict__ in, long long ldi, const float* __re
   }
 }
 
+// out[r1][r2][:] = a[r1][:] + b[r2][:]  (per-block modulation tables: modulation[i] + e0[u], model.py:296)
+__global__ void bcast_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                 int R1, int R2, int n) {
+  const long long total = static_cast<long long>(R1) * R2 * n;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(t % n);
+    const int r2 = static_cast<int>((t / n) % R2);
+    const int r1 = static_cast<int>(t / (static_cast<long long>(n) * R2));
+    out[t] = a[static_cast<long long>(r1) * n + c] + b[static_cast<long long>(r2) * n + c];
+  }
+}
+
 }  // namespace yb
 
 using namespace yb;
+
+extern "C" int yb_bcast_add(const void* a, const void* b, void* out, int R1, int R2, int n, void* stream_) {
+  if (!a || !b || !out || R1 <= 0 || R2 <= 0 || n <= 0) return YB_ERR_ARG;
+  const long long total = static_cast<long long>(R1) * R2 * n;
+  const int blocks = static_cast<int>(total / 256 + 1 < 148LL * 8 ? total / 256 + 1 : 148LL * 8);
+  bcast_add_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const float*>(a), static_cast<const float*>(b), static_cast<float*>(out), R1, R2, n);
+  return check_launch("bcast_add");
+}
 
 extern "C" int yb_abi_version(void) { return 1; }
 
@@ -340,14 +363,15 @@ extern "C" int yb_rmsnorm_rope(void* qk, long long ld, const void* weight, const
   return check_launch("rmsnorm_rope");
 }
 
-extern "C" int yb_patchify(const void* x, void* out, long long ldo, int Cin, int F, int H, int W, int ph, int pw,
-                           void* stream_) {
+extern "C" int yb_patchify(const void* x, long long sc, long long sf, long long sh, long long sw, void* out,
+                           long long ldo, int Cin, int F, int H, int W, int ph, int pw, void* stream_) {
   if (!x || !out || Cin <= 0 || F <= 0 || H <= 0 || W <= 0 || ph <= 0 || pw <= 0) return YB_ERR_ARG;
   const int Hp = (H + ph - 1) / ph, Wp = (W + pw - 1) / pw;
   const long long total = static_cast<long long>(F) * Hp * Wp * Cin * ph * pw;
   const int blocks = static_cast<int>(total / 256 + 1 < 148LL * 16 ? total / 256 + 1 : 148LL * 16);
   patchify_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), ldo, Cin, F, H, W, ph, pw, Hp, Wp);
+      static_cast<const float*>(x), sc, sf, sh, sw, static_cast<__nv_bfloat16*>(out), ldo, Cin, F, H, W, ph, pw, Hp,
+      Wp);
   return check_launch("patchify");
 }
 

@@ -9,6 +9,7 @@
 //   YB_EPI_BF16       out_bf16 = acc + bias                        (q/k/v projections)
 //   YB_EPI_GELU_BF16  out_bf16 = gelu_tanh(acc + bias)             (ffn.0 + nn.GELU(approximate='tanh'))
 //   YB_EPI_F32        out_f32  = acc + bias                        (patch embedding -> fp32 residual stream)
+//   YB_EPI_GELU_ERF_BF16 out_bf16 = gelu_erf(acc + bias)         (MLPProj nn.GELU(), wan/modules/model.py:536)
 //   YB_EPI_GATE_RES   resid_f32 += (acc + bias) * gate[tok[m], n]  (o-proj / ffn.2 + adaLN gate + residual add:
 //                                                                   model.py:304, 308, 312)
 //
@@ -194,10 +195,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               v[4 * i + 3] += b.w;
             }
           }
-          if (EPI == YB_EPI_BF16 || EPI == YB_EPI_GELU_BF16) {
+          if (EPI == YB_EPI_BF16 || EPI == YB_EPI_GELU_BF16 || EPI == YB_EPI_GELU_ERF_BF16) {
             if (EPI == YB_EPI_GELU_BF16) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+            }
+            if (EPI == YB_EPI_GELU_ERF_BF16) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.7071067811865476f));
             }
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
             uint4* o4 = reinterpret_cast<uint4*>(o);
@@ -286,7 +291,8 @@ extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
   if (!a || !a->A || !a->B || !a->out) return YB_ERR_ARG;
   if (a->M <= 0 || a->N <= 0 || a->K <= 0) return YB_ERR_ARG;
   if (a->N % 32 != 0 || a->K % 8 != 0) return YB_ERR_SHAPE;
-  if (a->epilogue < 0 || a->epilogue > YB_EPI_GATE_RES) return YB_ERR_ARG;
+  if (a->epilogue < 0 || a->epilogue > YB_EPI_GELU_ERF_BF16) return YB_ERR_ARG;
+  if ((a->lda % 8) || (a->ldb % 8) || (a->ldo % 8) || (reinterpret_cast<uintptr_t>(a->out) & 0xF)) return YB_ERR_ALIGNMENT;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int block_n = (a->block_n == 128 || a->block_n == 256) ? a->block_n : ((a->N % 256 == 0 || a->N > 1024) ? 256 : 128);
   CUtensorMap tmA, tmB;
@@ -309,6 +315,7 @@ extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
     case YB_EPI_BF16: return launch_gemm<BN, YB_EPI_BF16>(tmA, tmB, p, stream);           \
     case YB_EPI_GELU_BF16: return launch_gemm<BN, YB_EPI_GELU_BF16>(tmA, tmB, p, stream); \
     case YB_EPI_F32: return launch_gemm<BN, YB_EPI_F32>(tmA, tmB, p, stream);             \
+    case YB_EPI_GELU_ERF_BF16: return launch_gemm<BN, YB_EPI_GELU_ERF_BF16>(tmA, tmB, p, stream); \
     default: return launch_gemm<BN, YB_EPI_GATE_RES>(tmA, tmB, p, stream);                \
   }
   if (block_n == 256) {

@@ -1,0 +1,459 @@
+"""WanDiT — the B200 denoise-forward engine behind the reference's `WanModel.forward`.
+
+One engine instance owns the re-packed weights of one WanModel (5B `wan23` tree or 14B `wan` tree) and runs the
+whole forward through libyume_b200.so. Host code here is orchestration only: shapes, the FramePack segment plan,
+RoPE position tables, workspace reuse. Every FLOP and every byte of activation traffic happens in the CUDA
+kernels (yume_b200/csrc); there is no PyTorch compute fallback.
+
+Reference semantics followed (file:line in /root/reference):
+  forward 5B   wan23/modules/model.py:547-865      forward 14B  wan/modules/model.py:723-1013
+  block        wan23/modules/model.py:272-316      block 14B    wan/modules/model.py:444-496
+  FramePack    wan23/modules/model.py:588-741      (14B: wan/modules/model.py:768-910)
+Numerics: bf16 GEMM/attention inputs with fp32 accumulation, fp32 residual stream / modulation / norms — the
+regime the reference runs under torch.autocast(bf16).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from ._lib import YumeB200Error
+
+Tensor = torch.Tensor
+_BF16 = torch.bfloat16
+_F32 = torch.float32
+
+
+def _pad_cols(w: Tensor, mult: int) -> Tensor:
+    """Zero-pad the K (last) dimension of a [N, K] matrix to a multiple of `mult` (TMA needs 16-byte row pitch)."""
+    k = w.shape[1]
+    kp = (k + mult - 1) // mult * mult
+    if kp == k:
+        return w.contiguous()
+    out = w.new_zeros(w.shape[0], kp)
+    out[:, :k] = w
+    return out
+
+
+def _pad_rows(w: Tensor, mult: int) -> Tensor:
+    n = w.shape[0]
+    np_ = (n + mult - 1) // mult * mult
+    if np_ == n:
+        return w.contiguous()
+    out = w.new_zeros(np_, *w.shape[1:])
+    out[:n] = w
+    return out
+
+
+@dataclass
+class _Segment:
+    frames: slice      # frames of the history tensor
+    name: str          # embedder (state-dict prefix)
+    patch: int         # spatial patch (= 2 * compression)
+    pre_2x_f: bool     # apply patch_embedding_2x_f first (deepest history level)
+
+
+def framepack_plan(hist: int, branch_hist: int) -> List[_Segment]:
+    """Which history frames go through which patch embedder, in token order.
+
+    Restates the branch ladder of wan23/modules/model.py:599-718 (identical in wan/modules/model.py:779-898):
+    the newest 3 history frames keep full resolution, the next 2 are embedded with 4x4 patches, the next 16 with
+    8x8, then 64 with 16x16, then 256 with 32x32, the oldest with 2x_f + 32x32; the very first frame is always kept
+    (full resolution up to 86 history frames, 4x4 patches beyond). `branch_hist` is the quantity the reference's
+    conditions test (f_num - latent_frame_zero for 5B, f_num - 9 for 14B)."""
+    H = hist
+    levels = [("patch_embedding", 2), ("patch_embedding_2x", 4), ("patch_embedding_4x", 8),
+              ("patch_embedding_8x", 16), ("patch_embedding_16x", 32)]
+    if branch_hist <= 6:
+        depth = 1
+    elif branch_hist <= 22:
+        depth = 2
+    elif branch_hist <= 86:
+        depth = 3
+    elif branch_hist <= 342:
+        depth = 4
+    elif branch_hist <= 1366:
+        depth = 5
+    else:
+        raise UnboundLocalError(
+            "freqs_i: the reference has no FramePack branch for more than 1366 history latent frames")
+    segs: List[_Segment] = []
+    first_level = 0 if depth <= 3 else 1                      # frame 0: 1x up to 86 frames of history, else 2x
+    segs.append(_Segment(slice(0, 1), *levels[first_level], False))
+    if depth == 1:
+        mid = slice(H - 1, H) if H - 2 <= 0 else slice(1, H - 1)
+        segs.append(_Segment(mid, *levels[1], False))
+        segs.append(_Segment(slice(H - 1, H), *levels[0], False))
+        return segs
+    # tail windows, newest last: [-3:] 1x, [-5:-3] 2x, [-21:-5] 4x, [-85:-21] 8x, [-341:-85] 16x
+    bounds = [3, 5, 21, 85, 341]
+    deep = min(depth, 4)                                      # level of the "everything older" segment
+    cut = bounds[depth - 1]                                   # frames kept in the finer tail windows
+    mid = slice(H - cut, H - cut + 1) if H - (cut + 1) <= 0 else slice(1, H - cut)
+    segs.append(_Segment(mid, *levels[deep], depth == 5))
+    for lvl in range(depth - 1, 0, -1):                       # coarser -> finer windows
+        lo, hi = bounds[lvl], bounds[lvl - 1]
+        segs.append(_Segment(slice(H - lo, H - hi), *levels[min(lvl, 4)], False))
+    segs.append(_Segment(slice(H - 3, H), *levels[0], False))
+    return segs
+
+
+class WanDiT:
+    """B200 engine for one WanModel. `variant` is '5b' (wan23 tree) or '14b' (wan tree)."""
+
+    def __init__(self, state_dict: Dict[str, Tensor], variant: str, dim: int, ffn_dim: int, num_heads: int,
+                 num_layers: int, in_dim: int, out_dim: int, text_len: int = 512, freq_dim: int = 256,
+                 patch_size: Sequence[int] = (1, 2, 2), eps: float = 1e-6, device: str | torch.device = "cuda"):
+        if variant not in ("5b", "14b"):
+            raise YumeB200Error("variant must be '5b' or '14b'")
+        if tuple(patch_size) != (1, 2, 2):
+            raise YumeB200Error("only patch_size (1, 2, 2) is supported (both Yume models use it)")
+        if dim % num_heads or dim // num_heads != 128:
+            raise YumeB200Error("the attention kernel is built for head_dim 128 (both Yume models)")
+        self.variant, self.dim, self.ffn_dim, self.heads, self.layers = variant, dim, ffn_dim, num_heads, num_layers
+        self.in_dim, self.out_dim, self.text_len, self.freq_dim, self.eps = in_dim, out_dim, text_len, freq_dim, eps
+        self.device = torch.device(device)
+        self.head_dim = 128
+        self._ws: Dict[Tuple, Tensor] = {}
+        self._rope_cache: Dict[Tuple, Tensor] = {}
+        self._repack(state_dict)
+
+    # ------------------------------------------------------------------------------------------------------
+    # weights
+    # ------------------------------------------------------------------------------------------------------
+    def _repack(self, sd: Dict[str, Tensor]) -> None:
+        dev, C = self.device, self.dim
+
+        def w16(name):
+            return sd[name].detach().to(device=dev, dtype=_BF16).contiguous()
+
+        def f32(name):
+            return sd[name].detach().to(device=dev, dtype=_F32).contiguous()
+
+        def cat16(names):
+            return torch.cat([sd[n].detach().to(device=dev, dtype=_BF16) for n in names], dim=0).contiguous()
+
+        def cat32(names):
+            return torch.cat([sd[n].detach().to(device=dev, dtype=_F32) for n in names], dim=0).contiguous()
+
+        self.embed: Dict[str, Tuple[Tensor, Tensor]] = {}
+        for name in ("patch_embedding", "patch_embedding_2x", "patch_embedding_4x", "patch_embedding_8x",
+                     "patch_embedding_16x", "patch_embedding_2x_f"):
+            if name + ".weight" in sd:
+                w = sd[name + ".weight"].detach().to(device=dev, dtype=_BF16).flatten(1)   # [N, cin*ph*pw]
+                b = f32(name + ".bias")
+                if name == "patch_embedding_2x_f":                                         # N = in_dim: pad to 32
+                    w, b = _pad_rows(w, 32), _pad_rows(b, 32)
+                self.embed[name] = (_pad_cols(w, 8), b)
+        self.text0 = (w16("text_embedding.0.weight"), f32("text_embedding.0.bias"))
+        self.text2 = (w16("text_embedding.2.weight"), f32("text_embedding.2.bias"))
+        self.time0 = (f32("time_embedding.0.weight"), f32("time_embedding.0.bias"))
+        self.time2 = (f32("time_embedding.2.weight"), f32("time_embedding.2.bias"))
+        self.tproj = (f32("time_projection.1.weight"), f32("time_projection.1.bias"))
+        self.head_w, self.head_b = f32("head.head.weight"), f32("head.head.bias")
+        self.head_mod = f32("head.modulation").reshape(2, C)
+        if self.variant == "14b":
+            self.img = dict(ln0=(f32("img_emb.proj.0.weight"), f32("img_emb.proj.0.bias")),
+                            fc1=(w16("img_emb.proj.1.weight"), f32("img_emb.proj.1.bias")),
+                            fc3=(w16("img_emb.proj.3.weight"), f32("img_emb.proj.3.bias")),
+                            ln4=(f32("img_emb.proj.4.weight"), f32("img_emb.proj.4.bias")))
+        self.blocks = []
+        mods = []
+        for i in range(self.layers):
+            p = f"blocks.{i}"
+            sa, ca = p + ".self_attn", p + ".cross_attn"
+            blk = dict(
+                w_qkv=cat16([sa + ".q.weight", sa + ".k.weight", sa + ".v.weight"]),
+                b_qkv=cat32([sa + ".q.bias", sa + ".k.bias", sa + ".v.bias"]),
+                w_o=w16(sa + ".o.weight"), b_o=f32(sa + ".o.bias"),
+                nq=f32(sa + ".norm_q.weight"), nk=f32(sa + ".norm_k.weight"),
+                cw_q=w16(ca + ".q.weight"), cb_q=f32(ca + ".q.bias"),
+                cw_kv=cat16([ca + ".k.weight", ca + ".v.weight"]), cb_kv=cat32([ca + ".k.bias", ca + ".v.bias"]),
+                cw_o=w16(ca + ".o.weight"), cb_o=f32(ca + ".o.bias"),
+                cnq=f32(ca + ".norm_q.weight"), cnk=f32(ca + ".norm_k.weight"),
+                n3w=f32(p + ".norm3.weight"), n3b=f32(p + ".norm3.bias"),
+                w1=w16(p + ".ffn.0.weight"), b1=f32(p + ".ffn.0.bias"),
+                w2=w16(p + ".ffn.2.weight"), b2=f32(p + ".ffn.2.bias"),
+            )
+            if self.variant == "14b":
+                blk["cw_kv_img"] = cat16([ca + ".k_img.weight", ca + ".v_img.weight"])
+                blk["cb_kv_img"] = cat32([ca + ".k_img.bias", ca + ".v_img.bias"])
+                blk["cnk_img"] = f32(ca + ".norm_k_img.weight")
+            self.blocks.append(blk)
+            mods.append(f32(p + ".modulation").reshape(6 * C))
+        self.block_mod = torch.stack(mods).contiguous()            # [layers, 6C]
+
+    @classmethod
+    def from_module(cls, model: torch.nn.Module, variant: str, device="cuda") -> "WanDiT":
+        """Build from a live reference WanModel (or yume_b200.model.WanModel): reads its parameters, never
+        modifies the checkpoint format (SURVEY.md §8b 'State-dict')."""
+        sd = dict(model.state_dict())
+        for name in ("patch_embedding_2x", "patch_embedding_4x", "patch_embedding_8x", "patch_embedding_16x",
+                     "patch_embedding_2x_f"):  # attached as plain attributes in the 14B tree (wan/image2video.py:155-159)
+            m = getattr(model, name, None)
+            if m is not None and name + ".weight" not in sd:
+                sd[name + ".weight"], sd[name + ".bias"] = m.weight, m.bias
+        return cls(sd, variant, dim=model.dim, ffn_dim=model.ffn_dim, num_heads=model.num_heads,
+                   num_layers=model.num_layers, in_dim=model.in_dim, out_dim=model.out_dim, text_len=model.text_len,
+                   freq_dim=model.freq_dim, patch_size=model.patch_size, eps=model.eps, device=device)
+
+    # ------------------------------------------------------------------------------------------------------
+    # workspace / tables
+    # ------------------------------------------------------------------------------------------------------
+    def _buf(self, key: str, shape: Tuple[int, ...], dtype) -> Tensor:
+        k = (key, tuple(shape), dtype)
+        t = self._ws.get(k)
+        if t is None:
+            for old in [o for o in self._ws if o[0] == key]:   # geometry changed: drop the stale buffer
+                del self._ws[old]
+            t = torch.empty(shape, device=self.device, dtype=dtype)
+            self._ws[k] = t
+        return t
+
+    def _axis_angles(self, n: int, axis_dim: int) -> Tensor:
+        """angles[pos, j] = pos * theta^(-2j/axis_dim) in fp64 (rope_params, model.py:27-35)."""
+        inv = 1.0 / torch.pow(10000.0, torch.arange(0, axis_dim, 2, dtype=torch.float64) / axis_dim)
+        return torch.outer(torch.arange(n, dtype=torch.float64), inv)
+
+    def _rope_segment(self, f: int, h: int, w: int, f0: int) -> Tensor:
+        """fp64 angles [f*h*w, 64] of one regular grid segment with temporal offset f0 (up_fre, model.py:933-940)."""
+        d = self.head_dim
+        dt, dh = d - 4 * (d // 6), 2 * (d // 6)
+        at = self._axis_angles(f0 + f, dt)[f0:]
+        ah, aw = self._axis_angles(h, dh), self._axis_angles(w, dh)
+        return torch.cat([at.view(f, 1, 1, -1).expand(f, h, w, -1), ah.view(1, h, 1, -1).expand(f, h, w, -1),
+                          aw.view(1, 1, w, -1).expand(f, h, w, -1)], dim=-1).reshape(f * h * w, -1)
+
+    def _rope_table(self, segments: Sequence[Tuple[int, int, int, int]]) -> Tensor:
+        """(cos, sin) f32 [L, 64, 2] on the device for a token sequence made of grid segments (f, h, w, f0)."""
+        key = tuple(segments)
+        t = self._rope_cache.get(key)
+        if t is None:
+            ang = torch.cat([self._rope_segment(*s) for s in segments], dim=0)
+            t = torch.stack([ang.cos(), ang.sin()], dim=-1).to(_F32).contiguous().to(self.device)
+            if len(self._rope_cache) > 16:
+                self._rope_cache.clear()
+            self._rope_cache[key] = t
+        return t
+
+    # ------------------------------------------------------------------------------------------------------
+    # pieces of the forward
+    # ------------------------------------------------------------------------------------------------------
+    def _embed_tokens(self, u: Tensor, name: str, patch: int, out_rows: Tensor) -> Tuple[int, int, int]:
+        """Patch-embed u [Cin, f, H, W] (f32, any strides) with Conv3d `name` (kernel == stride == (1,patch,patch)),
+        writing f32 token rows into out_rows [f*hp*wp, C]. Returns (f, hp, wp)."""
+        w, b = self.embed[name]
+        cin, f, H, W = u.shape
+        hp, wp = -(-H // patch), -(-W // patch)
+        n_tok = f * hp * wp
+        a = self._buf("patch_a", (n_tok, w.shape[1]), _BF16)
+        if w.shape[1] != cin * patch * patch:
+            a.zero_()                                           # K padding columns must be zero
+        ops.patchify(u, a, patch, patch)
+        ops.gemm(a, w, b, out_rows, ops.YB_EPI_F32)
+        return f, hp, wp
+
+    def _time_tables(self, t_unique: Tensor):
+        """e [U, C], per-block modulation tables [layers, U, 6, C], head table [U, 2, C] (model.py:805-812, 296, 344)."""
+        s = ops.sinusoidal(t_unique, self.freq_dim)
+        e = ops.linear_f32_small(s, *self.time0)
+        e = ops.linear_f32_small(e, *self.time2, silu_in=True)
+        e0 = ops.linear_f32_small(e, *self.tproj, silu_in=True)                    # [U, 6C]
+        U, C = e.shape[0], self.dim
+        mod = ops.bcast_add(self.block_mod, e0).view(self.layers, U, 6, C)
+        head = ops.bcast_add(e, self.head_mod).view(U, 2, C)                       # head uses e, not e0 (:344)
+        return e, mod, head
+
+    def _context(self, context: Tensor, clip_fea: Optional[Tensor]) -> Tensor:
+        """text_embedding on the zero-padded context (+ img_emb for 14B) -> bf16 [text_len (+257), C]
+        (model.py:815-821; wan/modules/model.py:939-941)."""
+        C = self.dim
+        n_img = 257 if self.variant == "14b" else 0
+        ctx_in = self._buf("ctx_in", (self.text_len, context.shape[1]), _BF16)
+        ctx_in.zero_()
+        ctx_in[:context.shape[0]].copy_(context)
+        hid = self._buf("ctx_hid", (self.text_len, C), _BF16)
+        out = self._buf("ctx_out", (n_img + self.text_len, C), _BF16)
+        ops.gemm(ctx_in, self.text0[0], self.text0[1], hid, ops.YB_EPI_GELU_BF16)
+        ops.gemm(hid, self.text2[0], self.text2[1], out[n_img:], ops.YB_EPI_BF16)
+        if n_img:
+            cf = clip_fea.reshape(-1, clip_fea.shape[-1]).to(device=self.device, dtype=_F32).contiguous()
+            cd = cf.shape[1]
+            a = self._buf("img_a", (n_img, cd), _BF16)
+            ops.ln_modulate(cf, a, None, None, None, *self.img["ln0"], eps=1e-5)
+            h1 = self._buf("img_h", (n_img, cd), _BF16)
+            ops.gemm(a, *self.img["fc1"], h1, ops.YB_EPI_GELU_ERF_BF16)
+            h3 = self._buf("img_o", (n_img, C), _F32)
+            ops.gemm(h1, *self.img["fc3"], h3, ops.YB_EPI_F32)
+            ops.ln_modulate(h3, out[:n_img], None, None, None, *self.img["ln4"], eps=1e-5)
+        return out
+
+    def _block(self, i: int, xs: Tensor, mod: Tensor, tok_idx: Optional[Tensor], rope: Tensor, rope_len: int,
+               ctx: Tensor) -> None:
+        """One WanAttentionBlock in place on the fp32 residual stream xs [L, C]."""
+        b, C, H, D = self.blocks[i], self.dim, self.heads, self.head_dim
+        L = xs.shape[0]
+        m = mod[i]                                             # [U, 6, C]: shift_a, scale_a, gate_a, shift_f, scale_f, gate_f
+        h = self._buf("h", (L, C), _BF16)
+        qkv = self._buf("qkv", (L, 3 * C), _BF16)
+        att = self._buf("att", (L, C), _BF16)
+        # --- self-attention ---
+        ops.ln_modulate(xs, h, m[:, 1], m[:, 0], tok_idx, eps=self.eps)
+        ops.gemm(h, b["w_qkv"], b["b_qkv"], qkv, ops.YB_EPI_BF16)
+        ops.rmsnorm_rope(qkv[:, :C], b["nq"], rope, D, self.eps, rope_len)
+        ops.rmsnorm_rope(qkv[:, C:2 * C], b["nk"], rope, D, self.eps, rope_len)
+        ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], att, H)
+        ops.gemm(att, b["w_o"], b["b_o"], xs, ops.YB_EPI_GATE_RES, gate=m[:, 2], tok_idx=tok_idx)
+        # --- cross-attention (no gate, affine norm3) ---
+        ops.ln_modulate(xs, h, None, None, None, b["n3w"], b["n3b"], eps=self.eps)
+        q2 = qkv[:, :C]
+        ops.gemm(h, b["cw_q"], b["cb_q"], q2, ops.YB_EPI_BF16)
+        ops.rmsnorm_rope(q2, b["cnq"], None, D, self.eps)
+        n_img = 257 if self.variant == "14b" else 0
+        ctx_txt = ctx[n_img:]
+        kv = self._buf("ckv", (ctx_txt.shape[0], 2 * C), _BF16)
+        ops.gemm(ctx_txt, b["cw_kv"], b["cb_kv"], kv, ops.YB_EPI_BF16)
+        ops.rmsnorm_rope(kv[:, :C], b["cnk"], None, D, self.eps)
+        ops.attention(q2, kv[:, :C], kv[:, C:], att, H)
+        if n_img:
+            kvi = self._buf("ckv_img", (n_img, 2 * C), _BF16)
+            ops.gemm(ctx[:n_img], b["cw_kv_img"], b["cb_kv_img"], kvi, ops.YB_EPI_BF16)
+            ops.rmsnorm_rope(kvi[:, :C], b["cnk_img"], None, D, self.eps)
+            ops.attention(q2, kvi[:, :C], kvi[:, C:], att, H, accumulate=True)
+        ops.gemm(att, b["cw_o"], b["cb_o"], xs, ops.YB_EPI_GATE_RES)
+        # --- FFN ---
+        ops.ln_modulate(xs, h, m[:, 4], m[:, 3], tok_idx, eps=self.eps)
+        hid = self._buf("ffn_hid", (L, self.ffn_dim), _BF16)
+        ops.gemm(h, b["w1"], b["b1"], hid, ops.YB_EPI_GELU_BF16)
+        ops.gemm(hid, b["w2"], b["b2"], xs, ops.YB_EPI_GATE_RES, gate=m[:, 5], tok_idx=tok_idx)
+
+    def block_forward(self, i: int, x: Tensor, e: Tensor, grid: Tuple[int, int, int], context: Tensor) -> Tensor:
+        """Single-block entry (BASELINE.json configs[0]): the arithmetic of WanAttentionBlock.forward for one sample.
+        x f32 [L, C]; e f32 [L, 6, C] (5B, per token) or [6, C] (14B); context bf16/f32 [S, C] already embedded."""
+        C = self.dim
+        xs = x.to(device=self.device, dtype=_F32).clone().contiguous()
+        L = xs.shape[0]
+        e = e.to(device=self.device, dtype=_F32)
+        if e.dim() == 2:
+            e0, tok_idx = e.reshape(1, 6 * C), None
+        else:
+            e0, tok_idx = e.reshape(L, 6 * C).contiguous(), torch.arange(L, device=self.device, dtype=torch.int32)
+        mod = ops.bcast_add(self.block_mod, e0).view(self.layers, e0.shape[0], 6, C)
+        rope = self._rope_table([(grid[0], grid[1], grid[2], 0)])
+        ctx = context.to(device=self.device, dtype=_BF16).contiguous()
+        self._block(i, xs, mod, tok_idx, rope, rope.shape[0], ctx)
+        return xs
+
+    # ------------------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x: Tensor, t: Tensor, context: Tensor, seq_len: int, y: Optional[Tensor] = None,
+                clip_fea: Optional[Tensor] = None, latent_frame_zero: Optional[int] = None, packed: bool = True) -> Tensor:
+        """One sample. x f32 [C_x, F, H, W] (+ y concatenated on channels), t f32 [1] or [1, L] / [2]-style
+        (first = history, last = new), context [S<=text_len, text_dim]. Returns f32 [C_out, F_new, H, W]."""
+        dev, C = self.device, self.dim
+        x = x.to(device=dev, dtype=_F32)
+        if y is not None:
+            x = torch.cat([x, y.to(device=dev, dtype=_F32)], dim=0)
+        if x.shape[0] != self.in_dim:
+            raise YumeB200Error(f"input has {x.shape[0]} channels, model expects {self.in_dim}")
+        if latent_frame_zero is None:
+            latent_frame_zero = 8 if self.variant == "5b" else 9
+        cin, Ftot, Hh, Ww = x.shape
+
+        # ---- tokens + rope table -----------------------------------------------------------------------
+        if packed:
+            hist = Ftot - latent_frame_zero
+            if hist < 1:
+                raise YumeB200Error("FramePack needs at least one history frame (u1 is empty in the reference)")
+            branch_hist = Ftot - (latent_frame_zero if self.variant == "5b" else 9)
+            plan = framepack_plan(hist, branch_hist)
+            u1, u2 = x[:, :hist], x[:, hist:]
+            shapes = []
+            for seg in plan:                                   # token counts first (to size the stream)
+                f = seg.frames.stop - seg.frames.start
+                hh, ww = Hh, Ww
+                if seg.pre_2x_f:
+                    hh, ww = -(-hh // 4), -(-ww // 4)
+                shapes.append((f, -(-hh // seg.patch), -(-ww // seg.patch)))
+            new_shape = (latent_frame_zero, -(-Hh // 2), -(-Ww // 2))
+            L_hist = sum(f * a * b for f, a, b in shapes)
+            L = L_hist + new_shape[0] * new_shape[1] * new_shape[2]
+            xs = self._buf("xs", (L, C), _F32)
+            row, f_z, rope_segs = 0, 0, []
+            for seg, (f, hp, wp) in zip(plan, shapes):
+                src = u1[:, seg.frames]
+                if seg.pre_2x_f:                               # model.py:696-698
+                    wpre, bpre = self.embed["patch_embedding_2x_f"]
+                    f2, h2, w2 = f, -(-Hh // 4), -(-Ww // 4)
+                    tmp = self._buf("pre2xf", (f2 * h2 * w2, wpre.shape[0]), _F32)
+                    a = self._buf("patch_a", (f2 * h2 * w2, wpre.shape[1]), _BF16)
+                    ops.patchify(src, a, 4, 4)
+                    ops.gemm(a, wpre, bpre, tmp, ops.YB_EPI_F32)
+                    ld = tmp.stride(0)                         # view the token-major result as [Cin, f, h, w]
+                    src = torch.as_strided(tmp, (cin, f2, h2, w2), (1, h2 * w2 * ld, w2 * ld, ld))
+                n = f * hp * wp
+                self._embed_tokens(src, seg.name, seg.patch, xs[row:row + n])
+                rope_segs.append((f, hp, wp, f_z))
+                row += n
+                f_z += f
+            self._embed_tokens(u2, "patch_embedding", 2, xs[row:])
+            rope_segs.append((*new_shape, f_z))
+            grid_new, rope_len = new_shape, L
+        else:
+            grid_new = (Ftot, -(-Hh // 2), -(-Ww // 2))
+            L_grid = grid_new[0] * grid_new[1] * grid_new[2]
+            if L_grid > seq_len:
+                raise AssertionError("seq_lens.max() <= seq_len")   # model.py:755
+            L, L_hist = seq_len, 0
+            xs = self._buf("xs", (L, C), _F32)
+            self._embed_tokens(x, "patch_embedding", 2, xs[:L_grid])
+            if L > L_grid:
+                xs[L_grid:].zero_()                            # padded tokens are zeros (model.py:756-759)
+            rope_segs, rope_len = [(*grid_new, 0)], L_grid
+        rope = self._rope_table(rope_segs)
+
+        # ---- timestep tables ---------------------------------------------------------------------------
+        t = t.to(device=dev, dtype=_F32).flatten()
+        tok_idx = None
+        if self.variant == "14b":
+            t_unique = t[:1]                                   # per-sample e (wan/modules/model.py:924-928)
+        elif packed:
+            t_unique = torch.stack([t[0], t[-1]])              # history tokens t[0], new tokens t[-1] (:730-737)
+            tok_idx = self._buf("tok_idx", (L,), torch.int32)
+            tok_idx[:L_hist] = 0
+            tok_idx[L_hist:] = 1
+        elif t.numel() == 1:
+            t_unique = t
+        else:                                                  # arbitrary per-token vector (t2v_dmd, textimage2video.py:629-634)
+            if t.numel() != L:
+                raise YumeB200Error("per-token t must have seq_len entries")
+            t_unique, inv = torch.unique(t, return_inverse=True)
+            tok_idx = inv.to(torch.int32).contiguous()
+        e_parts, mod_parts, head_parts = [], [], []
+        for s in range(0, t_unique.numel(), 16):               # the small-M linear handles 16 rows per launch
+            e_, m_, h_ = self._time_tables(t_unique[s:s + 16].contiguous())
+            e_parts.append(e_), mod_parts.append(m_), head_parts.append(h_)
+        mod = mod_parts[0] if len(mod_parts) == 1 else torch.cat(mod_parts, dim=1).contiguous()
+        head_tab = head_parts[0] if len(head_parts) == 1 else torch.cat(head_parts, dim=0).contiguous()
+
+        # ---- context -----------------------------------------------------------------------------------
+        ctx = self._context(context.to(device=dev), clip_fea)
+
+        # ---- blocks ------------------------------------------------------------------------------------
+        for i in range(self.layers):
+            self._block(i, xs, mod, tok_idx, rope, rope_len, ctx)
+
+        # ---- head + unpatchify (fp32, model.py:336-348, 856-890) -----------------------------------------
+        hn = self._buf("head_in", (L, C), _F32)
+        ops.ln_modulate(xs, hn, head_tab[:, 1], head_tab[:, 0], tok_idx, eps=self.eps)
+        yo = self._buf("head_out", (L, 4 * self.out_dim), _F32)
+        ops.linear_f32(hn, self.head_w, self.head_b, yo)
+        out = torch.empty(self.out_dim, grid_new[0], grid_new[1] * 2, grid_new[2] * 2, device=dev, dtype=_F32)
+        ops.unpatchify(yo[L_hist:], out, grid_new[0], grid_new[1], grid_new[2], 2, 2)
+        return out

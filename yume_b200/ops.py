@@ -9,12 +9,14 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (YB_EPI_BF16, YB_EPI_F32, YB_EPI_GATE_RES, YB_EPI_GELU_BF16, GemmArgs, YumeB200Error, check)
+from ._lib import (YB_ATT_ACCUMULATE, YB_ATT_P_SMEM, YB_EPI_BF16, YB_EPI_F32, YB_EPI_GATE_RES, YB_EPI_GELU_BF16,
+                   YB_EPI_GELU_ERF_BF16, GemmArgs, YumeB200Error, check)
 
 __all__ = [
     "gemm", "ln_modulate", "rmsnorm_rope", "attention", "patchify", "unpatchify", "sinusoidal",
     "linear_f32_small", "linear_f32", "umma_probe", "launch_count", "reset_launch_count",
-    "YB_EPI_BF16", "YB_EPI_GELU_BF16", "YB_EPI_F32", "YB_EPI_GATE_RES",
+    "YB_EPI_BF16", "YB_EPI_GELU_BF16", "YB_EPI_F32", "YB_EPI_GATE_RES", "YB_EPI_GELU_ERF_BF16", "bcast_add",
+    "YB_ATT_P_SMEM", "YB_ATT_ACCUMULATE",
 ]
 
 _launches = 0
@@ -57,7 +59,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
     N, K2 = w.shape
     if K2 != K:
         raise YumeB200Error(f"gemm K mismatch: {K} vs {K2}")
-    want = torch.bfloat16 if epilogue in (YB_EPI_BF16, YB_EPI_GELU_BF16) else torch.float32
+    want = torch.bfloat16 if epilogue in (YB_EPI_BF16, YB_EPI_GELU_BF16, YB_EPI_GELU_ERF_BF16) else torch.float32
     _need(out, want, "out")
     if out.shape[0] != M or out.shape[1] != N:
         raise YumeB200Error(f"gemm out shape {tuple(out.shape)} != ({M}, {N})")
@@ -119,7 +121,7 @@ def rmsnorm_rope(qk: torch.Tensor, weight: torch.Tensor, rope: Optional[torch.Te
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, heads: int,
-              scale: Optional[float] = None, variant: int = 0) -> torch.Tensor:
+              scale: Optional[float] = None, variant: int = 0, accumulate: bool = False) -> torch.Tensor:
     """softmax(q k^T * scale) v, non-causal. q [Lq, heads*128], k/v [Lk, heads*128] bf16 (row strides arbitrary)."""
     global _launches
     for n, t in (("q", q), ("k", k), ("v", v), ("out", out)):
@@ -130,22 +132,24 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     if scale is None:
         scale = 1.0 / math.sqrt(128.0)
     check(_lib.load().yb_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
-                                   out.data_ptr(), out.stride(0), Lq, Lk, heads, scale, variant, _stream()),
+                                   out.data_ptr(), out.stride(0), Lq, Lk, heads, scale,
+                                   (YB_ATT_P_SMEM if variant == 1 else 0) | (YB_ATT_ACCUMULATE if accumulate else 0),
+                                   _stream()),
           "yb_attention")
     _launches += 1
     return out
 
 
 def patchify(x: torch.Tensor, out: torch.Tensor, ph: int, pw: int) -> torch.Tensor:
-    """x f32 [Cin, F, H, W] (contiguous) -> out bf16 [F*ceil(H/ph)*ceil(W/pw), >= Cin*ph*pw]."""
+    """x f32 [Cin, F, H, W] (any strides) -> out bf16 [F*ceil(H/ph)*ceil(W/pw), >= Cin*ph*pw]."""
     global _launches
-    _need(x, torch.float32, "x")
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise YumeB200Error("patchify input must be a CUDA float32 tensor")
     _need(out, torch.bfloat16, "out")
-    if not x.is_contiguous():
-        raise YumeB200Error("patchify input must be contiguous")
     Cin, F, H, W = x.shape
-    check(_lib.load().yb_patchify(x.data_ptr(), out.data_ptr(), out.stride(0), Cin, F, H, W, ph, pw, _stream()),
-          "yb_patchify")
+    sc, sf, sh, sw = x.stride()
+    check(_lib.load().yb_patchify(x.data_ptr(), sc, sf, sh, sw, out.data_ptr(), out.stride(0), Cin, F, H, W, ph, pw,
+                                  _stream()), "yb_patchify")
     _launches += 1
     return out
 
@@ -158,6 +162,20 @@ def unpatchify(y: torch.Tensor, out: torch.Tensor, F: int, Hp: int, Wp: int, ph:
     Cout = out.shape[0]
     check(_lib.load().yb_unpatchify(y.data_ptr(), y.stride(0), out.data_ptr(), Cout, F, Hp, Wp, ph, pw, _stream()),
           "yb_unpatchify")
+    _launches += 1
+    return out
+
+
+def bcast_add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """out[r1, r2, :] = a[r1, :] + b[r2, :] (f32, contiguous 2-D inputs)."""
+    global _launches
+    _need(a, torch.float32, "a")
+    _need(b, torch.float32, "b")
+    if not (a.is_contiguous() and b.is_contiguous()) or a.shape[1] != b.shape[1]:
+        raise YumeB200Error("bcast_add needs contiguous [R, n] operands with equal n")
+    out = torch.empty(a.shape[0], b.shape[0], a.shape[1], device=a.device, dtype=torch.float32)
+    check(_lib.load().yb_bcast_add(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.shape[0], b.shape[0], a.shape[1],
+                                   _stream()), "yb_bcast_add")
     _launches += 1
     return out
 
