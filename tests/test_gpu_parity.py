@@ -1,0 +1,337 @@
+"""GPU parity tests (`-m gpu`): the CUDA path, called through the C ABI, against (a) the CPU oracle, (b) the
+golden vectors generated from the reference's own code, (c) size-independent properties at full 5B size.
+
+Tolerances (bf16 path vs fp32-weight oracle, SURVEY.md §8c / BASELINE.md §3):
+  * index / gather ops (patchify, unpatchify): bit-exact
+  * single kernels vs an fp32 torch reference: bf16 output rounding, rel-Frobenius <= 4e-3
+  * one WanAttentionBlock (delta y - x): rel-Frobenius <= 1e-2, max-abs <= 3e-2 on unit-variance inputs
+  * whole tiny model output: rel-Frobenius <= 1.5e-2
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import synth
+from oracle.wan_dit import WanOracle, grid_freqs
+
+pytestmark = pytest.mark.gpu
+
+KERNEL_TOL = 4e-3
+BLOCK_TOL_REL, BLOCK_TOL_ABS = 1e-2, 3e-2
+MODEL_TOL = 1.5e-2
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import yume_b200
+    yume_b200.load()  # fail loudly if the extension is missing
+    return "cuda"
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# building blocks
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_umma_probe(dev, mode):
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(mode)
+    a = torch.randn(128, 128, generator=g).to(dev).bfloat16()
+    b = torch.randn(128, 128, generator=g).to(dev).bfloat16()
+    d = ops.umma_probe(a, b, mode)
+    ref = a.float() @ (b.float().t() if mode == 0 else b.float())
+    assert rel(d, ref) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 0), (300, 384, 192, 0), (1000, 3072, 3072, 0), (512, 128, 4096, 128),
+                                       (77, 96, 144, 0), (4097, 768, 256, 256)])
+def test_gemm_bf16_matches_fp32_reference(dev, M, N, K, bn):
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(dev)
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, bias, out, ops.YB_EPI_BF16, block_n=bn)
+    assert rel(out, a.float() @ w.float().t() + bias) < KERNEL_TOL
+
+
+def test_gemm_epilogues(dev):
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(5)
+    M, N, K, U = 1000, 512, 320, 3
+    a = (torch.randn(M, K, generator=g) * 0.5).to(dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) * 0.1).to(dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(dev)
+    acc = a.float() @ w.float().t() + bias
+    o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, bias, o, ops.YB_EPI_GELU_BF16)
+    assert rel(o, torch.nn.functional.gelu(acc, approximate="tanh")) < KERNEL_TOL
+    ops.gemm(a, w, bias, o, ops.YB_EPI_GELU_ERF_BF16)
+    assert rel(o, torch.nn.functional.gelu(acc)) < KERNEL_TOL
+    o32 = torch.empty(M, N, device=dev)
+    ops.gemm(a, w, None, o32, ops.YB_EPI_F32)
+    assert rel(o32, acc - bias) < 1e-5
+    gate = torch.randn(U, 6, N, generator=g).to(dev)
+    tok = torch.randint(0, U, (M,), generator=g).to(dev, torch.int32)
+    x = torch.randn(M, N, generator=g).to(dev)
+    want = x + acc * gate[tok.long(), 2]
+    ops.gemm(a, w, bias, x, ops.YB_EPI_GATE_RES, gate=gate[:, 2], tok_idx=tok)
+    assert rel(x, want) < 1e-5
+    x2 = torch.randn(M, N, generator=g).to(dev)
+    want2 = x2 + acc
+    ops.gemm(a, w, bias, x2, ops.YB_EPI_GATE_RES)
+    assert rel(x2, want2) < 1e-5
+
+
+def _sdpa(q, k, v, heads):
+    Lq, Lk = q.shape[0], k.shape[0]
+    f = lambda t, L: t.reshape(L, heads, 128).transpose(0, 1).float()[None]  # noqa: E731
+    o = torch.nn.functional.scaled_dot_product_attention(f(q, Lq), f(k, Lk), f(v, Lk))[0]
+    return o.transpose(0, 1).reshape(Lq, heads * 128)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("Lq,Lk,heads", [(128, 128, 1), (300, 200, 2), (1000, 512, 3), (777, 1500, 2), (257, 257, 2),
+                                         (1, 1, 1), (130, 769, 2)])
+def test_attention_matches_sdpa(dev, variant, Lq, Lk, heads):
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(Lq * 7 + Lk)
+    qkv = torch.randn(max(Lq, Lk), 3 * heads * 128, generator=g).to(dev).bfloat16()
+    q, k, v = qkv[:Lq, :heads * 128], qkv[:Lk, heads * 128:2 * heads * 128], qkv[:Lk, 2 * heads * 128:]
+    out = torch.zeros(Lq, heads * 128, device=dev, dtype=torch.bfloat16)
+    ops.attention(q, k, v, out, heads, variant=variant)
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, _sdpa(q, k, v, heads)) < KERNEL_TOL
+
+
+def test_attention_large_logits_and_accumulate(dev):
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(11)
+    Lq, Lk, heads = 512, 1024, 2
+    q = (torch.randn(Lq, heads * 128, generator=g) * 4).to(dev).bfloat16()
+    k = (torch.randn(Lk, heads * 128, generator=g) * 4).to(dev).bfloat16()
+    v = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
+    out = torch.zeros(Lq, heads * 128, device=dev, dtype=torch.bfloat16)
+    ops.attention(q, k, v, out, heads)            # row maxima jump by >> 2^8: exercises the lazy O rescale
+    ref = _sdpa(q, k, v, heads)
+    assert rel(out, ref) < KERNEL_TOL
+    k2 = torch.randn(257, heads * 128, generator=g).to(dev).bfloat16()
+    v2 = torch.randn(257, heads * 128, generator=g).to(dev).bfloat16()
+    ops.attention(q, k2, v2, out, heads, accumulate=True)
+    assert rel(out, ref + _sdpa(q, k2, v2, heads)) < 2 * KERNEL_TOL
+
+
+def test_elementwise_kernels(dev):
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(3)
+    L, C, D, U = 1000, 3072, 128, 2
+    x = (torch.randn(L, C, generator=g) * 2 + 0.3).to(dev)
+    mod = (torch.randn(U, 6, C, generator=g) * 0.5).to(dev)
+    tok = torch.randint(0, U, (L,), generator=g).to(dev, torch.int32)
+    out = torch.empty(L, C, device=dev, dtype=torch.bfloat16)
+    ops.ln_modulate(x, out, mod[:, 1], mod[:, 0], tok)
+    ln = torch.nn.functional.layer_norm(x, (C,), eps=1e-6)
+    assert rel(out, ln * (1 + mod[tok.long(), 1]) + mod[tok.long(), 0]) < KERNEL_TOL
+    w, b = torch.randn(C, generator=g).to(dev), torch.randn(C, generator=g).to(dev)
+    ops.ln_modulate(x, out, None, None, None, w, b)
+    assert rel(out, ln * w + b) < KERNEL_TOL
+    o32 = torch.empty(L, C, device=dev)
+    ops.ln_modulate(x, o32, mod[0, 1], mod[0, 0])
+    assert rel(o32, ln * (1 + mod[0, 1]) + mod[0, 0]) < 1e-5
+    # RMSNorm + RoPE against the reference formula (fp64 complex multiply, wan23/modules/model.py:62-72)
+    qkv = torch.randn(L, 3 * C, generator=g).to(dev).bfloat16()
+    q0, v0 = qkv[:, :C].clone(), qkv[:, 2 * C:].clone()
+    wq = (torch.rand(C, generator=g) + 0.5).to(dev)
+    ang = (torch.rand(L, D // 2, generator=g, dtype=torch.float64) * 6.28).to(dev)
+    rope = torch.stack([ang.cos(), ang.sin()], -1).float().contiguous()
+    ops.rmsnorm_rope(qkv[:, :C], wq, rope, D, rope_len=L - 100)
+    xf = q0.float()
+    n = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6) * wq
+    c = torch.view_as_complex(n.double().view(L, C // D, D // 2, 2)) * torch.polar(torch.ones_like(ang), ang)[:, None]
+    want = torch.view_as_real(c).flatten(1).float()
+    want[L - 100:] = n[L - 100:]                      # tokens past the grid are not rotated (model.py:73)
+    assert rel(qkv[:, :C], want) < KERNEL_TOL
+    assert torch.equal(qkv[:, 2 * C:], v0)            # neighbours untouched
+    # small fp32 pieces
+    t = torch.tensor([0.0, 999.0, 500.5], device=dev)
+    half = 128
+    s = torch.outer(t.double(), torch.pow(10000, -torch.arange(half, device=dev).double().div(half)))
+    assert (ops.sinusoidal(t, 256) - torch.cat([s.cos(), s.sin()], 1).float()).abs().max() < 1e-6
+    xi, w1, b1 = torch.randn(3, 256, generator=g).to(dev), (torch.randn(512, 256, generator=g) * 0.05).to(dev), torch.randn(512, generator=g).to(dev)
+    assert rel(ops.linear_f32_small(xi, w1, b1), xi @ w1.t() + b1) < 1e-5
+    assert rel(ops.linear_f32_small(xi, w1, None, True), torch.nn.functional.silu(xi) @ w1.t()) < 1e-5
+    xa, wh = torch.randn(1000, 3072, generator=g).to(dev), (torch.randn(192, 3072, generator=g) * 0.02).to(dev)
+    oh = torch.empty(1000, 192, device=dev)
+    ops.linear_f32(xa, wh, None, oh)
+    assert rel(oh, xa.double() @ wh.double().t()) < 1e-5
+    a2, b2 = torch.randn(5, 64, generator=g).to(dev), torch.randn(3, 64, generator=g).to(dev)
+    assert torch.equal(ops.bcast_add(a2, b2), a2[:, None] + b2[None])
+
+
+def test_patchify_unpatchify_are_bit_exact(dev):
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(4)
+    for (cin, F, H, W, p) in [(48, 3, 10, 12, 2), (48, 2, 9, 11, 4), (36, 2, 7, 33, 32), (48, 21, 44, 80, 2)]:
+        x = torch.randn(cin, F, H, W, generator=g).to(dev)
+        hp, wp = -(-H // p), -(-W // p)
+        out = torch.empty(F * hp * wp, cin * p * p, device=dev, dtype=torch.bfloat16)
+        ops.patchify(x, out, p, p)
+        xp = torch.nn.functional.pad(x, (0, wp * p - W, 0, hp * p - H)).bfloat16().float()
+        want = torch.nn.functional.unfold(xp.permute(1, 0, 2, 3), p, stride=p).permute(0, 2, 1).reshape(F * hp * wp, cin * p * p)
+        assert torch.equal(out.float(), want)
+        xs = x[:, 1:]                                  # frame slice = non-contiguous channel stride
+        out2 = torch.empty((F - 1) * hp * wp, cin * p * p, device=dev, dtype=torch.bfloat16)
+        ops.patchify(xs, out2, p, p)
+        assert torch.equal(out2, out[hp * wp:])
+    F, hp, wp, co = 3, 5, 6, 48
+    y = torch.randn(F * hp * wp, 4 * co, generator=g).to(dev)
+    uo = torch.empty(co, F, hp * 2, wp * 2, device=dev)
+    ops.unpatchify(y, uo, F, hp, wp, 2, 2)
+    want = torch.einsum("fhwpqrc->cfphqwr", y.view(F, hp, wp, 1, 2, 2, co)).reshape(co, F, hp * 2, wp * 2)
+    assert torch.equal(uo, want)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# block and model parity vs the oracle and the reference-generated golden vectors
+# ------------------------------------------------------------------------------------------------------------
+def _engine(cfg, sd, dev):
+    from yume_b200.dit import WanDiT
+    kw = synth.oracle_kwargs(cfg)
+    variant = kw.pop("variant")
+    return WanDiT(sd, variant, device=dev, **kw)
+
+
+@pytest.fixture(scope="module")
+def tiny5(dev, golden_dir):
+    g = torch.load(golden_dir / "wan23_tiny.pt", weights_only=False)
+    sd = synth.make_state_dict(g["cfg"], g["seed_w"])
+    return g, sd, _engine(g["cfg"], sd, dev)
+
+
+@pytest.fixture(scope="module")
+def tiny14(dev, golden_dir):
+    g = torch.load(golden_dir / "wan21_tiny.pt", weights_only=False)
+    sd = synth.make_state_dict(g["cfg"], g["seed_w"])
+    return g, sd, _engine(g["cfg"], sd, dev)
+
+
+def test_single_block_config0(tiny5):
+    """BASELINE.json configs[0]: one WanAttentionBlock, 128 tokens (grid 2x8x8), vs the reference output."""
+    g, sd, eng = tiny5
+    cfg, b = g["cfg"], g["block"]
+    gen = torch.Generator().manual_seed(b["seed"])
+    L, C = b["L"], cfg["dim"]
+    x = torch.randn(1, L, C, generator=gen)
+    e = 0.5 * torch.randn(1, L, 6, C, generator=gen)
+    ctx = torch.randn(1, cfg["text_len"], C, generator=gen)
+    y = eng.block_forward(0, x[0], e[0], b["grid"], ctx[0]).cpu()
+    delta_ref = b["out"][0] - x[0]
+    delta = y - x[0]
+    assert float((delta - delta_ref).norm() / delta_ref.norm()) < BLOCK_TOL_REL
+    # bf16-rounded context differs from the fp32 one the reference saw; abs tolerance covers it
+    assert float((y - b["out"][0]).abs().max()) < BLOCK_TOL_ABS * max(1.0, float(b["out"].abs().mean()))
+
+
+@pytest.mark.parametrize("case", ["5b_grid", "5b_grid_padded", "5b_pack_h3", "5b_pack_h1", "5b_pack_h10",
+                                  "5b_pack_h30", "5b_pack_h100", "5b_pack_h400"])
+def test_5b_forward_vs_reference_golden(tiny5, case):
+    g, sd, eng = tiny5
+    c, cfg = g["cases"][case], g["cfg"]
+    inp = synth.make_inputs(cfg, c["seed"], c["frames"], c["H"], c["W"], c["ctx_len"])
+    out = eng.forward(inp["x"], torch.tensor(c["t"]), inp["context"], c["seq_len"], latent_frame_zero=c["lfz"],
+                      packed=c["flag"])
+    assert out.shape == c["out"].shape
+    assert rel(out, c["out"]) < MODEL_TOL
+
+
+@pytest.mark.parametrize("case", ["14b_grid", "14b_pack_h4", "14b_pack_lfz8", "14b_pack_h12"])
+def test_14b_forward_vs_reference_golden(tiny14, case):
+    g, sd, eng = tiny14
+    c, cfg = g["cases"][case], g["cfg"]
+    inp = synth.make_inputs(cfg, c["seed"], c["frames"], c["H"], c["W"], c["ctx_len"])
+    out = eng.forward(inp["x"], torch.tensor(c["t"]), inp["context"], c["seq_len"], y=inp["y"], clip_fea=inp["clip_fea"],
+                      latent_frame_zero=c["lfz"], packed=c["rand_num_img"] >= 0.4)
+    assert out.shape == c["out"].shape
+    assert rel(out, c["out"]) < MODEL_TOL
+
+
+def test_mirror_module_keeps_reference_signature(tiny5, dev):
+    """WanModel5B built on the meta device + install(state_dict): forward(x list, t, context list, seq_len, ...)."""
+    from yume_b200.model import WanModel5B
+    g, sd, _ = tiny5
+    cfg, c = g["cfg"], g["cases"]["5b_pack_h10"]
+    with torch.device("meta"):
+        m = WanModel5B(model_type="ti2v", text_len=cfg["text_len"], in_dim=cfg["in_dim"], dim=cfg["dim"],
+                       ffn_dim=cfg["ffn_dim"], freq_dim=cfg["freq_dim"], text_dim=cfg["text_dim"], out_dim=cfg["out_dim"],
+                       num_heads=cfg["num_heads"], num_layers=cfg["num_layers"])
+    m.install(dev, state_dict=sd)
+    inp = synth.make_inputs(cfg, c["seed"], c["frames"], c["H"], c["W"], c["ctx_len"])
+    outs = m([inp["x"]], torch.tensor(c["t"]), [inp["context"]], seq_len=c["seq_len"], latent_frame_zero=c["lfz"], flag=True)
+    assert isinstance(outs, list) and outs[0].dtype == torch.float32
+    assert rel(outs[0], c["out"]) < MODEL_TOL
+    with pytest.raises(NotImplementedError):
+        m([inp["x"]], torch.tensor(c["t"]), [inp["context"]], seq_len=c["seq_len"], enable_mask=True)
+
+
+def test_oracle_block_at_real_width(dev):
+    """One block at the real 5B width (C=3072, 24 heads, F=14336), L=256: CUDA vs oracle (seconds on CPU)."""
+    cfg = dict(synth.CFG_5B, num_layers=1, text_len=64)
+    sd = synth.make_state_dict(cfg, 77, num_layers=1)
+    eng = _engine(cfg, sd, dev)
+    gen = torch.Generator().manual_seed(9)
+    L, C = 256, cfg["dim"]
+    x = torch.randn(1, L, C, generator=gen)
+    e = 0.5 * torch.randn(1, L, 6, C, generator=gen)
+    ctx = torch.randn(1, 64, C, generator=gen).bfloat16().float()
+    m = WanOracle(sd, **synth.oracle_kwargs(cfg))
+    want = m.block(0, x, e, grid_freqs(m.tables, 4, 8, 8), ctx)[0]
+    got = eng.block_forward(0, x[0], e[0], (4, 8, 8), ctx[0]).cpu()
+    d_ref, d = want - x[0], got - x[0]
+    assert float((d - d_ref).norm() / d_ref.norm()) < BLOCK_TOL_REL
+    assert float((got - want).abs().max()) < BLOCK_TOL_ABS * max(1.0, float(want.abs().mean()))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs[1] geometry: L = 18480, 24 heads) — no oracle needed
+# ------------------------------------------------------------------------------------------------------------
+def test_fullsize_attention_is_key_permutation_invariant(dev):
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(21)
+    L, heads = 18480, 2
+    q = torch.randn(L, heads * 128, generator=g).to(dev).bfloat16()
+    k = torch.randn(L, heads * 128, generator=g).to(dev).bfloat16()
+    v = torch.randn(L, heads * 128, generator=g).to(dev).bfloat16()
+    o1 = torch.empty_like(q)
+    o2 = torch.empty_like(q)
+    ops.attention(q, k, v, o1, heads)
+    perm = torch.randperm(L, generator=g).to(dev)
+    ops.attention(q, k[perm].contiguous(), v[perm].contiguous(), o2, heads)
+    assert rel(o1, o2) < 3e-3                          # only the fp32 summation order changes
+    idx = torch.randint(0, L, (256,), generator=g).to(dev)
+    assert rel(o1[idx], _sdpa(q[idx].contiguous(), k, v, heads)) < KERNEL_TOL
+
+
+def test_fullsize_gemm_linearity_and_row_independence(dev):
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(22)
+    M, N, K = 18480, 3072, 3072
+    a1 = (torch.randn(M, K, generator=g) * 0.5).to(dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev).bfloat16()
+    o1 = torch.empty(M, N, device=dev)
+    ops.gemm(a1, w, None, o1, ops.YB_EPI_F32)
+    o2 = torch.empty(M, N, device=dev)
+    ops.gemm((a1.float() * 2).bfloat16(), w, None, o2, ops.YB_EPI_F32)     # exact scaling by 2 in bf16
+    assert torch.equal(o2, o1 * 2)
+    rows = torch.randint(0, M, (300,), generator=g).to(dev)
+    sub = torch.empty(300, N, device=dev)
+    ops.gemm(a1[rows].contiguous(), w, None, sub, ops.YB_EPI_F32)
+    assert torch.equal(sub, o1[rows])                                      # a row's result does not depend on its tile
+    assert rel(o1[rows], a1[rows].float() @ w.float().t()) < 1e-4

@@ -1,0 +1,136 @@
+"""CPU tests of the host side: the C-ABI library exports, the FramePack plan, RoPE tables, error behaviour,
+and the rule that nothing under yume_b200/ touches oracle/."""
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+import yume_b200
+from oracle import synth
+from oracle.wan_dit import WanOracle, grid_freqs, rope_tables
+from yume_b200 import _lib, ops
+from yume_b200.dit import WanDiT, framepack_plan
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_header_symbol():
+    header = (ROOT / "include" / "yume_b200.h").read_text()
+    declared = set(re.findall(r"^\s*int\s+(yb_\w+)\s*\(", header, flags=re.M))
+    assert declared, "no declarations parsed"
+    lib = yume_b200.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/yume_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes signature table and header disagree"
+    assert lib.yb_abi_version() == 1
+
+
+def test_ops_have_no_cpu_path():
+    a = torch.zeros(128, 64, dtype=torch.bfloat16)
+    with pytest.raises(yume_b200.YumeB200Error):
+        ops.gemm(a, a, None, torch.zeros(128, 128, dtype=torch.bfloat16), ops.YB_EPI_BF16)
+    with pytest.raises(yume_b200.YumeB200Error):
+        ops.ln_modulate(torch.zeros(4, 64), torch.zeros(4, 64, dtype=torch.bfloat16), None, None)
+
+
+def test_product_path_never_imports_oracle():
+    for f in (ROOT / "yume_b200").rglob("*.py"):
+        src = f.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f"{f} imports oracle/"
+    for f in (ROOT / "yume_b200" / "csrc").glob("*"):
+        if f.suffix in (".cu", ".cuh", ".h"):
+            assert "oracle" not in f.read_text()
+
+
+def _oracle_segments(variant, hist, branch_hist):
+    m = WanOracle.__new__(WanOracle)
+    m.variant = variant
+    out = []
+    for sl, name, padm, pre in m._segments(hist, branch_hist):
+        start, stop, _ = sl.indices(hist)
+        out.append((start, stop, name, pre))
+    return out
+
+
+@pytest.mark.parametrize("variant,lfz", [("5b", 8), ("14b", 9), ("14b", 8)])
+def test_framepack_plan_matches_oracle_for_every_history_length(variant, lfz):
+    lo = 1
+    for hist in range(lo, 1367):
+        branch = hist if variant == "5b" else hist + lfz - 9
+        if branch > 1366:
+            break
+        try:
+            want = _oracle_segments(variant, hist, branch)
+        except IndexError:
+            continue
+        got = [(s.frames.start, s.frames.stop, s.name, s.pre_2x_f) for s in framepack_plan(hist, branch)]
+        if any(a >= b or a < 0 for a, b, *_ in want):
+            continue  # the reference itself indexes out of range / produces empty segments here
+        assert got == want, (hist, got, want)
+
+
+def test_framepack_plan_rejects_too_long_history():
+    with pytest.raises(UnboundLocalError):
+        framepack_plan(1400, 1400)
+
+
+def _token_count(variant, frames, H, W, lfz):
+    hist = frames - lfz
+    plan = framepack_plan(hist, frames - (lfz if variant == "5b" else 9))
+    n = 0
+    for s in plan:
+        f = s.frames.stop - s.frames.start
+        n += f * -(-H // s.patch) * -(-W // s.patch)
+    return n + lfz * (H // 2) * (W // 2)
+
+
+def test_real_geometry_token_counts():
+    # 5B FramePack chunk 13 latent frames @44x80 -> 9460; 14B @68x120 -> 21930 (lfz 8) / 23460 (lfz 9)
+    assert _token_count("5b", 13, 44, 80, 8) == 9460
+    assert _token_count("14b", 13, 68, 120, 8) == 21930
+    assert _token_count("14b", 13, 68, 120, 9) == 23460
+    assert 21 * 22 * 40 == 18480
+
+
+@pytest.fixture(scope="module")
+def tiny_engine_cpu():
+    cfg = synth.CFG_5B_TINY
+    sd = synth.make_state_dict(cfg, 1234)
+    kw = synth.oracle_kwargs(cfg)
+    kw.pop("variant")
+    return WanDiT(sd, "5b", device="cpu", **kw)
+
+
+def test_rope_table_matches_reference_tables(tiny_engine_cpu):
+    eng = tiny_engine_cpu
+    tabs = rope_tables(128)
+    segs = [(1, 3, 5, 0), (2, 2, 3, 1), (4, 3, 5, 3)]
+    want = torch.cat([grid_freqs(tabs, f, h, w, f0) for f, h, w, f0 in segs], dim=0).squeeze(1)  # complex128 [L, 64]
+    got = eng._rope_table(segs)
+    assert got.shape == (want.shape[0], 64, 2)
+    assert torch.allclose(got[..., 0].double(), want.real, atol=1e-6)
+    assert torch.allclose(got[..., 1].double(), want.imag, atol=1e-6)
+
+
+def test_repack_layouts(tiny_engine_cpu):
+    eng, C = tiny_engine_cpu, 256
+    assert eng.blocks[0]["w_qkv"].shape == (3 * C, C) and eng.blocks[0]["w_qkv"].dtype == torch.bfloat16
+    assert eng.block_mod.shape == (2, 6 * C)
+    w, b = eng.embed["patch_embedding_2x_f"]
+    assert w.shape == (64, 48 * 16) and b.shape == (64,)          # N padded 48 -> 64 for the GEMM tile
+    assert eng.embed["patch_embedding_16x"][0].shape == (C, 48 * 32 * 32)
+
+
+def test_mirror_state_dict_keys_match_reference_names():
+    from yume_b200.model import WanModel14B, WanModel5B
+    for cls, cfg in ((WanModel5B, synth.CFG_5B_TINY), (WanModel14B, synth.CFG_14B_TINY)):
+        kw = dict(model_type="ti2v" if cfg["variant"] == "5b" else "i2v", text_len=cfg["text_len"], in_dim=cfg["in_dim"],
+                  dim=cfg["dim"], ffn_dim=cfg["ffn_dim"], freq_dim=cfg["freq_dim"], text_dim=cfg["text_dim"],
+                  out_dim=cfg["out_dim"], num_heads=cfg["num_heads"], num_layers=cfg["num_layers"])
+        if cfg["variant"] == "14b":
+            kw["clip_dim"] = cfg["clip_dim"]
+        m = cls(**kw)
+        have = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        want = synth.param_shapes(cfg)
+        assert have == {k: tuple(v) for k, v in want.items()}

@@ -22,6 +22,7 @@ import torch
 
 from . import ops
 from ._lib import YumeB200Error
+from .utils import KernelTimer
 
 Tensor = torch.Tensor
 _BF16 = torch.bfloat16
@@ -120,6 +121,7 @@ class WanDiT:
         self.head_dim = 128
         self._ws: Dict[Tuple, Tensor] = {}
         self._rope_cache: Dict[Tuple, Tensor] = {}
+        self.timer = KernelTimer()          # bench.py switches it on to time individual kernels inside a live step
         self._repack(state_dict)
 
     # ------------------------------------------------------------------------------------------------------
@@ -302,12 +304,23 @@ class WanDiT:
         qkv = self._buf("qkv", (L, 3 * C), _BF16)
         att = self._buf("att", (L, C), _BF16)
         # --- self-attention ---
+        T = self.timer
+        T.begin("ln_modulate")
         ops.ln_modulate(xs, h, m[:, 1], m[:, 0], tok_idx, eps=self.eps)
+        T.end("ln_modulate")
+        T.begin("gemm_qkv")
         ops.gemm(h, b["w_qkv"], b["b_qkv"], qkv, ops.YB_EPI_BF16)
+        T.end("gemm_qkv")
+        T.begin("rmsnorm_rope")
         ops.rmsnorm_rope(qkv[:, :C], b["nq"], rope, D, self.eps, rope_len)
+        T.end("rmsnorm_rope")
         ops.rmsnorm_rope(qkv[:, C:2 * C], b["nk"], rope, D, self.eps, rope_len)
+        T.begin("self_attention")
         ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], att, H)
+        T.end("self_attention")
+        T.begin("gemm_o")
         ops.gemm(att, b["w_o"], b["b_o"], xs, ops.YB_EPI_GATE_RES, gate=m[:, 2], tok_idx=tok_idx)
+        T.end("gemm_o")
         # --- cross-attention (no gate, affine norm3) ---
         ops.ln_modulate(xs, h, None, None, None, b["n3w"], b["n3b"], eps=self.eps)
         q2 = qkv[:, :C]
@@ -318,7 +331,9 @@ class WanDiT:
         kv = self._buf("ckv", (ctx_txt.shape[0], 2 * C), _BF16)
         ops.gemm(ctx_txt, b["cw_kv"], b["cb_kv"], kv, ops.YB_EPI_BF16)
         ops.rmsnorm_rope(kv[:, :C], b["cnk"], None, D, self.eps)
+        T.begin("cross_attention")
         ops.attention(q2, kv[:, :C], kv[:, C:], att, H)
+        T.end("cross_attention")
         if n_img:
             kvi = self._buf("ckv_img", (n_img, 2 * C), _BF16)
             ops.gemm(ctx[:n_img], b["cw_kv_img"], b["cb_kv_img"], kvi, ops.YB_EPI_BF16)
@@ -328,8 +343,12 @@ class WanDiT:
         # --- FFN ---
         ops.ln_modulate(xs, h, m[:, 4], m[:, 3], tok_idx, eps=self.eps)
         hid = self._buf("ffn_hid", (L, self.ffn_dim), _BF16)
+        T.begin("gemm_ffn1")
         ops.gemm(h, b["w1"], b["b1"], hid, ops.YB_EPI_GELU_BF16)
+        T.end("gemm_ffn1")
+        T.begin("gemm_ffn2")
         ops.gemm(hid, b["w2"], b["b2"], xs, ops.YB_EPI_GATE_RES, gate=m[:, 5], tok_idx=tok_idx)
+        T.end("gemm_ffn2")
 
     def block_forward(self, i: int, x: Tensor, e: Tensor, grid: Tuple[int, int, int], context: Tensor) -> Tensor:
         """Single-block entry (BASELINE.json configs[0]): the arithmetic of WanAttentionBlock.forward for one sample.
