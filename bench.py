@@ -226,7 +226,8 @@ def product_arm(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(3, args.warmup)):
+    n_warm = args.warmup if args.quick else max(3, args.warmup)
+    for _ in range(n_warm):
         step_device()
     torch.cuda.synchronize()
 
@@ -238,9 +239,12 @@ def product_arm(args):
         eng.timer.active = False
         launches = ops.launch_count()
         kern = eng.timer.summary()
-    for _ in range(2):
-        step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
+    if args.quick:
+        e2e_ms = float("nan")
+    else:
+        for _ in range(2):
+            step_e2e()
+        e2e_ms = timed(step_e2e, args.steps)
 
     ms_per_step = total_ms / args.steps
     e2e_ms_per_step = e2e_ms / args.steps
@@ -277,7 +281,7 @@ def product_arm(args):
     if rank == 0:
         line = {
             "metric": "latent_frames_per_sec", "value": frames / (ms_per_step * 1e-3), "unit": "latent-frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+            "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "Yume-5B-720P single denoise step (WanModel.forward, flag=False), 81-frame 704x1280 "
                                    "latent [48,21,44,80], L=18480 tokens, 512-token text context, t=500",
@@ -295,7 +299,7 @@ def product_arm(args):
             "kernels": kernels,
             "clocks": clocks.summary(),
         }
-    if world == 1 and not args.no_cpu_baseline and rank == 0:
+    if world == 1 and not args.no_cpu_baseline and not args.quick and rank == 0:
         r = cpu_reference_sample(budget_s=25.0, reps=1, warmup=1)
         line["cpu_baseline"] = {"value": frames / r["t_step_s"], "unit": "latent-frames/s", "cores": r["cores"],
                                 "kind": "port", "sample": r["sample"], "ms_per_step": r["t_step_s"] * 1e3}
@@ -312,6 +316,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="yume_b200", choices=["yume_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: exact --warmup, no e2e leg, no CPU baseline")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

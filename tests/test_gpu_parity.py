@@ -314,7 +314,7 @@ def test_fullsize_attention_is_key_permutation_invariant(dev):
     ops.attention(q, k, v, o1, heads)
     perm = torch.randperm(L, generator=g).to(dev)
     ops.attention(q, k[perm].contiguous(), v[perm].contiguous(), o2, heads)
-    assert rel(o1, o2) < 3e-3                          # only the fp32 summation order changes
+    assert rel(o1, o2) < 5e-3                          # two independently bf16-rounded outputs: sqrt(2) x rounding noise
     idx = torch.randint(0, L, (256,), generator=g).to(dev)
     assert rel(o1[idx], _sdpa(q[idx].contiguous(), k, v, heads)) < KERNEL_TOL
 
