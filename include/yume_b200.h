@@ -52,6 +52,9 @@ typedef struct yb_gemm_args {
   int M, N, K;
   int epilogue;    /* YB_EPI_* */
   int block_n;     /* 0 = auto, or 128 / 256 */
+  int n_split;     /* YB_EPI_BF16 only: > 0 => output column block j (width n_split, % 32 == 0) is written at
+                      out + j*split_stride + m*ldo + (n % n_split): the peer-major layout the Ulysses all-to-all sends */
+  long long split_stride;
 } yb_gemm_args;
 int yb_gemm_bf16(const yb_gemm_args* args, void* stream);
 

@@ -32,6 +32,7 @@ class GemmArgs(C.Structure):
         ("gate", C.c_void_p), ("tok_idx", C.c_void_p),
         ("lda", C.c_longlong), ("ldb", C.c_longlong), ("ldo", C.c_longlong), ("gate_ld", C.c_longlong),
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("epilogue", C.c_int), ("block_n", C.c_int),
+        ("n_split", C.c_int), ("split_stride", C.c_longlong),
     ]
 
 

@@ -117,25 +117,31 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t sQ = smem_u32(smem + Cfg::Q_OFF);
       const uint32_t sP = smem_u32(smem + Cfg::P_OFF);
       const uint32_t sKV = smem_u32(smem + Cfg::KV_OFF);
+      // Descriptors differ only in their 14-bit start-address field; build the constant part once and add the
+      // (compile-time) tile offsets: one 64-bit add per operand per MMA keeps the issue loop short.
+      const uint64_t kdesc0 = make_smem_desc_sw128(0, 16, 1024);      // K-major tiles (Q, K, P-in-smem)
+      const uint64_t vdesc0 = make_smem_desc_sw128(0, 16384, 1024);   // MN-major V tile
+      const uint64_t qdesc[2] = {kdesc0 + (sQ >> 4), kdesc0 + ((sQ + ATT_TILE_BYTES) >> 4)};
+      const uint64_t pdesc[2] = {kdesc0 + (sP >> 4), kdesc0 + ((sP + ATT_TILE_BYTES) >> 4)};
       auto issue_S = [&](int X, uint32_t kbase) {
+        const uint64_t kd = kdesc0 + (kbase >> 4);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-          umma_ss(tmem_base + X * 128, make_smem_desc_sw128(sQ + X * ATT_TILE_BYTES + off, 16, 1024),
-                  make_smem_desc_sw128(kbase + off, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
+          const uint32_t off16 = ((kk >> 2) * 16384 + (kk & 3) * 32) >> 4;
+          umma_ss(tmem_base + X * 128, qdesc[X] + off16, kd + off16, idesc_s, kk != 0 ? 1u : 0u);
         }
       };
       auto issue_PV = [&](int X, uint32_t vbase, bool acc) {
+        const uint64_t vd = vdesc0 + (vbase >> 4);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t bdesc = make_smem_desc_sw128(vbase + kk * 2048, 16384, 1024);  // MN-major V tile
+          const uint64_t bdesc = vd + ((kk * 2048) >> 4);
           if (P_TMEM) {
             umma_ts(tmem_base + 256 + X * 128, tmem_base + X * 128 + kk * 8, bdesc, idesc_pv,
                     (acc || kk != 0) ? 1u : 0u);
           } else {
-            const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-            umma_ss(tmem_base + 256 + X * 128, make_smem_desc_sw128(sP + X * ATT_TILE_BYTES + off, 16, 1024), bdesc,
-                    idesc_pv, (acc || kk != 0) ? 1u : 0u);
+            const uint32_t off16 = ((kk >> 2) * 16384 + (kk & 3) * 32) >> 4;
+            umma_ss(tmem_base + 256 + X * 128, pdesc[X] + off16, bdesc, idesc_pv, (acc || kk != 0) ? 1u : 0u);
           }
         }
       };
@@ -156,6 +162,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
         const uint32_t vbase = sKV + slot_v * ATT_TILE_BYTES;
         const uint32_t kbase = sKV + slot_k * ATT_TILE_BYTES;
+#pragma unroll
         for (int X = 0; X < 2; ++X) {
           mbar_wait(&p_full[X], j & 1);
           tc_fence_after();
@@ -201,11 +208,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int i = 0; i < 32; ++i)
             if (c * 32 + i >= kv_rem) s[c][i] = 0xff800000u;  // -inf
       }
-      float mx = -INFINITY;
+      // 8 independent running maxima (a single fmaxf chain is 128 dependent ops of 4-cycle latency each)
+      float mxa[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) mxa[a] = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[c][i]));
+        for (int i = 0; i < 32; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(s[c][i]));
+      const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
+                             fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
       const float ms = mx * sc;
       if (j == 0) {
         m_used = ms;
@@ -228,7 +240,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           m_used = m_new;
         }
       }
-      float lsum = 0.f;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};  // independent partial row sums
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t pk[32];
@@ -237,7 +249,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const int c0 = h * 64 + 2 * i;
           const float p0 = fast_exp2(fmaf(__uint_as_float(s[c0 >> 5][c0 & 31]), sc, -m_used));
           const float p1 = fast_exp2(fmaf(__uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31]), sc, -m_used));
-          lsum += p0 + p1;
+          ls[i & 3] += p0 + p1;
           pk[i] = pack_bf16x2(p0, p1);
         }
         if (P_TMEM) {
@@ -252,7 +264,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
       }
-      l += lsum;
+      l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       if (P_TMEM) {
         tmem_st_wait();
       } else {

@@ -37,6 +37,8 @@ struct GemmParams {
   const float* gate;      // GATE_RES: [U, gate_ld] fp32 table (null => gate = 1)
   long long gate_ld;      // row stride of the gate table
   const int* tok_idx;     // GATE_RES: [M] token -> row of gate table (null => row 0)
+  int n_split;            // bf16 outputs: >0 => column block j (width n_split) is written at out + j*split_stride
+  long long split_stride;
   int num_m_tiles, num_n_tiles;
 };
 
@@ -46,7 +48,9 @@ struct GemmCfg {
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int STAGE_OFF = BAR_OFF + 256;                // epilogue transpose buffers: 4 warps x 32 x 36 floats
+  static constexpr int SMEM_BYTES = STAGE_OFF + 4 * 32 * 36 * 4 + 1024 /*align slack*/;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 512 or 256: power of two
 };
 
@@ -157,7 +161,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ------------------------------- epilogue warps -------------------------------
+    // TMEM -> registers (lane = row) -> per-warp smem transpose (row pitch 36 floats: conflict-free for both the
+    // row-per-lane writes and the row-segment reads) -> global, so that every global access is a full 64/128-byte
+    // row segment shared by 4/8 adjacent lanes instead of 32 different rows per instruction.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    float* stage = reinterpret_cast<float*>(smem + Cfg::STAGE_OFF) + quad * (32 * 36);
+    constexpr bool kBf16Out = (EPI == YB_EPI_BF16 || EPI == YB_EPI_GELU_BF16 || EPI == YB_EPI_GELU_ERF_BF16);
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       int m_tile, n_tile;
@@ -166,88 +175,90 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m_tile * GEMM_BLOCK_M + quad * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row0 = m_tile * GEMM_BLOCK_M + quad * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
-      const float* gate_row = nullptr;
-      if (EPI == YB_EPI_GATE_RES && p.gate != nullptr && row_ok) {
-        const int u = p.tok_idx ? p.tok_idx[row] : 0;
-        gate_row = p.gate + static_cast<long long>(u) * p.gate_ld;
-      }
+      int my_tok = 0;  // gate-table row of tile row `lane`
+      if (EPI == YB_EPI_GATE_RES && p.gate != nullptr && p.tok_idx != nullptr && row0 + lane < p.M)
+        my_tok = p.tok_idx[row0 + lane];
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(t_row + c * 32, r);
         tmem_ld_wait();
         const int col0 = n_tile * BLOCK_N + c * 32;
-        if (row_ok && col0 < p.N) {
-          float v[32];
+        float4* st = reinterpret_cast<float4*>(stage + lane * 36);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (p.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 b = __ldg(b4 + i);
-              v[4 * i + 0] += b.x;
-              v[4 * i + 1] += b.y;
-              v[4 * i + 2] += b.z;
-              v[4 * i + 3] += b.w;
+        for (int i = 0; i < 8; ++i)
+          st[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                              __uint_as_float(r[4 * i + 3]));
+        __syncwarp();
+        if (col0 < p.N) {
+          if (kBf16Out) {
+            const int cq = (lane & 3) * 8;  // this lane's 8 columns of the 32-column chunk
+            float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (p.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq + 4));
+              b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
             }
-          }
-          if (EPI == YB_EPI_BF16 || EPI == YB_EPI_GELU_BF16 || EPI == YB_EPI_GELU_ERF_BF16) {
-            if (EPI == YB_EPI_GELU_BF16) {
+            // optional N-split output (Ulysses layout): column block j of width n_split goes to out + j*split_stride
+            long long col_off = col0 + cq;
+            if (p.n_split > 0) col_off = static_cast<long long>(col0 / p.n_split) * p.split_stride + (col0 % p.n_split) + cq;
+            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + col_off;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
-            }
-            if (EPI == YB_EPI_GELU_ERF_BF16) {
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + (lane >> 2);
+              const float4 a0 = *reinterpret_cast<const float4*>(stage + rr * 36 + cq);
+              const float4 a1 = *reinterpret_cast<const float4*>(stage + rr * 36 + cq + 4);
+              float v[8] = {a0.x + b[0], a0.y + b[1], a0.z + b[2], a0.w + b[3],
+                            a1.x + b[4], a1.y + b[5], a1.z + b[6], a1.w + b[7]};
+              if (EPI == YB_EPI_GELU_BF16) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.7071067811865476f));
-            }
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
-            uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 w;
-              w.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-              w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-              w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-              w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-              o4[i] = w;
-            }
-          } else if (EPI == YB_EPI_F32) {
-            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
-                                                   static_cast<long long>(row) * p.ldo + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {  // YB_EPI_GATE_RES
-            float4* x4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
-                                                   static_cast<long long>(row) * p.ldo + col0);
-            if (gate_row) {
-              const float4* g4 = reinterpret_cast<const float4*>(gate_row + col0);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float4 g = __ldg(g4 + i);
-                float4 x = x4[i];
-                x.x += v[4 * i + 0] * g.x;
-                x.y += v[4 * i + 1] * g.y;
-                x.z += v[4 * i + 2] * g.z;
-                x.w += v[4 * i + 3] * g.w;
-                x4[i] = x;
+                for (int i = 0; i < 8; ++i) v[i] = gelu_tanh(v[i]);
               }
-            } else {
+              if (EPI == YB_EPI_GELU_ERF_BF16) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float4 x = x4[i];
-                x.x += v[4 * i + 0];
-                x.y += v[4 * i + 1];
-                x.z += v[4 * i + 2];
-                x.w += v[4 * i + 3];
-                x4[i] = x;
+                for (int i = 0; i < 8; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.7071067811865476f));
+              }
+              if (row0 + rr < p.M) {
+                uint4 w;
+                w.x = pack_bf16x2(v[0], v[1]);
+                w.y = pack_bf16x2(v[2], v[3]);
+                w.z = pack_bf16x2(v[4], v[5]);
+                w.w = pack_bf16x2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(obase + static_cast<long long>(row0 + rr) * p.ldo) = w;
+              }
+            }
+          } else {
+            const int cq = (lane & 7) * 4;  // this lane's 4 columns
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq));
+            float* obase = reinterpret_cast<float*>(p.out) + col0 + cq;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + (lane >> 3);
+              float4 a = *reinterpret_cast<const float4*>(stage + rr * 36 + cq);
+              a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+              const int tok = __shfl_sync(0xffffffffu, my_tok, rr);
+              if (row0 + rr < p.M) {
+                float4* o4 = reinterpret_cast<float4*>(obase + static_cast<long long>(row0 + rr) * p.ldo);
+                if (EPI == YB_EPI_F32) {
+                  *o4 = a;
+                } else {  // YB_EPI_GATE_RES
+                  float4 x = *o4;
+                  if (p.gate) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + static_cast<long long>(tok) * p.gate_ld + col0 + cq));
+                    x.x += a.x * g.x; x.y += a.y * g.y; x.z += a.z * g.z; x.w += a.w * g.w;
+                  } else {
+                    x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
+                  }
+                  *o4 = x;
+                }
               }
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -310,6 +321,9 @@ extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
   p.gate = static_cast<const float*>(a->gate);
   p.gate_ld = a->gate_ld;
   p.tok_idx = static_cast<const int*>(a->tok_idx);
+  p.n_split = a->n_split;
+  p.split_stride = a->split_stride;
+  if (a->n_split < 0 || (a->n_split > 0 && (a->n_split % 32 != 0 || a->epilogue != YB_EPI_BF16))) return YB_ERR_ARG;
 #define YB_DISPATCH(BN)                                                                  \
   switch (a->epilogue) {                                                                 \
     case YB_EPI_BF16: return launch_gemm<BN, YB_EPI_BF16>(tmA, tmB, p, stream);           \

@@ -75,8 +75,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > YB_WAIT_LIMIT_CYCLES) {
+#ifdef YB_DEBUG_WAIT  // the printf call costs registers and a stack frame in every waiting role; debug builds only
       printf("yb: mbarrier wait timeout block=(%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
              threadIdx.x, smem_u32(bar), parity);
+#endif
       __trap();
     }
   }
