@@ -92,6 +92,8 @@ int yb_rmsnorm_rope(void* qk, long long ld, const void* weight, const void* rope
 int yb_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                  long long ldo, int Lq, int Lk, int heads, float scale, int flags, void* stream);
 #define YB_ATT_P_SMEM 1     /* flags bit 0: stage P through shared memory instead of TMEM (debug variant) */
+#define YB_ATT_EMU_SHIFT 2  /* flags bits 2-3: fraction of exponentials evaluated on the FMA pipe instead of the MUFU:
+                               0 = none, 1 = 1/4, 2 = 1/3, 3 = 1/2 (tuning knob; results agree to < 2e-4 relative) */
 #define YB_ATT_ACCUMULATE 2 /* flags bit 1: out += result (WanI2VCrossAttention sums the text and image branches,
                                wan/modules/model.py:380-387) */
 

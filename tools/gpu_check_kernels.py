@@ -219,7 +219,20 @@ def sec_elementwise():
     print(f"rmsnorm_rope L={L2}: {ms*1e3:.1f} us = {L2*Cdim*4/ms/1e6:.0f} GB/s")
 
 
-SECTIONS = {"probe": sec_probe, "gemm": sec_gemm, "attention": sec_attention, "elementwise": sec_elementwise}
+def sec_atttune():
+    heads, L = 24, 18480
+    qkv = torch.randn(L, 3 * heads * 128, device=dev).bfloat16()
+    q = qkv[:, : heads * 128]; k = qkv[:, heads * 128: 2 * heads * 128]; v = qkv[:, 2 * heads * 128:]
+    out = torch.empty(L, heads * 128, device=dev, dtype=torch.bfloat16)
+    idx = torch.randint(0, L, (256,), device=dev)
+    ref = sdpa_ref(q[idx].contiguous(), k, v, heads)
+    fl = 4.0 * L * L * heads * 128
+    for emu in (0, 1, 2, 3):
+        ms = min(timeit(lambda: ops.attention(q, k, v, out, heads, emu=emu), n=5) for _ in range(3))
+        print(f"attention emu={emu}: {ms:.3f} ms = {fl/ms/1e9:.0f} TF/s   rel/max {rel(out[idx], ref)}")
+
+
+SECTIONS = {"atttune": sec_atttune, "probe": sec_probe, "gemm": sec_gemm, "attention": sec_attention, "elementwise": sec_elementwise}
 if __name__ == "__main__":
     names = sys.argv[1:] or list(SECTIONS)
     print(torch.cuda.get_device_name(0))

@@ -43,7 +43,10 @@ struct AttCfg {
   static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256;
 };
 
-template <bool P_TMEM>
+// EMU: 0 = every exp2 on the MUFU; n > 0 = one of every n probabilities is computed by exp2_poly on the FMA pipe
+// (the MUFU's 16 ex2/clk/SM is exactly co-saturated with the tensor pipe at head_dim 128, so part of the
+// exponentials has to move off it for the MMA to stay fed).
+template <bool P_TMEM, int EMU>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttParams p) {
@@ -247,8 +250,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int c0 = h * 64 + 2 * i;
-          const float p0 = fast_exp2(fmaf(__uint_as_float(s[c0 >> 5][c0 & 31]), sc, -m_used));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31]), sc, -m_used));
+          const float x0 = fmaf(__uint_as_float(s[c0 >> 5][c0 & 31]), sc, -m_used);
+          const float x1 = fmaf(__uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31]), sc, -m_used);
+          const bool emu0 = (EMU > 0) && ((2 * i) % EMU == 0);
+          const bool emu1 = (EMU > 0) && ((2 * i + 1) % EMU == 0);
+          const float p0 = emu0 ? exp2_poly(x0) : fast_exp2(x0);
+          const float p1 = emu1 ? exp2_poly(x1) : fast_exp2(x1);
           ls[i & 3] += p0 + p1;
           pk[i] = pack_bf16x2(p0, p1);
         }
@@ -321,11 +328,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
-template <bool P_TMEM>
+template <bool P_TMEM, int EMU>
 static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                             const AttParams& p, int heads, cudaStream_t stream) {
   using Cfg = AttCfg<P_TMEM>;
-  auto kern = attention_kernel<P_TMEM>;
+  auto kern = attention_kernel<P_TMEM, EMU>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -367,6 +374,11 @@ extern "C" int yb_attention(const void* q, long long ldq, const void* k, long lo
   p.accumulate = (flags & YB_ATT_ACCUMULATE) ? 1 : 0;
   p.scale_log2 = scale * 1.4426950408889634f;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (flags & YB_ATT_P_SMEM) return launch_attention<false>(tmQ, tmK, tmV, p, heads, stream);
-  return launch_attention<true>(tmQ, tmK, tmV, p, heads, stream);
+  if (flags & YB_ATT_P_SMEM) return launch_attention<false, 0>(tmQ, tmK, tmV, p, heads, stream);
+  switch ((flags >> 2) & 3) {
+    case 1: return launch_attention<true, 4>(tmQ, tmK, tmV, p, heads, stream);
+    case 2: return launch_attention<true, 3>(tmQ, tmK, tmV, p, heads, stream);
+    case 3: return launch_attention<true, 2>(tmQ, tmK, tmV, p, heads, stream);
+    default: return launch_attention<true, 0>(tmQ, tmK, tmV, p, heads, stream);
+  }
 }

@@ -234,24 +234,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq));
             float* obase = reinterpret_cast<float*>(p.out) + col0 + cq;
+            // all loads first, then all stores: the residual rows may alias as far as the compiler can tell, so a
+            // load placed after a store would serialise one L2 round trip per row
+            float4 xv[8], gv[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + (lane >> 3);
+              const int tok = __shfl_sync(0xffffffffu, my_tok, rr);
+              xv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              gv[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (EPI == YB_EPI_GATE_RES && row0 + rr < p.M) {
+                xv[it] = *reinterpret_cast<const float4*>(obase + static_cast<long long>(row0 + rr) * p.ldo);
+                if (p.gate)
+                  gv[it] = __ldg(reinterpret_cast<const float4*>(p.gate + static_cast<long long>(tok) * p.gate_ld + col0 + cq));
+              }
+            }
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int rr = it * 4 + (lane >> 3);
               float4 a = *reinterpret_cast<const float4*>(stage + rr * 36 + cq);
               a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-              const int tok = __shfl_sync(0xffffffffu, my_tok, rr);
               if (row0 + rr < p.M) {
                 float4* o4 = reinterpret_cast<float4*>(obase + static_cast<long long>(row0 + rr) * p.ldo);
                 if (EPI == YB_EPI_F32) {
                   *o4 = a;
                 } else {  // YB_EPI_GATE_RES
-                  float4 x = *o4;
-                  if (p.gate) {
-                    const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + static_cast<long long>(tok) * p.gate_ld + col0 + cq));
-                    x.x += a.x * g.x; x.y += a.y * g.y; x.z += a.z * g.z; x.w += a.w * g.w;
-                  } else {
-                    x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
-                  }
+                  float4 x = xv[it];
+                  x.x += a.x * gv[it].x; x.y += a.y * gv[it].y; x.z += a.z * gv[it].z; x.w += a.w * gv[it].w;
                   *o4 = x;
                 }
               }

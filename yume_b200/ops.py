@@ -121,7 +121,7 @@ def rmsnorm_rope(qk: torch.Tensor, weight: torch.Tensor, rope: Optional[torch.Te
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, heads: int,
-              scale: Optional[float] = None, variant: int = 0, accumulate: bool = False) -> torch.Tensor:
+              scale: Optional[float] = None, variant: int = 0, accumulate: bool = False, emu: int = 0) -> torch.Tensor:
     """softmax(q k^T * scale) v, non-causal. q [Lq, heads*128], k/v [Lk, heads*128] bf16 (row strides arbitrary)."""
     global _launches
     for n, t in (("q", q), ("k", k), ("v", v), ("out", out)):
@@ -133,7 +133,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
         scale = 1.0 / math.sqrt(128.0)
     check(_lib.load().yb_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
                                    out.data_ptr(), out.stride(0), Lq, Lk, heads, scale,
-                                   (YB_ATT_P_SMEM if variant == 1 else 0) | (YB_ATT_ACCUMULATE if accumulate else 0),
+                                   (YB_ATT_P_SMEM if variant == 1 else 0) | (YB_ATT_ACCUMULATE if accumulate else 0)
+                                   | ((emu & 3) << 2),
                                    _stream()),
           "yb_attention")
     _launches += 1
