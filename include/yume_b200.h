@@ -91,6 +91,12 @@ int yb_rmsnorm_rope(void* qk, long long ld, const void* weight, const void* rope
  * ------------------------------------------------------------------------------------------- */
 int yb_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                  long long ldo, int Lq, int Lk, int heads, float scale, int flags, void* stream);
+/* Same, with an optional clock64 trace buffer (int64 [32*32]) filled by CTA (1,0) for KV tiles 16..47: per tile
+ * [X*8 + {0: before S wait, 1: S ready, 2: S in registers, 3: row max done, 4: P stored, 5: arrived}] for the softmax
+ * warp of query tile X, and [16 + X*4 + {0: before P wait, 1: P ready, 2: PV+S issued}] for the MMA thread.
+ * Tuning / tests only; pass NULL in production. */
+int yb_attention_ex(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
+                    long long ldo, int Lq, int Lk, int heads, float scale, int flags, void* trace, void* stream);
 #define YB_ATT_P_SMEM 1     /* flags bit 0: stage P through shared memory instead of TMEM (debug variant) */
 #define YB_ATT_EMU_SHIFT 2  /* flags bits 2-3: fraction of exponentials evaluated on the FMA pipe instead of the MUFU:
                                0 = none, 1 = 1/4, 2 = 1/3, 3 = 1/2 (tuning knob; results agree to < 2e-4 relative) */

@@ -30,6 +30,7 @@ struct AttParams {
   int Lq, Lk;
   int nkv;
   int accumulate;    // out += result (sum of two attention branches)
+  long long* trace;  // optional clock64 trace of CTA (1,0), KV tiles 16..47 (tests/tools only; null in production)
   float scale_log2;  // softmax scale * log2(e)
 };
 
@@ -43,7 +44,7 @@ struct AttCfg {
   static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256;
 };
 
-// EMU: 0 = every exp2 on the MUFU; n > 0 = one of every n probabilities is computed by exp2_poly on the FMA pipe
+// EMU: 0 = every exp2 on the MUFU; n > 0 = one of every n probability PAIRS is computed by exp2_poly2 on the FMA pipe
 // (the MUFU's 16 ex2/clk/SM is exactly co-saturated with the tensor pipe at head_dim 128, so part of the
 // exponentials has to move off it for the MMA to stay fed).
 template <bool P_TMEM, int EMU>
@@ -58,8 +59,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* kv_full = q_full + 1;
   uint64_t* kv_empty = kv_full + NS;
   uint64_t* s_full = kv_empty + NS;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* o_done = p_full + 2;
+  uint64_t* p_half = s_full + 2;  // [X][half]: P columns [64*half, 64*half+64) of query tile X are in place
+  uint64_t* o_done = p_half + 4;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -79,7 +80,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_half[2 * i], 128);
+      mbar_init(&p_half[2 * i + 1], 128);
       mbar_init(&o_done[i], 1);
     }
     fence_barrier_init();
@@ -134,10 +136,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           umma_ss(tmem_base + X * 128, qdesc[X] + off16, kd + off16, idesc_s, kk != 0 ? 1u : 0u);
         }
       };
-      auto issue_PV = [&](int X, uint32_t vbase, bool acc) {
+      auto issue_PV = [&](int X, uint32_t vbase, bool acc, int half) {
         const uint64_t vd = vdesc0 + (vbase >> 4);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+        for (int kq = 0; kq < 4; ++kq) {
+          const int kk = half * 4 + kq;
           const uint64_t bdesc = vd + ((kk * 2048) >> 4);
           if (P_TMEM) {
             umma_ts(tmem_base + 256 + X * 128, tmem_base + X * 128 + kk * 8, bdesc, idesc_pv,
@@ -167,15 +170,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t kbase = sKV + slot_k * ATT_TILE_BYTES;
 #pragma unroll
         for (int X = 0; X < 2; ++X) {
-          mbar_wait(&p_full[X], j & 1);
+          long long* tr = (p.trace != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && j >= 16 && j < 48)
+                              ? p.trace + (j - 16) * 32 + 16 + X * 4 : nullptr;
+          if (tr) tr[0] = clock64();
+          mbar_wait(&p_half[2 * X], j & 1);
+          if (tr) tr[1] = clock64();
           tc_fence_after();
-          issue_PV(X, vbase, j > 0);
+          issue_PV(X, vbase, j > 0, 0);             // keys 0..63 of the tile, while the softmax warps finish 64..127
+          mbar_wait(&p_half[2 * X + 1], j & 1);
+          tc_fence_after();
+          issue_PV(X, vbase, true, 1);
           if (has_next) {
             issue_S(X, kbase);
             umma_commit(&s_full[X]);
           } else {
             umma_commit(&o_done[X]);
           }
+          if (tr) tr[2] = clock64();
         }
         umma_commit(&kv_empty[slot_v]);
         if (has_next) umma_commit(&kv_empty[slot_k]);
@@ -195,22 +206,35 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     float l = 0.f;
 
     for (int j = 0; j < nkv; ++j) {
+      long long* tr = (p.trace != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && (warp & 3) == 0 && lane == 0 &&
+                       j >= 16 && j < 48) ? p.trace + (j - 16) * 32 + X * 8 : nullptr;
+      if (tr) tr[0] = clock64();
       mbar_wait(&s_full[X], j & 1);
+      if (tr) tr[1] = clock64();
       tc_fence_after();
+      const int kv_rem = p.Lk - j * 128;
+      if (kv_rem < 128) {
+        // last, partial KV tile (k_lens contract): overwrite the out-of-range columns of S with -inf in TMEM.
+        // Kept as a cold side-effecting loop so the per-element selects are not if-converted into every tile.
+#pragma unroll 1
+        for (int c = kv_rem >> 5; c < 4; ++c) {
+          uint32_t t[32];
+          tmem_ld32(tS + c * 32, t);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= kv_rem) t[i] = 0xff800000u;  // -inf
+          tmem_st32(tS + c * 32, t);
+        }
+        tmem_st_wait();
+      }
       uint32_t s[4][32];
       tmem_ld32(tS + 0, s[0]);
       tmem_ld32(tS + 32, s[1]);
       tmem_ld32(tS + 64, s[2]);
       tmem_ld32(tS + 96, s[3]);
       tmem_ld_wait();
-      const int kv_rem = p.Lk - j * 128;
-      if (kv_rem < 128) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= kv_rem) s[c][i] = 0xff800000u;  // -inf
-      }
+      if (tr) tr[2] = clock64();
       // 8 independent running maxima (a single fmaxf chain is 128 dependent ops of 4-cycle latency each)
       float mxa[8];
 #pragma unroll
@@ -222,6 +246,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
                              fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
       const float ms = mx * sc;
+      if (tr) {
+        asm volatile("" ::"f"(ms));
+        tr[3] = clock64();
+      }
       if (j == 0) {
         m_used = ms;
       } else {
@@ -243,24 +271,37 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           m_used = m_new;
         }
       }
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};  // independent partial row sums
+      // probabilities on packed fp32 pairs: one FFMA2 scales+shifts two scores, one FADD2 accumulates two sums;
+      // every EMU-th pair takes the FMA-pipe polynomial instead of two MUFU.EX2
+      const uint64_t sc2 = f2_pack(sc, sc);
+      const uint64_t negm2 = f2_pack(-m_used, -m_used);
+      uint64_t ls2[2] = {0ull, 0ull};  // two independent packed partial row sums (0ull == (+0.f, +0.f))
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t pk[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int c0 = h * 64 + 2 * i;
-          const float x0 = fmaf(__uint_as_float(s[c0 >> 5][c0 & 31]), sc, -m_used);
-          const float x1 = fmaf(__uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31]), sc, -m_used);
-          const bool emu0 = (EMU > 0) && ((2 * i) % EMU == 0);
-          const bool emu1 = (EMU > 0) && ((2 * i + 1) % EMU == 0);
-          const float p0 = emu0 ? exp2_poly(x0) : fast_exp2(x0);
-          const float p1 = emu1 ? exp2_poly(x1) : fast_exp2(x1);
-          ls[i & 3] += p0 + p1;
+          const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[c0 >> 5][c0 & 31]),
+                                             __uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31])), sc2, negm2);
+          uint64_t p2;
+          float p0, p1;
+          if ((EMU > 0) && (i % EMU == EMU - 1)) {
+            p2 = exp2_poly2(x2);
+            f2_unpack(p2, p0, p1);
+          } else {
+            float x0, x1;
+            f2_unpack(x2, x0, x1);
+            p0 = fast_exp2(x0);
+            p1 = fast_exp2(x1);
+            p2 = f2_pack(p0, p1);
+          }
+          ls2[i & 1] = f2_add(ls2[i & 1], p2);
           pk[i] = pack_bf16x2(p0, p1);
         }
         if (P_TMEM) {
           tmem_st32(tS + h * 32, pk);
+          tmem_st_wait();
         } else {
           // K-major 128B-swizzled slab h of the P tile: row r, 16-byte chunk c -> r*128 + ((c ^ (r & 7)) << 4)
           uint8_t* slab = smem + Cfg::P_OFF + X * ATT_TILE_BYTES + h * 16384 + row_in_tile * 128;
@@ -269,16 +310,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             uint4 w = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
             *reinterpret_cast<uint4*>(slab + ((c ^ (row_in_tile & 7)) << 4)) = w;
           }
+          fence_proxy_async_smem();
         }
+        if (tr) tr[4 + h] = clock64();
+        tc_fence_before();
+        mbar_arrive(&p_half[2 * X + h]);
       }
-      l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      if (P_TMEM) {
-        tmem_st_wait();
-      } else {
-        fence_proxy_async_smem();
+      {
+        float a0, a1, b0, b1;
+        f2_unpack(ls2[0], a0, a1);
+        f2_unpack(ls2[1], b0, b1);
+        l += (a0 + a1) + (b0 + b1);
       }
-      tc_fence_before();
-      mbar_arrive(&p_full[X]);
     }
 
     // epilogue: O / l -> bf16 -> global [Lq, heads*128]
@@ -350,9 +393,19 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, cons
 
 }  // namespace yb
 
+extern "C" int yb_attention_ex(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                               long long ldv, void* out, long long ldo, int Lq, int Lk, int heads, float scale,
+                               int flags, void* trace, void* stream_);
+
 extern "C" int yb_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                             void* out, long long ldo, int Lq, int Lk, int heads, float scale, int flags,
                             void* stream_) {
+  return yb_attention_ex(q, ldq, k, ldk, v, ldv, out, ldo, Lq, Lk, heads, scale, flags, nullptr, stream_);
+}
+
+extern "C" int yb_attention_ex(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                               long long ldv, void* out, long long ldo, int Lq, int Lk, int heads, float scale,
+                               int flags, void* trace, void* stream_) {
   using namespace yb;
   if (!q || !k || !v || !out) return YB_ERR_ARG;
   if (Lq <= 0 || Lk <= 0 || heads <= 0) return YB_ERR_ARG;
@@ -372,6 +425,7 @@ extern "C" int yb_attention(const void* q, long long ldq, const void* k, long lo
   p.Lk = Lk;
   p.nkv = (Lk + 127) / 128;
   p.accumulate = (flags & YB_ATT_ACCUMULATE) ? 1 : 0;
+  p.trace = static_cast<long long*>(trace);
   p.scale_log2 = scale * 1.4426950408889634f;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (flags & YB_ATT_P_SMEM) return launch_attention<false, 0>(tmQ, tmK, tmV, p, heads, stream);

@@ -218,6 +218,54 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// Packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 process two fp32 values per lane per instruction).
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// exp2 of two values on the FMA pipe: same algorithm as exp2_poly, the arithmetic on packed pairs.
+__device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  x2 = f2_pack(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+  const uint64_t kMagic = f2_pack(12582912.0f, 12582912.0f);
+  const uint64_t kNegMagic = f2_pack(-12582912.0f, -12582912.0f);
+  const uint64_t kNegOne = f2_pack(-1.0f, -1.0f);
+  const uint64_t t2 = f2_add(x2, kMagic);
+  const uint64_t r2 = f2_add(t2, kNegMagic);
+  const uint64_t f2 = f2_fma(r2, kNegOne, x2);
+  uint64_t p2 = f2_fma(f2_pack(0.053027521818876266f, 0.053027521818876266f), f2,
+                       f2_pack(0.24221394956111908f, 0.24221394956111908f));
+  p2 = f2_fma(p2, f2, f2_pack(0.6935725808143616f, 0.6935725808143616f));
+  p2 = f2_fma(p2, f2, f2_pack(0.9999590516090393f, 0.9999590516090393f));
+  float p0, p1, t0, t1;
+  f2_unpack(p2, p0, p1);
+  f2_unpack(t2, t0, t1);
+  p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+  return f2_pack(p0, p1);
+}
+
+// bf16x2 pack on the ALU pipe (IADD + PRMT) instead of F2FP, which issues to the same XU pipe as MUFU.EX2.
+// Round-half-up on the magnitude (add 0x8000, truncate): differs from round-to-nearest-even only on exact ties.
+// Inputs must be finite and non-negative (softmax probabilities).
+__device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
+  return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
