@@ -55,6 +55,10 @@ typedef struct yb_gemm_args {
   int n_split;     /* YB_EPI_BF16 only: > 0 => output column block j (width n_split, % 32 == 0) is written at
                       out + j*split_stride + m*ldo + (n % n_split): the peer-major layout the Ulysses all-to-all sends */
   long long split_stride;
+  int a_split;     /* > 0 => A is K-split: logical column k is element (k % a_split) of chunk k / a_split, chunks
+                      a_split_stride elements apart (the [P, L/P, heads/P*128] buffer an Ulysses all-to-all delivers);
+                      a_split % 64 == 0, K % a_split == 0. 0 => ordinary [M, K] matrix. */
+  long long a_split_stride;
 } yb_gemm_args;
 int yb_gemm_bf16(const yb_gemm_args* args, void* stream);
 
@@ -81,6 +85,10 @@ int yb_ln_modulate(const void* x, long long ldx, void* out, long long ldo, int o
  * ------------------------------------------------------------------------------------------- */
 int yb_rmsnorm_rope(void* qk, long long ld, const void* weight, const void* rope, int rope_len, int L, int C, int D,
                     float eps, void* stream);
+/* Same with the C columns of a row stored in pieces: column c is element (c % piece_cols) of piece c / piece_cols,
+ * pieces piece_stride elements apart (peer-major Ulysses send buffer). piece_cols % 8 == 0, C % piece_cols == 0. */
+int yb_rmsnorm_rope_pieces(void* qk, long long ld, int piece_cols, long long piece_stride, const void* weight,
+                           const void* rope, int rope_len, int L, int C, int D, float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Non-causal softmax(Q K^T * scale) V, head_dim 128, bf16 in / bf16 out, fp32 softmax + accumulate.

@@ -335,3 +335,17 @@ def test_fullsize_gemm_linearity_and_row_independence(dev):
     ops.gemm(a1[rows].contiguous(), w, None, sub, ops.YB_EPI_F32)
     assert torch.equal(sub, o1[rows])                                      # a row's result does not depend on its tile
     assert rel(o1[rows], a1[rows].float() @ w.float().t()) < 1e-4
+
+
+def test_ulysses_two_gpus_matches_golden(dev):
+    """Sequence-parallel forward on 2 GPUs (torchrun, NCCL) vs the reference-generated golden outputs."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(root / "tools" / "sp_parity.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

@@ -32,7 +32,7 @@ class GemmArgs(C.Structure):
         ("gate", C.c_void_p), ("tok_idx", C.c_void_p),
         ("lda", C.c_longlong), ("ldb", C.c_longlong), ("ldo", C.c_longlong), ("gate_ld", C.c_longlong),
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("epilogue", C.c_int), ("block_n", C.c_int),
-        ("n_split", C.c_int), ("split_stride", C.c_longlong),
+        ("n_split", C.c_int), ("split_stride", C.c_longlong), ("a_split", C.c_int), ("a_split_stride", C.c_longlong),
     ]
 
 
@@ -43,6 +43,7 @@ SIGNATURES = {
     "yb_gemm_bf16": (_i, [C.POINTER(GemmArgs), _vp]),
     "yb_ln_modulate": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp, _ll, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "yb_rmsnorm_rope": (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "yb_rmsnorm_rope_pieces": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "yb_attention": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _f, _i, _vp]),
     "yb_attention_ex": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _f, _i, _vp, _vp]),
     "yb_patchify": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),

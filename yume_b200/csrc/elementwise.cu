@@ -117,11 +117,18 @@ constexpr int RR_THREADS = 256;
 constexpr int RR_MAX_CHUNK = 4;  // C <= 8192
 
 __global__ void __launch_bounds__(RR_THREADS)
-rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ qk, long long ld, const float* __restrict__ weight,
+rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ qk, long long ld, int piece_cols, long long piece_stride,
+                    const float* __restrict__ weight,
                     const float2* __restrict__ rope, int rope_len, int C, int D, float eps) {
   __shared__ float red[8];
   const int row = blockIdx.x;
-  uint4* xr = reinterpret_cast<uint4*>(qk + static_cast<long long>(row) * ld);
+  __nv_bfloat16* xrow = qk + static_cast<long long>(row) * ld;
+  // chunk idx (8 elements at column idx*8) lives in piece (col / piece_cols) at offset col % piece_cols
+  auto chunk_ptr = [&](int idx) -> uint4* {
+    const int col = idx << 3;
+    const int piece = col / piece_cols;
+    return reinterpret_cast<uint4*>(xrow + piece * piece_stride + (col - piece * piece_cols));
+  };
   const int nchunk = C >> 3;
   uint4 raw[RR_MAX_CHUNK];
   float ss = 0.f;
@@ -129,7 +136,7 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ qk, long long ld, const float* _
   for (int i = 0; i < RR_MAX_CHUNK; ++i) {
     const int idx = threadIdx.x + i * RR_THREADS;
     if (idx < nchunk) {
-      raw[i] = xr[idx];
+      raw[i] = *chunk_ptr(idx);
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -166,7 +173,7 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ qk, long long ld, const float* _
         }
         o[k] = pack_bf16x2(a, b);
       }
-      xr[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+      *chunk_ptr(idx) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 }
@@ -352,15 +359,22 @@ extern "C" int yb_ln_modulate(const void* x, long long ldx, void* out, long long
   return check_launch("ln_modulate");
 }
 
+extern "C" int yb_rmsnorm_rope_pieces(void* qk, long long ld, int piece_cols, long long piece_stride,
+                                      const void* weight, const void* rope, int rope_len, int L, int C, int D,
+                                      float eps, void* stream_) {
+  if (!qk || !weight || L <= 0 || C <= 0 || D <= 0 || piece_cols <= 0) return YB_ERR_ARG;
+  if (C % 8 != 0 || C > RR_THREADS * RR_MAX_CHUNK * 8 || D % 8 != 0 || C % D != 0) return YB_ERR_SHAPE;
+  if (piece_cols % 8 != 0 || C % piece_cols != 0) return YB_ERR_SHAPE;
+  if ((ld % 8) || (piece_stride % 8) || (reinterpret_cast<uintptr_t>(qk) & 0xF)) return YB_ERR_ALIGNMENT;
+  rmsnorm_rope_kernel<<<L, RR_THREADS, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<__nv_bfloat16*>(qk), ld, piece_cols, piece_stride, static_cast<const float*>(weight),
+      static_cast<const float2*>(rope), rope_len, C, D, eps);
+  return check_launch("rmsnorm_rope");
+}
+
 extern "C" int yb_rmsnorm_rope(void* qk, long long ld, const void* weight, const void* rope, int rope_len, int L,
                                int C, int D, float eps, void* stream_) {
-  if (!qk || !weight || L <= 0 || C <= 0 || D <= 0) return YB_ERR_ARG;
-  if (C % 8 != 0 || C > RR_THREADS * RR_MAX_CHUNK * 8 || D % 8 != 0 || C % D != 0) return YB_ERR_SHAPE;
-  if ((ld % 8) || (reinterpret_cast<uintptr_t>(qk) & 0xF)) return YB_ERR_ALIGNMENT;
-  rmsnorm_rope_kernel<<<L, RR_THREADS, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      static_cast<__nv_bfloat16*>(qk), ld, static_cast<const float*>(weight), static_cast<const float2*>(rope), rope_len,
-      C, D, eps);
-  return check_launch("rmsnorm_rope");
+  return yb_rmsnorm_rope_pieces(qk, ld, C, 0, weight, rope, rope_len, L, C, D, eps, stream_);
 }
 
 extern "C" int yb_patchify(const void* x, long long sc, long long sf, long long sh, long long sw, void* out,

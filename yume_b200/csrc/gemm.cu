@@ -37,6 +37,7 @@ struct GemmParams {
   const float* gate;      // GATE_RES: [U, gate_ld] fp32 table (null => gate = 1)
   long long gate_ld;      // row stride of the gate table
   const int* tok_idx;     // GATE_RES: [M] token -> row of gate table (null => row 0)
+  int a_split;            // columns of A per chunk (== K for an ordinary matrix)
   int n_split;            // bf16 outputs: >0 => column block j (width n_split) is written at out + j*split_stride
   long long split_stride;
   int num_m_tiles, num_n_tiles;
@@ -116,7 +117,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BLOCK_K, m_tile * GEMM_BLOCK_M);
+          // A goes through a 3-D map [chunk, row, col]: logical column k lives in chunk k / a_split (one chunk when
+          // the operand is an ordinary matrix; P chunks for the Ulysses-received attention output)
+          const int kcol = kb * GEMM_BLOCK_K;
+          const int chunk = kcol / p.a_split;
+          tma_load_3d(sa, &tmA, &full_bar[stage], kcol - chunk * p.a_split, m_tile * GEMM_BLOCK_M, chunk);
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BLOCK_K, n_tile * BLOCK_N);
           if (++stage == Cfg::STAGES) {
             stage = 0;
@@ -316,7 +321,16 @@ extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int block_n = (a->block_n == 128 || a->block_n == 256) ? a->block_n : ((a->N % 256 == 0 || a->N > 1024) ? 256 : 128);
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_bf16_2d(&tmA, a->A, a->M, a->K, a->lda, GEMM_BLOCK_M, GEMM_BLOCK_K);
+  int a_split = a->K;
+  long long a_chunk_ld = 0;
+  if (a->a_split > 0) {
+    if (a->a_split % GEMM_BLOCK_K != 0 || a->K % a->a_split != 0) return YB_ERR_SHAPE;
+    a_split = a->a_split;
+    a_chunk_ld = a->a_split_stride;
+  }
+  const int a_chunks = a->K / a_split;
+  int rc = make_tmap_bf16_3d(&tmA, a->A, a_chunks, a->M, a_split, a->lda, a_chunks > 1 ? a_chunk_ld : a->lda * (long long)a->M + 8,
+                             GEMM_BLOCK_M, GEMM_BLOCK_K);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, a->B, a->N, a->K, a->ldb, block_n, GEMM_BLOCK_K);
   if (rc) return rc;
@@ -330,6 +344,7 @@ extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
   p.gate = static_cast<const float*>(a->gate);
   p.gate_ld = a->gate_ld;
   p.tok_idx = static_cast<const int*>(a->tok_idx);
+  p.a_split = a_split;
   p.n_split = a->n_split;
   p.split_stride = a->split_stride;
   if (a->n_split < 0 || (a->n_split > 0 && (a->n_split % 32 != 0 || a->epilogue != YB_EPI_BF16))) return YB_ERR_ARG;

@@ -45,6 +45,23 @@ inline int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, u
   return r == CUDA_SUCCESS ? YB_OK : YB_ERR_TENSORMAP;
 }
 
+// 3D bf16 tensor map: [chunks, rows, cols] with row stride `ld` and chunk stride `chunk_ld` (elements),
+// box {box_cols, box_rows, 1}. Used for a K-split A operand: logical column k = chunk * cols + c.
+inline int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t chunks, uint64_t rows, uint64_t cols,
+                             uint64_t ld, uint64_t chunk_ld, uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return YB_ERR_NO_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 0xF) || ((ld * 2) & 0xF) || ((chunk_ld * 2) & 0xF)) return YB_ERR_ALIGNMENT;
+  cuuint64_t gdim[3] = {cols, rows, chunks};
+  cuuint64_t gstride[2] = {ld * 2, chunk_ld * 2};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? YB_OK : YB_ERR_TENSORMAP;
+}
+
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

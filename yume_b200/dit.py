@@ -103,6 +103,21 @@ def framepack_plan(hist: int, branch_hist: int) -> List[_Segment]:
     return segs
 
 
+def sp_qkv_row_order(dim: int, heads: int, world: int) -> Tensor:
+    """Row permutation of the fused [3C, C] q|k|v weight for Ulysses: [peer][part q,k,v][that peer's heads]."""
+    wh = (heads // world) * (dim // heads)
+    return torch.cat([torch.arange(part * dim + p * wh, part * dim + (p + 1) * wh)
+                      for p in range(world) for part in range(3)])
+
+
+def sp_shard(L: int, world: int, rank: int) -> Tuple[int, int, int]:
+    """(rows per rank Lp, first global row, valid rows) of `rank`'s contiguous token shard; L is padded up to
+    world*Lp like the reference pads seq_len (wan23/distributed/sequence_parallel.py:120-122)."""
+    lp = -(-L // world)
+    r0 = rank * lp
+    return lp, r0, max(0, min(L, r0 + lp) - r0)
+
+
 class WanDiT:
     """B200 engine for one WanModel. `variant` is '5b' (wan23 tree) or '14b' (wan tree)."""
 
@@ -122,6 +137,7 @@ class WanDiT:
         self._ws: Dict[Tuple, Tensor] = {}
         self._rope_cache: Dict[Tuple, Tensor] = {}
         self.timer = KernelTimer()          # bench.py switches it on to time individual kernels inside a live step
+        self.sp_group, self.sp_world, self.sp_rank = None, 1, 0
         self._repack(state_dict)
 
     # ------------------------------------------------------------------------------------------------------
@@ -188,6 +204,22 @@ class WanDiT:
             self.blocks.append(blk)
             mods.append(f32(p + ".modulation").reshape(6 * C))
         self.block_mod = torch.stack(mods).contiguous()            # [layers, 6C]
+
+    def enable_sequence_parallel(self, group) -> None:
+        """Shard the token sequence Ulysses-style over `group` (one process per GPU). Builds the peer-major fused
+        q|k|v weight: rows ordered [peer p][q, k, v][heads p*H/P .. (p+1)*H/P) so that the QKV GEMM's `n_split`
+        epilogue emits exactly the chunks the all-to-all sends."""
+        import torch.distributed as dist
+        P = dist.get_world_size(group)
+        if self.heads % P:
+            raise YumeB200Error(f"{self.heads} heads do not divide over {P} ranks")
+        self.sp_group, self.sp_world, self.sp_rank = group, P, dist.get_rank(group)
+        if P == 1:
+            return
+        idx = sp_qkv_row_order(self.dim, self.heads, P).to(self.device)
+        for b in self.blocks:
+            b["w_qkv_sp"] = b["w_qkv"][idx].contiguous()
+            b["b_qkv_sp"] = b["b_qkv"][idx].contiguous()
 
     @classmethod
     def from_module(cls, model: torch.nn.Module, variant: str, device="cuda") -> "WanDiT":
@@ -294,9 +326,50 @@ class WanDiT:
             ops.ln_modulate(h3, out[:n_img], None, None, None, *self.img["ln4"], eps=1e-5)
         return out
 
+    def _self_attention_sp(self, b: dict, h: Tensor, xs: Tensor, m: Tensor, tok_idx: Optional[Tensor], rope: Tensor,
+                           rope_len: int, L_true: int) -> None:
+        """Ulysses self-attention on a token shard (design reference wan23/distributed/ulysses.py:9-47,
+        sequence_parallel.py:147-176). xs/h hold this rank's Lp tokens. Two all-to-alls per block on the
+        head/sequence axis, nothing else is exchanged:
+          QKV GEMM -> peer-major [P, Lp, q|k|v of heads/P] (n_split epilogue, no pack kernel)
+          RMSNorm (spans all heads) + RoPE on the local tokens, before the exchange
+          all-to-all -> [P*Lp tokens, q|k|v of my heads/P] ; attention over all L_true keys for my heads
+          all-to-all -> [P, Lp, heads/P*128]; the o-projection reads it through a K-split 3-D TMA map."""
+        import torch.distributed as dist
+        C, D, P = self.dim, self.head_dim, self.sp_world
+        Hp = self.heads // P
+        Wh, W3 = Hp * D, 3 * Hp * D
+        Lp = xs.shape[0]
+        T = self.timer
+        send = self._buf("sp_qkv_send", (P, Lp, W3), _BF16)
+        recv = self._buf("sp_qkv_recv", (P, Lp, W3), _BF16)
+        T.begin("gemm_qkv")
+        ops.gemm(h, b["w_qkv_sp"], b["b_qkv_sp"], send, ops.YB_EPI_BF16, n_split=W3, split_stride=Lp * W3, shape=(Lp, C))
+        T.end("gemm_qkv")
+        T.begin("rmsnorm_rope")
+        ops.rmsnorm_rope(send[0], b["nq"], rope, D, self.eps, rope_len, pieces=(Lp, C, Wh, Lp * W3))
+        T.end("rmsnorm_rope")
+        ops.rmsnorm_rope(send[0][:, Wh:], b["nk"], rope, D, self.eps, rope_len, pieces=(Lp, C, Wh, Lp * W3))
+        T.begin("sp_all_to_all_qkv")
+        dist.all_to_all_single(recv, send, group=self.sp_group)
+        T.end("sp_all_to_all_qkv")
+        full = recv.view(P * Lp, W3)                            # global token order (rank-major shards)
+        att_send = self._buf("sp_att_send", (P, Lp, Wh), _BF16)
+        att_recv = self._buf("sp_att_recv", (P, Lp, Wh), _BF16)
+        T.begin("self_attention")
+        ops.attention(full[:, :Wh], full[:L_true, Wh:2 * Wh], full[:L_true, 2 * Wh:], att_send.view(P * Lp, Wh), Hp)
+        T.end("self_attention")
+        T.begin("sp_all_to_all_out")
+        dist.all_to_all_single(att_recv, att_send, group=self.sp_group)
+        T.end("sp_all_to_all_out")
+        T.begin("gemm_o")
+        ops.gemm(att_recv, b["w_o"], b["b_o"], xs, ops.YB_EPI_GATE_RES, gate=m[:, 2], tok_idx=tok_idx,
+                 a_split=Wh, a_split_stride=Lp * Wh, shape=(Lp, C))
+        T.end("gemm_o")
+
     def _block(self, i: int, xs: Tensor, mod: Tensor, tok_idx: Optional[Tensor], rope: Tensor, rope_len: int,
-               ctx: Tensor) -> None:
-        """One WanAttentionBlock in place on the fp32 residual stream xs [L, C]."""
+               ctx: Tensor, L_true: Optional[int] = None) -> None:
+        """One WanAttentionBlock in place on the fp32 residual stream xs [L, C] (a token shard under Ulysses)."""
         b, C, H, D = self.blocks[i], self.dim, self.heads, self.head_dim
         L = xs.shape[0]
         m = mod[i]                                             # [U, 6, C]: shift_a, scale_a, gate_a, shift_f, scale_f, gate_f
@@ -308,6 +381,14 @@ class WanDiT:
         T.begin("ln_modulate")
         ops.ln_modulate(xs, h, m[:, 1], m[:, 0], tok_idx, eps=self.eps)
         T.end("ln_modulate")
+        if self.sp_world > 1:
+            self._self_attention_sp(b, h, xs, m, tok_idx, rope, rope_len, L_true if L_true is not None else L)
+        else:
+            self._self_attention_local(b, h, qkv, att, xs, m, tok_idx, rope, rope_len)
+        self._cross_and_ffn(b, xs, h, qkv, att, m, tok_idx, ctx)
+
+    def _self_attention_local(self, b, h, qkv, att, xs, m, tok_idx, rope, rope_len) -> None:
+        C, H, D, T = self.dim, self.heads, self.head_dim, self.timer
         T.begin("gemm_qkv")
         ops.gemm(h, b["w_qkv"], b["b_qkv"], qkv, ops.YB_EPI_BF16)
         T.end("gemm_qkv")
@@ -321,6 +402,10 @@ class WanDiT:
         T.begin("gemm_o")
         ops.gemm(att, b["w_o"], b["b_o"], xs, ops.YB_EPI_GATE_RES, gate=m[:, 2], tok_idx=tok_idx)
         T.end("gemm_o")
+
+    def _cross_and_ffn(self, b, xs, h, qkv, att, m, tok_idx, ctx) -> None:
+        C, H, D, T = self.dim, self.heads, self.head_dim, self.timer
+        L = xs.shape[0]
         # --- cross-attention (no gate, affine norm3) ---
         ops.ln_modulate(xs, h, None, None, None, b["n3w"], b["n3b"], eps=self.eps)
         q2 = qkv[:, :C]
@@ -464,15 +549,40 @@ class WanDiT:
         # ---- context -----------------------------------------------------------------------------------
         ctx = self._context(context.to(device=dev), clip_fea)
 
+        # ---- Ulysses: keep only this rank's contiguous token shard --------------------------------------
+        L_true = L
+        if self.sp_world > 1:
+            import torch.distributed as dist
+            Lp, r0, n_valid = sp_shard(L, self.sp_world, self.sp_rank)
+            xs_full = xs
+            xs = self._buf("xs_shard", (Lp, C), _F32)
+            xs[:n_valid].copy_(xs_full[r0:r0 + n_valid])
+            if n_valid < Lp:
+                xs[n_valid:].zero_()                           # padding tokens (never used as keys: Lk = L_true)
+            if tok_idx is not None:
+                ti = self._buf("tok_idx_shard", (Lp,), torch.int32)
+                ti.zero_()
+                ti[:n_valid].copy_(tok_idx[r0:r0 + n_valid])
+                tok_idx = ti
+            rope = rope[min(r0, rope.shape[0]):]
+            if rope.shape[0] == 0:
+                rope = self._rope_table(rope_segs)[:1]
+            rope_len = max(0, min(rope_len - r0, Lp))
+
         # ---- blocks ------------------------------------------------------------------------------------
         for i in range(self.layers):
-            self._block(i, xs, mod, tok_idx, rope, rope_len, ctx)
+            self._block(i, xs, mod, tok_idx, rope, rope_len, ctx, L_true)
 
         # ---- head + unpatchify (fp32, model.py:336-348, 856-890) -----------------------------------------
-        hn = self._buf("head_in", (L, C), _F32)
+        Lloc = xs.shape[0]
+        hn = self._buf("head_in", (Lloc, C), _F32)
         ops.ln_modulate(xs, hn, head_tab[:, 1], head_tab[:, 0], tok_idx, eps=self.eps)
-        yo = self._buf("head_out", (L, 4 * self.out_dim), _F32)
+        yo = self._buf("head_out", (Lloc, 4 * self.out_dim), _F32)
         ops.linear_f32(hn, self.head_w, self.head_b, yo)
+        if self.sp_world > 1:                                  # one gather of the head output (gather_forward, :140)
+            yo_all = self._buf("head_out_all", (self.sp_world * Lloc, 4 * self.out_dim), _F32)
+            dist.all_gather_into_tensor(yo_all, yo, group=self.sp_group)
+            yo = yo_all
         out = torch.empty(self.out_dim, grid_new[0], grid_new[1] * 2, grid_new[2] * 2, device=dev, dtype=_F32)
         ops.unpatchify(yo[L_hist:], out, grid_new[0], grid_new[1], grid_new[2], 2, 2)
         return out

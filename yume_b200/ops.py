@@ -50,18 +50,23 @@ def _need(t: torch.Tensor, dtype, name: str) -> None:
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, epilogue: int,
-         gate: Optional[torch.Tensor] = None, tok_idx: Optional[torch.Tensor] = None, block_n: int = 0) -> torch.Tensor:
+         gate: Optional[torch.Tensor] = None, tok_idx: Optional[torch.Tensor] = None, block_n: int = 0,
+         n_split: int = 0, split_stride: int = 0, a_split: int = 0, a_split_stride: int = 0,
+         shape: Optional[tuple] = None) -> torch.Tensor:
     """out = epi(a[M,K] @ w[N,K]^T + bias). a, w bf16 (2-D, row stride arbitrary); see include/yume_b200.h."""
     global _launches
     _need(a, torch.bfloat16, "a")
     _need(w, torch.bfloat16, "w")
-    M, K = a.shape
     N, K2 = w.shape
+    if shape is not None:          # split layouts: logical (M, K) given explicitly, a / out are the raw buffers
+        M, K = shape
+    else:
+        M, K = a.shape
     if K2 != K:
         raise YumeB200Error(f"gemm K mismatch: {K} vs {K2}")
     want = torch.bfloat16 if epilogue in (YB_EPI_BF16, YB_EPI_GELU_BF16, YB_EPI_GELU_ERF_BF16) else torch.float32
     _need(out, want, "out")
-    if out.shape[0] != M or out.shape[1] != N:
+    if shape is None and (out.shape[0] != M or out.shape[1] != N):
         raise YumeB200Error(f"gemm out shape {tuple(out.shape)} != ({M}, {N})")
     if bias is not None:
         _need(bias, torch.float32, "bias")
@@ -71,8 +76,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
         _need(tok_idx, torch.int32, "tok_idx")
     args = GemmArgs(
         A=a.data_ptr(), B=w.data_ptr(), bias=_ptr(bias), out=out.data_ptr(), gate=_ptr(gate), tok_idx=_ptr(tok_idx),
-        lda=a.stride(0), ldb=w.stride(0), ldo=out.stride(0), gate_ld=(gate.stride(0) if gate is not None else 0),
-        M=M, N=N, K=K, epilogue=epilogue, block_n=block_n)
+        lda=a.stride(-2), ldb=w.stride(0), ldo=out.stride(-2), gate_ld=(gate.stride(0) if gate is not None else 0),
+        M=M, N=N, K=K, epilogue=epilogue, block_n=block_n, n_split=n_split, split_stride=split_stride,
+        a_split=a_split, a_split_stride=a_split_stride)
     check(_lib.load().yb_gemm_bf16(C.byref(args), _stream()), "yb_gemm_bf16")
     _launches += 1
     return out
@@ -102,20 +108,25 @@ def ln_modulate(x: torch.Tensor, out: torch.Tensor, scale: Optional[torch.Tensor
 
 
 def rmsnorm_rope(qk: torch.Tensor, weight: torch.Tensor, rope: Optional[torch.Tensor], head_dim: int,
-                 eps: float = 1e-6, rope_len: Optional[int] = None) -> torch.Tensor:
+                 eps: float = 1e-6, rope_len: Optional[int] = None, pieces: Optional[tuple] = None) -> torch.Tensor:
     """In place on bf16 rows qk [L, C] (row stride arbitrary): RMSNorm over C, * weight, RoPE with rope f32 [L, D/2, 2]."""
     global _launches
     _need(qk, torch.bfloat16, "qk")
     _need(weight, torch.float32, "weight")
-    L, Cdim = qk.shape
+    if pieces is not None:         # (L, C, piece_cols, piece_stride): qk is the first piece, rows `qk.stride(0)` apart
+        L, Cdim, piece_cols, piece_stride = pieces
+    else:
+        L, Cdim = qk.shape
+        piece_cols, piece_stride = Cdim, 0
     if rope is not None:
         _need(rope, torch.float32, "rope")
         if not rope.is_contiguous() or rope.shape[-1] != 2 or rope.shape[-2] != head_dim // 2:
             raise YumeB200Error("rope must be contiguous f32 [L, D/2, 2]")
         if rope_len is None:
             rope_len = rope.shape[0]
-    check(_lib.load().yb_rmsnorm_rope(qk.data_ptr(), qk.stride(0), weight.data_ptr(), _ptr(rope), rope_len or 0, L,
-                                      Cdim, head_dim, eps, _stream()), "yb_rmsnorm_rope")
+    check(_lib.load().yb_rmsnorm_rope_pieces(qk.data_ptr(), qk.stride(0), piece_cols, piece_stride, weight.data_ptr(),
+                                             _ptr(rope), rope_len or 0, L, Cdim, head_dim, eps, _stream()),
+          "yb_rmsnorm_rope")
     _launches += 1
     return qk
 
