@@ -39,6 +39,8 @@ int yb_abi_version(void);
 #define YB_EPI_GELU_BF16 1 /* out bf16 = gelu_tanh(acc + bias)            (nn.GELU(approximate='tanh')) */
 #define YB_EPI_F32 2       /* out f32  = acc + bias */
 #define YB_EPI_GATE_RES 3  /* out f32 += (acc + bias) * gate[tok_idx[m]][n]   (model.py:304,308,312) */
+#define YB_EPI_RES_BF16 5  /* out bf16 = acc + bias + res[m][n]  (ResnetBlockCausal3D skip add, unet_causal_3d_blocks.py:413;
+                              diffusers Attention residual_connection) */
 #define YB_EPI_GELU_ERF_BF16 4 /* out bf16 = gelu_erf(acc + bias)         (nn.GELU() in MLPProj, wan/modules/model.py:536) */
 
 typedef struct yb_gemm_args {
@@ -59,8 +61,29 @@ typedef struct yb_gemm_args {
                       a_split_stride elements apart (the [P, L/P, heads/P*128] buffer an Ulysses all-to-all delivers);
                       a_split % 64 == 0, K % a_split == 0. 0 => ordinary [M, K] matrix. */
   long long a_split_stride;
+  const void* res;  /* YB_EPI_RES_BF16: bf16 [M, N] residual, row stride res_ld */
+  long long res_ld;
 } yb_gemm_args;
 int yb_gemm_bf16(const yb_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CausalConv3d k=3 (replicate pad W 1,1 / H 1,1 / T 2,0 then Conv3d: hyvideo/vae/unet_causal_3d_blocks.py:48-74) as an
+ * implicit GEMM on tcgen05: out[voxel, co] = bias[co] + sum_{tap,ci} xpad[t+dt, h+dh, w+dw, ci] * w[co, tap*Cp + ci].
+ *   xpad  bf16 [T+2, H+2, W+2, Cp] channels-last, already replicate-padded (yb_vae_pad_act writes it), Cp % 64 == 0
+ *   w     bf16 [Cout, 27*Cp], tap = (dt*3 + dh)*3 + dw (Conv3d weight permuted to [co, kt, kh, kw, ci]); Cout % 32 == 0
+ *   out   [T*H*W, ldo] channels-last; epilogue YB_EPI_BF16, YB_EPI_F32 or YB_EPI_RES_BF16 (+ res bf16 [T*H*W, res_ld])
+ * ------------------------------------------------------------------------------------------- */
+typedef struct yb_conv3d_args {
+  const void* xpad;
+  const void* w;
+  const void* bias; /* f32 [Cout] or NULL */
+  void* out;
+  const void* res;
+  long long ldo, res_ld;
+  int T, H, W, Cp, Cout;
+  int epilogue;
+} yb_conv3d_args;
+int yb_conv3d_causal(const yb_conv3d_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused LayerNorm (no affine, eps) + adaLN modulate -> bf16:  h = LN(x) * (1 + scale) + shift
@@ -140,6 +163,29 @@ int yb_linear_f32_small(const void* in, const void* W, const void* bias, void* o
  * (wan23/modules/model.py:331,346) which the reference runs under autocast(fp32). N % 4 == 0, K % 4 == 0. */
 int yb_linear_f32(const void* in, long long ldi, const void* W, const void* bias, void* out, long long ldo, int M,
                   int N, int K, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * VAE decoder glue (hyvideo/vae; channels-last bf16 activations [T*H*W, C]).
+ * ------------------------------------------------------------------------------------------- */
+/* GroupNorm statistics: stats f64 [G][2] += (sum, sum of squares) per group over x bf16 [N, C] (row stride ld).
+ * Caller zeroes `stats`. (nn.GroupNorm(32, C, eps=1e-6): unet_causal_3d_blocks.py:299,323; vae.py:204) */
+int yb_gn_stats(const void* x, long long ld, void* stats, long long N, int C, int G, void* stream);
+/* One gather pass: [GroupNorm apply (stats, gamma, beta) ->] [SiLU ->] nearest upsample (ft in {1,2}; fh, fw) ->
+ * replicate padding (pad=1: out bf16 [T+2, H+2, W+2, Cp], temporal pad 2 in front; pad=0: out [T, H, W, Cp]) where
+ * (T, H, W) = (ft==2 ? 1+2(Ts-1) : Ts, Hs*fh, Ws*fw) and the first frame is only upsampled spatially
+ * (UpsampleCausal3D :156-163; CausalConv3d padding :61-62,73; ResnetBlockCausal3D norm+act :375-379,401-409). */
+int yb_vae_pad_act(const void* x, long long ldx, int Ts, int Hs, int Ws, int C, void* out, int Cp, int pad, int ft, int fh,
+                   int fw, const void* stats, const void* gamma, const void* beta, int G, float eps, int silu,
+                   void* stream);
+/* Frame-causal softmax of attention scores S f32 [L, ldS] -> P bf16 [L, ldP]: row i keeps keys j < (i/hw + 1)*hw
+ * (prepare_causal_attention_mask :37-45; upcast softmax of the diffusers Attention). */
+int yb_masked_softmax(const void* S, long long ldS, void* P, long long ldP, int L, int hw, void* stream);
+/* z f32 [Cn, N] (NCDHW, N = T*H*W) -> bf16 [N, ldo] channels-last (columns >= Cn zero), and back for f32. */
+int yb_nchw_to_nhwc_bf16(const void* x, void* out, long long N, int Cn, int ldo, void* stream);
+int yb_nhwc_to_nchw_f32(const void* x, long long ldx, void* out, long long N, int Cn, void* stream);
+/* Tile cross-fade (blend_v / blend_h / blend_t, autoencoder_kl_causal_3d.py:343-359) on contiguous f32 tiles:
+ * b[o, y, i] = a[o, ea-ext+y, i] * (1 - y/ext) + b[o, y, i] * (y/ext) for y < ext; a is [outer, ea, inner], b [outer, eb, inner]. */
+int yb_blend(const void* a, void* b, long long outer, int ea, int eb, int ext, long long inner, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Self-test of the tcgen05 building blocks on one 128x128x128 tile (used by tests/, not by the product path).

@@ -349,3 +349,106 @@ def test_ulysses_two_gpus_matches_golden(dev):
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(root / "tools" / "sp_parity.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# hyvideo causal 3D VAE decode
+# ------------------------------------------------------------------------------------------------------------
+VAE_TOL = 3e-2   # ~35 bf16 conv/norm layers deep; fp32 oracle / reference fixtures
+
+
+@pytest.mark.parametrize("T,H,W,ci,co", [(3, 8, 8, 64, 64), (2, 6, 10, 128, 128), (5, 32, 32, 64, 256), (1, 18, 32, 128, 96),
+                                         (9, 4, 4, 64, 32)])
+def test_conv3d_causal_matches_torch(dev, T, H, W, ci, co):
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(T * 100 + H)
+    x = torch.randn(T * H * W, ci, generator=g).to(dev).bfloat16()
+    wt = (torch.randn(co, ci, 3, 3, 3, generator=g) / math.sqrt(27 * ci)).to(dev).bfloat16()
+    b = torch.randn(co, generator=g).to(dev)
+    res = torch.randn(T * H * W, co, generator=g).to(dev).bfloat16()
+    xpad = torch.empty(T + 2, H + 2, W + 2, ci, device=dev, dtype=torch.bfloat16)
+    ops.vae_pad_act(x, (T, H, W), xpad, True)
+    xn = x.float().view(T, H, W, ci).permute(3, 0, 1, 2)[None]
+    want_pad = torch.nn.functional.pad(xn, (1, 1, 1, 1, 2, 0), mode="replicate")
+    assert torch.equal(xpad.float().permute(3, 0, 1, 2)[None], want_pad)            # replicate padding is bit-exact
+    wk = wt.permute(0, 2, 3, 4, 1).reshape(co, 27 * ci).contiguous()
+    out = torch.empty(T * H * W, co, device=dev, dtype=torch.bfloat16)
+    ops.conv3d_causal(xpad, wk, b, out, T, H, W, ops.YB_EPI_RES_BF16, res)
+    ref = torch.nn.functional.conv3d(want_pad, wt.float(), b)[0].permute(1, 2, 3, 0).reshape(T * H * W, co) + res.float()
+    assert rel(out, ref) < KERNEL_TOL
+    o32 = torch.empty(T * H * W, co, device=dev)
+    ops.conv3d_causal(xpad, wk, None, o32, T, H, W, ops.YB_EPI_F32)
+    assert rel(o32, ref - res.float() - b) < 1e-4
+
+
+def test_vae_glue_kernels(dev):
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(8)
+    Ts, Hs, Ws, C, G = 3, 5, 6, 64, 32
+    x = (torch.randn(Ts * Hs * Ws, C, generator=g) * 2 + 0.5).to(dev).bfloat16()
+    gamma, beta = torch.randn(C, generator=g).to(dev), torch.randn(C, generator=g).to(dev)
+    st = ops.gn_stats(x, G)
+    xg = x.float().view(-1, G, C // G)
+    assert torch.allclose(st[:, 0], xg.sum((0, 2)).double(), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[:, 1], (xg * xg).sum((0, 2)).double(), rtol=1e-4)
+    # GroupNorm + SiLU + (2,2,2) upsample + replicate pad in one pass vs the four torch ops
+    T, H, W = 1 + 2 * (Ts - 1), 2 * Hs, 2 * Ws
+    out = torch.empty(T + 2, H + 2, W + 2, C, device=dev, dtype=torch.bfloat16)
+    ops.vae_pad_act(x, (Ts, Hs, Ws), out, True, (2, 2, 2), st, gamma, beta, G, 1e-6, True)
+    xn = x.float().view(Ts, Hs, Ws, C).permute(3, 0, 1, 2)[None]
+    y = torch.nn.functional.silu(torch.nn.functional.group_norm(xn, G, gamma, beta, eps=1e-6))
+    first = torch.nn.functional.interpolate(y[:, :, 0], scale_factor=(2, 2), mode="nearest")[:, :, None]
+    other = torch.nn.functional.interpolate(y[:, :, 1:], scale_factor=(2, 2, 2), mode="nearest")
+    want = torch.nn.functional.pad(torch.cat([first, other], 2), (1, 1, 1, 1, 2, 0), mode="replicate")
+    assert rel(out.float().permute(3, 0, 1, 2)[None], want) < KERNEL_TOL
+    # frame-causal softmax
+    L, hw = 96, 32
+    S = torch.randn(L, L, generator=g).to(dev)
+    P = torch.empty(L, L, device=dev, dtype=torch.bfloat16)
+    ops.masked_softmax(S, P, L, hw)
+    fr = torch.arange(L, device=dev) // hw
+    wantP = torch.where(fr[:, None] >= fr[None, :], S, torch.full_like(S, float("-inf"))).softmax(-1)
+    assert rel(P, wantP) < KERNEL_TOL
+    # cross-fade and layout converters
+    a, b = torch.randn(1, 3, 4, 10, 7, generator=g).to(dev), torch.randn(1, 3, 4, 6, 7, generator=g).to(dev)
+    want = b.clone()
+    for yy in range(4):
+        want[:, :, :, yy] = a[:, :, :, -4 + yy] * (1 - yy / 4) + want[:, :, :, yy] * (yy / 4)
+    assert torch.allclose(ops.blend(a, b, 3, 4), want, atol=1e-6)
+    z = torch.randn(16, 40, generator=g).to(dev)
+    zl = torch.empty(40, 64, device=dev, dtype=torch.bfloat16)
+    ops.nchw_to_nhwc_bf16(z, zl)
+    assert torch.equal(zl[:, :16].float(), z.t().bfloat16().float()) and not zl[:, 16:].any()
+
+
+@pytest.fixture(scope="module")
+def vae_gold(dev, golden_dir):
+    from oracle import hyvae
+    g = torch.load(golden_dir / "hyvae_tiny.pt", weights_only=False)
+    return g, hyvae.make_state_dict(g["seed_w"], **g["cfg"])
+
+
+@pytest.mark.parametrize("case", ["untiled", "untiled_t1", "spatial_tiled", "temporal_spatial_tiled"])
+def test_vae_decode_vs_reference_golden(dev, vae_gold, case):
+    from yume_b200.vae import HyVaeDecoder
+    g, sd = vae_gold
+    c = g["cases"][case]
+    eng = HyVaeDecoder(sd, sample_size=c["sample_size"], sample_tsize=c["sample_tsize"], device=dev, **g["cfg"])
+    eng.enable_tiling(c["tiling"])
+    z = torch.randn(1, 16, c["T"], c["H"], c["W"], generator=torch.Generator().manual_seed(c["seed"]))
+    out = eng.decode(z).cpu()
+    assert tuple(out.shape) == c["shape"]
+    for name, got in (("sample", out[..., ::3, ::3]), ("rowsum", out.sum(-1)), ("colsum", out.sum(-2))):
+        assert float((got - c[name]).norm() / c[name].norm()) < VAE_TOL, name
+
+
+def test_vae_decode_real_width_tile_vs_oracle(dev):
+    """One small tile at the REAL channel widths (128/256/512/512) against the fp32 oracle."""
+    from oracle import hyvae
+    from yume_b200.vae import HyVaeDecoder
+    cfg = dict(block_out_channels=(128, 256, 512, 512), layers_per_block=2, latent_channels=16, out_channels=3)
+    sd = hyvae.make_state_dict(99, **cfg)
+    z = torch.randn(1, 16, 2, 4, 4, generator=torch.Generator().manual_seed(5))
+    want = hyvae.HyVaeOracle(sd, **cfg).decode(z)
+    got = HyVaeDecoder(sd, device=dev, **cfg).decode(z).cpu()
+    assert got.shape == want.shape and rel(got, want) < VAE_TOL

@@ -7,7 +7,7 @@ from pathlib import Path
 
 _LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libyume_b200.so"
 
-YB_EPI_BF16, YB_EPI_GELU_BF16, YB_EPI_F32, YB_EPI_GATE_RES, YB_EPI_GELU_ERF_BF16 = 0, 1, 2, 3, 4
+YB_EPI_BF16, YB_EPI_GELU_BF16, YB_EPI_F32, YB_EPI_GATE_RES, YB_EPI_GELU_ERF_BF16, YB_EPI_RES_BF16 = 0, 1, 2, 3, 4, 5
 YB_ATT_P_SMEM, YB_ATT_ACCUMULATE = 1, 2
 
 _ERRORS = {
@@ -33,6 +33,17 @@ class GemmArgs(C.Structure):
         ("lda", C.c_longlong), ("ldb", C.c_longlong), ("ldo", C.c_longlong), ("gate_ld", C.c_longlong),
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("epilogue", C.c_int), ("block_n", C.c_int),
         ("n_split", C.c_int), ("split_stride", C.c_longlong), ("a_split", C.c_int), ("a_split_stride", C.c_longlong),
+        ("res", C.c_void_p), ("res_ld", C.c_longlong),
+    ]
+
+
+class Conv3dArgs(C.Structure):
+    """Mirror of `struct yb_conv3d_args`."""
+
+    _fields_ = [
+        ("xpad", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p), ("res", C.c_void_p),
+        ("ldo", C.c_longlong), ("res_ld", C.c_longlong),
+        ("T", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cp", C.c_int), ("Cout", C.c_int), ("epilogue", C.c_int),
     ]
 
 
@@ -41,6 +52,13 @@ _vp, _ll, _i, _f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 SIGNATURES = {
     "yb_abi_version": (_i, []),
     "yb_gemm_bf16": (_i, [C.POINTER(GemmArgs), _vp]),
+    "yb_conv3d_causal": (_i, [C.POINTER(Conv3dArgs), _vp]),
+    "yb_gn_stats": (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp]),
+    "yb_vae_pad_act": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _f, _i, _vp]),
+    "yb_masked_softmax": (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp]),
+    "yb_nchw_to_nhwc_bf16": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
+    "yb_nhwc_to_nchw_f32": (_i, [_vp, _ll, _vp, _ll, _i, _vp]),
+    "yb_blend": (_i, [_vp, _vp, _ll, _i, _i, _i, _ll, _vp]),
     "yb_ln_modulate": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp, _ll, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "yb_rmsnorm_rope": (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "yb_rmsnorm_rope_pieces": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp]),

@@ -40,6 +40,13 @@ struct GemmParams {
   int a_split;            // columns of A per chunk (== K for an ordinary matrix)
   int n_split;            // bf16 outputs: >0 => column block j (width n_split) is written at out + j*split_stride
   long long split_stride;
+  const __nv_bfloat16* res;  // YB_EPI_RES_BF16: residual added before the bf16 store, indexed like `out`
+  long long res_ld;
+  // implicit-GEMM causal conv3d (conv != 0): A rows are output voxels, K = 27 taps x cin_chunks x 64 channels,
+  // loaded as 4-D TMA boxes {64, TW, TH, TT} from the replicate-padded channels-last input [T+2, H+2, W+2, Cp]
+  int conv, cin_chunks;
+  int TW, TH, TT, tiles_w, tiles_h;
+  int cT, cH, cW;
   int num_m_tiles, num_n_tiles;
 };
 
@@ -120,8 +127,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // A goes through a 3-D map [chunk, row, col]: logical column k lives in chunk k / a_split (one chunk when
           // the operand is an ordinary matrix; P chunks for the Ulysses-received attention output)
           const int kcol = kb * GEMM_BLOCK_K;
-          const int chunk = kcol / p.a_split;
-          tma_load_3d(sa, &tmA, &full_bar[stage], kcol - chunk * p.a_split, m_tile * GEMM_BLOCK_M, chunk);
+          if (p.conv) {
+            // tap (dt, dh, dw) reads padded voxel (t + dt, h + dh, w + dw): P[tp][hp][wp] = X[max(tp-2,0)][clamp(hp-1)]
+            // [clamp(wp-1)] — temporal pad 2 in front only (causal), replicate everywhere
+            const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
+            const int dt = tap / 9, dh = (tap / 3) % 3, dw = tap % 3;
+            const int per_t = p.tiles_h * p.tiles_w;
+            const int it = m_tile / per_t, rem = m_tile - it * per_t;
+            const int ih = rem / p.tiles_w, iw = rem - ih * p.tiles_w;
+            tma_load_4d(sa, &tmA, &full_bar[stage], cc * GEMM_BLOCK_K, iw * p.TW + dw, ih * p.TH + dh, it * p.TT + dt);
+          } else {
+            const int chunk = kcol / p.a_split;
+            tma_load_3d(sa, &tmA, &full_bar[stage], kcol - chunk * p.a_split, m_tile * GEMM_BLOCK_M, chunk);
+          }
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BLOCK_K, n_tile * BLOCK_N);
           if (++stage == Cfg::STAGES) {
             stage = 0;
@@ -171,7 +189,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // row segment shared by 4/8 adjacent lanes instead of 32 different rows per instruction.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     float* stage = reinterpret_cast<float*>(smem + Cfg::STAGE_OFF) + quad * (32 * 36);
-    constexpr bool kBf16Out = (EPI == YB_EPI_BF16 || EPI == YB_EPI_GELU_BF16 || EPI == YB_EPI_GELU_ERF_BF16);
+    constexpr bool kBf16Out = (EPI == YB_EPI_BF16 || EPI == YB_EPI_GELU_BF16 || EPI == YB_EPI_GELU_ERF_BF16 ||
+                               EPI == YB_EPI_RES_BF16);
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       int m_tile, n_tile;
@@ -180,11 +199,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row0 = m_tile * GEMM_BLOCK_M + quad * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+      // logical output row of tile row (quad*32 + lane): the matrix row, or the voxel index of a conv tile; -1 = none
+      int my_row;
+      {
+        const int r = quad * 32 + lane;
+        if (p.conv) {
+          const int per_t = p.tiles_h * p.tiles_w;
+          const int it = m_tile / per_t, rem = m_tile - it * per_t;
+          const int ih = rem / p.tiles_w, iw = rem - ih * p.tiles_w;
+          const int tw = r % p.TW, th = (r / p.TW) % p.TH, tt = r / (p.TW * p.TH);
+          const int t = it * p.TT + tt, h = ih * p.TH + th, w = iw * p.TW + tw;
+          my_row = (t < p.cT && h < p.cH && w < p.cW) ? (t * p.cH + h) * p.cW + w : -1;
+        } else {
+          const int row = m_tile * GEMM_BLOCK_M + r;
+          my_row = row < p.M ? row : -1;
+        }
+      }
       int my_tok = 0;  // gate-table row of tile row `lane`
-      if (EPI == YB_EPI_GATE_RES && p.gate != nullptr && p.tok_idx != nullptr && row0 + lane < p.M)
-        my_tok = p.tok_idx[row0 + lane];
+      if (EPI == YB_EPI_GATE_RES && p.gate != nullptr && p.tok_idx != nullptr && my_row >= 0)
+        my_tok = p.tok_idx[my_row];
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t r[32];
@@ -210,9 +244,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             long long col_off = col0 + cq;
             if (p.n_split > 0) col_off = static_cast<long long>(col0 / p.n_split) * p.split_stride + (col0 % p.n_split) + cq;
             __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + col_off;
+            uint4 resv[4];
+            if (EPI == YB_EPI_RES_BF16) {  // residual loads first (they may alias the stores for all the compiler knows)
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int rowi = __shfl_sync(0xffffffffu, my_row, it * 8 + (lane >> 2));
+                resv[it] = make_uint4(0u, 0u, 0u, 0u);
+                if (rowi >= 0)
+                  resv[it] = *reinterpret_cast<const uint4*>(p.res + static_cast<long long>(rowi) * p.res_ld + col0 + cq);
+              }
+            }
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
               const int rr = it * 8 + (lane >> 2);
+              const int rowi = __shfl_sync(0xffffffffu, my_row, rr);
               const float4 a0 = *reinterpret_cast<const float4*>(stage + rr * 36 + cq);
               const float4 a1 = *reinterpret_cast<const float4*>(stage + rr * 36 + cq + 4);
               float v[8] = {a0.x + b[0], a0.y + b[1], a0.z + b[2], a0.w + b[3],
@@ -225,13 +270,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.7071067811865476f));
               }
-              if (row0 + rr < p.M) {
+              if (EPI == YB_EPI_RES_BF16) {
+                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&resv[it]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = __bfloat1622float2(rh[i]);
+                  v[2 * i] += f.x;
+                  v[2 * i + 1] += f.y;
+                }
+              }
+              if (rowi >= 0) {
                 uint4 w;
                 w.x = pack_bf16x2(v[0], v[1]);
                 w.y = pack_bf16x2(v[2], v[3]);
                 w.z = pack_bf16x2(v[4], v[5]);
                 w.w = pack_bf16x2(v[6], v[7]);
-                *reinterpret_cast<uint4*>(obase + static_cast<long long>(row0 + rr) * p.ldo) = w;
+                *reinterpret_cast<uint4*>(obase + static_cast<long long>(rowi) * p.ldo) = w;
               }
             }
           } else {
@@ -242,14 +296,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // all loads first, then all stores: the residual rows may alias as far as the compiler can tell, so a
             // load placed after a store would serialise one L2 round trip per row
             float4 xv[8], gv[8];
+            int rowv[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int rr = it * 4 + (lane >> 3);
               const int tok = __shfl_sync(0xffffffffu, my_tok, rr);
+              rowv[it] = __shfl_sync(0xffffffffu, my_row, rr);
               xv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
               gv[it] = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (EPI == YB_EPI_GATE_RES && row0 + rr < p.M) {
-                xv[it] = *reinterpret_cast<const float4*>(obase + static_cast<long long>(row0 + rr) * p.ldo);
+              if (EPI == YB_EPI_GATE_RES && rowv[it] >= 0) {
+                xv[it] = *reinterpret_cast<const float4*>(obase + static_cast<long long>(rowv[it]) * p.ldo);
                 if (p.gate)
                   gv[it] = __ldg(reinterpret_cast<const float4*>(p.gate + static_cast<long long>(tok) * p.gate_ld + col0 + cq));
               }
@@ -259,8 +315,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const int rr = it * 4 + (lane >> 3);
               float4 a = *reinterpret_cast<const float4*>(stage + rr * 36 + cq);
               a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-              if (row0 + rr < p.M) {
-                float4* o4 = reinterpret_cast<float4*>(obase + static_cast<long long>(row0 + rr) * p.ldo);
+              if (rowv[it] >= 0) {
+                float4* o4 = reinterpret_cast<float4*>(obase + static_cast<long long>(rowv[it]) * p.ldo);
                 if (EPI == YB_EPI_F32) {
                   *o4 = a;
                 } else {  // YB_EPI_GATE_RES
@@ -301,7 +357,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
     }
     attr_set = true;
   }
-  p.num_m_tiles = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  if (!p.conv) p.num_m_tiles = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
@@ -316,7 +372,8 @@ extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
   if (!a || !a->A || !a->B || !a->out) return YB_ERR_ARG;
   if (a->M <= 0 || a->N <= 0 || a->K <= 0) return YB_ERR_ARG;
   if (a->N % 32 != 0 || a->K % 8 != 0) return YB_ERR_SHAPE;
-  if (a->epilogue < 0 || a->epilogue > YB_EPI_GELU_ERF_BF16) return YB_ERR_ARG;
+  if (a->epilogue < 0 || a->epilogue > YB_EPI_RES_BF16) return YB_ERR_ARG;
+  if (a->epilogue == YB_EPI_RES_BF16 && (!a->res || (a->res_ld % 8))) return YB_ERR_ARG;
   if ((a->lda % 8) || (a->ldb % 8) || (a->ldo % 8) || (reinterpret_cast<uintptr_t>(a->out) & 0xF)) return YB_ERR_ALIGNMENT;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int block_n = (a->block_n == 128 || a->block_n == 256) ? a->block_n : ((a->N % 256 == 0 || a->N > 1024) ? 256 : 128);
@@ -345,6 +402,9 @@ extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
   p.gate_ld = a->gate_ld;
   p.tok_idx = static_cast<const int*>(a->tok_idx);
   p.a_split = a_split;
+  p.res = static_cast<const __nv_bfloat16*>(a->res);
+  p.res_ld = a->res_ld;
+  p.conv = 0;
   p.n_split = a->n_split;
   p.split_stride = a->split_stride;
   if (a->n_split < 0 || (a->n_split > 0 && (a->n_split % 32 != 0 || a->epilogue != YB_EPI_BF16))) return YB_ERR_ARG;
@@ -354,6 +414,7 @@ extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
     case YB_EPI_GELU_BF16: return launch_gemm<BN, YB_EPI_GELU_BF16>(tmA, tmB, p, stream); \
     case YB_EPI_F32: return launch_gemm<BN, YB_EPI_F32>(tmA, tmB, p, stream);             \
     case YB_EPI_GELU_ERF_BF16: return launch_gemm<BN, YB_EPI_GELU_ERF_BF16>(tmA, tmB, p, stream); \
+    case YB_EPI_RES_BF16: return launch_gemm<BN, YB_EPI_RES_BF16>(tmA, tmB, p, stream);   \
     default: return launch_gemm<BN, YB_EPI_GATE_RES>(tmA, tmB, p, stream);                \
   }
   if (block_n == 256) {
@@ -362,4 +423,57 @@ extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
     YB_DISPATCH(128)
   }
 #undef YB_DISPATCH
+}
+
+
+// Causal 3x3x3 conv (replicate padding) as an implicit GEMM on the same kernel. See include/yume_b200.h.
+extern "C" int yb_conv3d_causal(const yb_conv3d_args* a, void* stream_) {
+  using namespace yb;
+  if (!a || !a->xpad || !a->w || !a->out) return YB_ERR_ARG;
+  if (a->T <= 0 || a->H <= 0 || a->W <= 0 || a->Cp <= 0 || a->Cout <= 0) return YB_ERR_ARG;
+  if (a->Cp % 64 != 0 || a->Cout % 32 != 0) return YB_ERR_SHAPE;
+  if ((a->ldo % 8) || (reinterpret_cast<uintptr_t>(a->out) & 0xF)) return YB_ERR_ALIGNMENT;
+  if (a->epilogue != YB_EPI_BF16 && a->epilogue != YB_EPI_F32 && a->epilogue != YB_EPI_RES_BF16) return YB_ERR_ARG;
+  if (a->epilogue == YB_EPI_RES_BF16 && (!a->res || (a->res_ld % 8))) return YB_ERR_ARG;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  auto pow2_ge = [](int v) { int p = 1; while (p < v) p <<= 1; return p; };
+  GemmParams p;
+  p.TW = pow2_ge(a->W) < 128 ? pow2_ge(a->W) : 128;
+  p.TH = pow2_ge(a->H) < 128 / p.TW ? pow2_ge(a->H) : 128 / p.TW;
+  p.TT = 128 / (p.TW * p.TH);
+  p.tiles_w = (a->W + p.TW - 1) / p.TW;
+  p.tiles_h = (a->H + p.TH - 1) / p.TH;
+  const int tiles_t = (a->T + p.TT - 1) / p.TT;
+  p.conv = 1;
+  p.cin_chunks = a->Cp / 64;
+  p.cT = a->T; p.cH = a->H; p.cW = a->W;
+  p.M = a->T * a->H * a->W;
+  p.N = a->Cout;
+  p.K = 27 * a->Cp;
+  p.num_m_tiles = tiles_t * p.tiles_h * p.tiles_w;
+  p.bias = static_cast<const float*>(a->bias);
+  p.out = a->out;
+  p.ldo = a->ldo;
+  p.gate = nullptr; p.gate_ld = 0; p.tok_idx = nullptr;
+  p.a_split = p.K; p.n_split = 0; p.split_stride = 0;
+  p.res = static_cast<const __nv_bfloat16*>(a->res);
+  p.res_ld = a->res_ld;
+  const int block_n = (a->Cout % 256 == 0) ? 256 : 128;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_4d(&tmA, a->xpad, a->T + 2, a->H + 2, a->W + 2, a->Cp, p.TT, p.TH, p.TW, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, a->w, a->Cout, 27ull * a->Cp, 27ull * a->Cp, block_n, GEMM_BLOCK_K);
+  if (rc) return rc;
+#define YB_CONV_DISPATCH(BN)                                                                 \
+  switch (a->epilogue) {                                                                     \
+    case YB_EPI_BF16: return launch_gemm<BN, YB_EPI_BF16>(tmA, tmB, p, stream);               \
+    case YB_EPI_F32: return launch_gemm<BN, YB_EPI_F32>(tmA, tmB, p, stream);                 \
+    default: return launch_gemm<BN, YB_EPI_RES_BF16>(tmA, tmB, p, stream);                    \
+  }
+  if (block_n == 256) {
+    YB_CONV_DISPATCH(256)
+  } else {
+    YB_CONV_DISPATCH(128)
+  }
+#undef YB_CONV_DISPATCH
 }

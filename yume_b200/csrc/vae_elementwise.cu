@@ -1,0 +1,285 @@
+// vae_elementwise.cu — the HBM-bound glue of the causal 3D VAE decoder (hyvideo/vae), channels-last bf16:
+//   gn_stats          GroupNorm statistics (fp32 partials -> fp64 atomics)
+//   pad_act           GroupNorm-apply + SiLU + nearest upsample + replicate padding in ONE gather pass that writes the
+//                     padded input of the next implicit-GEMM conv (the reference runs GroupNorm, SiLU, interpolate,
+//                     F.pad as four separate full-tensor passes: unet_causal_3d_blocks.py:72,144-174,375-379)
+//   masked_softmax    frame-causal softmax of the mid-block attention scores (:37-45, diffusers Attention)
+//   layout converters and the tile cross-fade (autoencoder_kl_causal_3d.py:343-359)
+#include "yb_host.h"
+#include "yb_ptx.cuh"
+
+namespace yb {
+
+// ---------------------------------------------------------------------------------------------------------
+// GroupNorm statistics: x bf16 [N, C] (row stride ld) -> stats f64 [G][2] += (sum, sum of squares).
+// Thread owns one 8-channel chunk and strides over voxels; per-channel fp32 partials -> smem per-group -> fp64 atomics.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ld, double* __restrict__ stats, long long N, int C, int G) {
+  __shared__ float sg[64][2];
+  const int chunks = C >> 3;                 // 8-channel chunks per voxel
+  const int vox_per_block = 256 / chunks;    // voxels handled per block iteration (chunks <= 256)
+  const int tid = threadIdx.x;
+  if (tid < 64) sg[tid][0] = sg[tid][1] = 0.f;
+  __syncthreads();
+  const int cg = C / G;                      // channels per group
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (tid < chunks * vox_per_block) {
+    const int chunk = tid % chunks;
+    for (long long v = static_cast<long long>(blockIdx.x) * vox_per_block + tid / chunks; v < N;
+         v += static_cast<long long>(gridDim.x) * vox_per_block) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(x + v * ld + chunk * 8);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h[k]);
+        s[2 * k] += f.x; q[2 * k] += f.x * f.x;
+        s[2 * k + 1] += f.y; q[2 * k + 1] += f.y * f.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (chunk * 8 + i) / cg;
+      atomicAdd(&sg[g][0], s[i]);
+      atomicAdd(&sg[g][1], q[i]);
+    }
+  }
+  __syncthreads();
+  if (tid < G) {
+    atomicAdd(&stats[2 * tid], static_cast<double>(sg[tid][0]));
+    atomicAdd(&stats[2 * tid + 1], static_cast<double>(sg[tid][1]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pad_act: out[tp,hp,wp,:] = act(gn(x[src(tp,hp,wp),:])), written to the replicate-padded (pad=1: [T+2,H+2,W+2,Cp]) or
+// plain (pad=0: [T,H,W,Cp]) channels-last buffer. T,H,W are the OUTPUT dims (after the optional nearest upsample by
+// (ft,fh,fw) of the source [Ts,Hs,Ws]); first frame is upsampled only spatially (UpsampleCausal3D, :156-163).
+// Channels C..Cp-1 are written as zero.
+// ---------------------------------------------------------------------------------------------------------
+struct PadActParams {
+  const __nv_bfloat16* x;
+  long long ldx;
+  __nv_bfloat16* out;
+  const double* stats;   // null => no normalisation
+  const float* gamma;
+  const float* beta;
+  int Ts, Hs, Ws, C, Cp, G;
+  int T, H, W, ft, fh, fw;
+  int pad, silu;
+  float eps;
+  double inv_count;      // 1 / (Ts*Hs*Ws*C/G)
+};
+
+__global__ void __launch_bounds__(256) pad_act_kernel(const PadActParams p) {
+  const int chunks = p.Cp >> 3;
+  const int Tp = p.T + 2 * p.pad, Hp = p.H + 2 * p.pad, Wp = p.W + 2 * p.pad;
+  const long long total = static_cast<long long>(Tp) * Hp * Wp * chunks;
+  const int cg = p.G > 0 ? p.C / p.G : 1;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int chunk = static_cast<int>(i % chunks);
+    long long v = i / chunks;
+    const int wp = static_cast<int>(v % Wp);
+    v /= Wp;
+    const int hp = static_cast<int>(v % Hp);
+    const int tp = static_cast<int>(v / Hp);
+    // output (unpadded) coordinate, clamped = replicate padding; temporal pad is 2 frames in FRONT only (causal)
+    int t = p.pad ? max(tp - 2, 0) : tp;
+    int h = p.pad ? min(max(hp - 1, 0), p.H - 1) : hp;
+    int w = p.pad ? min(max(wp - 1, 0), p.W - 1) : wp;
+    if (p.ft == 2) t = (t == 0) ? 0 : 1 + ((t - 1) >> 1);
+    h /= p.fh;
+    w /= p.fw;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    const int c0 = chunk * 8;
+    if (c0 < p.C) {
+      const long long src = (static_cast<long long>(t) * p.Hs + h) * p.Ws + w;
+      const uint4 raw = *reinterpret_cast<const uint4*>(p.x + src * p.ldx + c0);
+      if (p.stats == nullptr && !p.silu) {
+        o = raw;
+      } else {
+        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 t2 = __bfloat1622float2(hh[k]);
+          f[2 * k] = t2.x;
+          f[2 * k + 1] = t2.y;
+        }
+        if (p.stats) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int g = (c0 + k) / cg;
+            const double mean = p.stats[2 * g] * p.inv_count;
+            const double var = p.stats[2 * g + 1] * p.inv_count - mean * mean;
+            const float rstd = rsqrtf(static_cast<float>(var) + p.eps);
+            f[k] = (f[k] - static_cast<float>(mean)) * rstd * __ldg(p.gamma + c0 + k) + __ldg(p.beta + c0 + k);
+          }
+        }
+        if (p.silu) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = f[k] / (1.f + __expf(-f[k]));
+        }
+        o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      }
+    }
+    *reinterpret_cast<uint4*>(p.out + i * 8) = o;
+  }
+}
+
+// frame-causal softmax: S f32 [L, ldS] -> P bf16 [L, ldP]; row i keeps keys j < (i / hw + 1) * hw, others become 0
+__global__ void __launch_bounds__(256)
+masked_softmax_kernel(const float* __restrict__ S, long long ldS, __nv_bfloat16* __restrict__ P, long long ldP, int L,
+                      int hw) {
+  __shared__ float red[8];
+  const int row = blockIdx.x;
+  const int nvalid = min(L, (row / hw + 1) * hw);
+  const float* s = S + static_cast<long long>(row) * ldS;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < nvalid; j += 256) mx = fmaxf(mx, s[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < nvalid; j += 256) sum += __expf(s[j] - mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  __nv_bfloat16* pr = P + static_cast<long long>(row) * ldP;
+  for (int j = threadIdx.x; j < ldP; j += 256)
+    pr[j] = __float2bfloat16_rn(j < nvalid ? __expf(s[j] - mx) * inv : 0.f);
+}
+
+// z f32 [Cn, N] (NCDHW, N = T*H*W) -> bf16 [N, ldo] channels-last, columns >= Cn zero
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long N, int Cn,
+                                    int ldo) {
+  const long long total = N * ldo;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % ldo);
+    const long long v = i / ldo;
+    out[i] = __float2bfloat16_rn(c < Cn ? x[static_cast<long long>(c) * N + v] : 0.f);
+  }
+}
+
+// x f32 [N, ldx] channels-last -> out f32 [Cn, N]
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, long long ldx, float* __restrict__ out, long long N,
+                                    int Cn) {
+  const long long total = N * Cn;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long v = i % N;
+    const int c = static_cast<int>(i / N);
+    out[i] = x[v * ldx + c];
+  }
+}
+
+// cross-fade along one axis of contiguous f32 [C, T, H, W] tiles (blend_v / blend_h / blend_t):
+//   b[.., y, ..] = a[.., ea - ext + y, ..] * (1 - y/ext) + b[.., y, ..] * (y/ext)   for y < ext
+// a has extent `ea` on the blend axis, b has `eb`; all other extents equal. outer/inner: product of the dims before /
+// after the axis.
+__global__ void blend_kernel(const float* __restrict__ a, float* __restrict__ b, long long outer, int ea, int eb, int ext,
+                             long long inner, long long a_outer_stride, long long b_outer_stride) {
+  const long long total = outer * ext * inner;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long in = i % inner;
+    const int y = static_cast<int>((i / inner) % ext);
+    const long long o = i / (inner * ext);
+    const float wb = static_cast<float>(y) / static_cast<float>(ext);
+    const float av = a[o * a_outer_stride + static_cast<long long>(ea - ext + y) * inner + in];
+    float* bp = b + o * b_outer_stride + static_cast<long long>(y) * inner + in;
+    *bp = av * (1.f - wb) + *bp * wb;
+  }
+}
+
+inline int grid_for(long long total) {
+  long long b = (total + 255) / 256;
+  const long long cap = 148LL * 16;
+  return static_cast<int>(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+extern "C" int yb_gn_stats(const void* x, long long ld, void* stats, long long N, int C, int G, void* stream_) {
+  if (!x || !stats || N <= 0 || C <= 0 || G <= 0) return YB_ERR_ARG;
+  if (C % 8 != 0 || C % G != 0 || C > 2048 || G > 64) return YB_ERR_SHAPE;
+  if ((ld % 8) || (reinterpret_cast<uintptr_t>(x) & 0xF)) return YB_ERR_ALIGNMENT;
+  const int vox_per_block = 256 / (C / 8);
+  long long blocks = (N + vox_per_block - 1) / vox_per_block;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  gn_stats_kernel<<<static_cast<int>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(x), ld, static_cast<double*>(stats), N, C, G);
+  return check_launch("gn_stats");
+}
+
+extern "C" int yb_vae_pad_act(const void* x, long long ldx, int Ts, int Hs, int Ws, int C, void* out, int Cp, int pad,
+                              int ft, int fh, int fw, const void* stats, const void* gamma, const void* beta, int G,
+                              float eps, int silu, void* stream_) {
+  if (!x || !out || Ts <= 0 || Hs <= 0 || Ws <= 0 || C <= 0) return YB_ERR_ARG;
+  if (C % 8 != 0 || Cp % 8 != 0 || Cp < C || (ft != 1 && ft != 2) || fh < 1 || fw < 1) return YB_ERR_SHAPE;
+  if (stats && (!gamma || !beta || G <= 0 || C % G != 0)) return YB_ERR_ARG;
+  if ((ldx % 8) || (reinterpret_cast<uintptr_t>(x) & 0xF) || (reinterpret_cast<uintptr_t>(out) & 0xF)) return YB_ERR_ALIGNMENT;
+  PadActParams p;
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.ldx = ldx;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.stats = static_cast<const double*>(stats);
+  p.gamma = static_cast<const float*>(gamma);
+  p.beta = static_cast<const float*>(beta);
+  p.Ts = Ts; p.Hs = Hs; p.Ws = Ws; p.C = C; p.Cp = Cp; p.G = G;
+  p.T = (ft == 2) ? 1 + 2 * (Ts - 1) : Ts;
+  p.H = Hs * fh; p.W = Ws * fw;
+  p.ft = ft; p.fh = fh; p.fw = fw;
+  p.pad = pad ? 1 : 0; p.silu = silu;
+  p.eps = eps;
+  p.inv_count = stats ? 1.0 / (static_cast<double>(Ts) * Hs * Ws * (C / G)) : 0.0;
+  const long long total = static_cast<long long>(p.T + 2 * p.pad) * (p.H + 2 * p.pad) * (p.W + 2 * p.pad) * (Cp / 8);
+  pad_act_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(p);
+  return check_launch("vae_pad_act");
+}
+
+extern "C" int yb_masked_softmax(const void* S, long long ldS, void* P, long long ldP, int L, int hw, void* stream_) {
+  if (!S || !P || L <= 0 || hw <= 0 || ldP < L || ldS < L) return YB_ERR_ARG;
+  masked_softmax_kernel<<<L, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const float*>(S), ldS, static_cast<__nv_bfloat16*>(P), ldP, L, hw);
+  return check_launch("masked_softmax");
+}
+
+extern "C" int yb_nchw_to_nhwc_bf16(const void* x, void* out, long long N, int Cn, int ldo, void* stream_) {
+  if (!x || !out || N <= 0 || Cn <= 0 || ldo < Cn) return YB_ERR_ARG;
+  nchw_to_nhwc_kernel<<<grid_for(N * ldo), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), N, Cn, ldo);
+  return check_launch("nchw_to_nhwc");
+}
+
+extern "C" int yb_nhwc_to_nchw_f32(const void* x, long long ldx, void* out, long long N, int Cn, void* stream_) {
+  if (!x || !out || N <= 0 || Cn <= 0 || ldx < Cn) return YB_ERR_ARG;
+  nhwc_to_nchw_kernel<<<grid_for(N * Cn), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const float*>(x), ldx, static_cast<float*>(out), N, Cn);
+  return check_launch("nhwc_to_nchw");
+}
+
+extern "C" int yb_blend(const void* a, void* b, long long outer, int ea, int eb, int ext, long long inner,
+                        void* stream_) {
+  if (!a || !b || outer <= 0 || ext <= 0 || inner <= 0 || ext > ea || ext > eb) return YB_ERR_ARG;
+  blend_kernel<<<grid_for(outer * ext * inner), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const float*>(a), static_cast<float*>(b), outer, ea, eb, ext, inner,
+      static_cast<long long>(ea) * inner, static_cast<long long>(eb) * inner);
+  return check_launch("blend");
+}

@@ -62,6 +62,22 @@ inline int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t chunks,
   return r == CUDA_SUCCESS ? YB_OK : YB_ERR_TENSORMAP;
 }
 
+// 4D bf16 tensor map over a dense channels-last volume [T, H, W, C], box {bc, bw, bh, bt} (conv3d A operand).
+inline int make_tmap_bf16_4d(CUtensorMap* tm, const void* base, uint64_t T, uint64_t H, uint64_t W, uint64_t C,
+                             uint32_t bt, uint32_t bh, uint32_t bw, uint32_t bc) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return YB_ERR_NO_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 0xF) || ((C * 2) & 0xF)) return YB_ERR_ALIGNMENT;
+  cuuint64_t gdim[4] = {C, W, H, T};
+  cuuint64_t gstride[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {bc, bw, bh, bt};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? YB_OK : YB_ERR_TENSORMAP;
+}
+
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import (YB_ATT_ACCUMULATE, YB_ATT_P_SMEM, YB_EPI_BF16, YB_EPI_F32, YB_EPI_GATE_RES, YB_EPI_GELU_BF16,
-                   YB_EPI_GELU_ERF_BF16, GemmArgs, YumeB200Error, check)
+                   YB_EPI_GELU_ERF_BF16, YB_EPI_RES_BF16, Conv3dArgs, GemmArgs, YumeB200Error, check)
 
 __all__ = [
     "gemm", "ln_modulate", "rmsnorm_rope", "attention", "patchify", "unpatchify", "sinusoidal",
@@ -52,7 +52,7 @@ def _need(t: torch.Tensor, dtype, name: str) -> None:
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, epilogue: int,
          gate: Optional[torch.Tensor] = None, tok_idx: Optional[torch.Tensor] = None, block_n: int = 0,
          n_split: int = 0, split_stride: int = 0, a_split: int = 0, a_split_stride: int = 0,
-         shape: Optional[tuple] = None) -> torch.Tensor:
+         shape: Optional[tuple] = None, res: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = epi(a[M,K] @ w[N,K]^T + bias). a, w bf16 (2-D, row stride arbitrary); see include/yume_b200.h."""
     global _launches
     _need(a, torch.bfloat16, "a")
@@ -64,7 +64,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
         M, K = a.shape
     if K2 != K:
         raise YumeB200Error(f"gemm K mismatch: {K} vs {K2}")
-    want = torch.bfloat16 if epilogue in (YB_EPI_BF16, YB_EPI_GELU_BF16, YB_EPI_GELU_ERF_BF16) else torch.float32
+    want = torch.bfloat16 if epilogue in (YB_EPI_BF16, YB_EPI_GELU_BF16, YB_EPI_GELU_ERF_BF16, YB_EPI_RES_BF16) else torch.float32
+    if res is not None:
+        _need(res, torch.bfloat16, "res")
     _need(out, want, "out")
     if shape is None and (out.shape[0] != M or out.shape[1] != N):
         raise YumeB200Error(f"gemm out shape {tuple(out.shape)} != ({M}, {N})")
@@ -78,7 +80,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
         A=a.data_ptr(), B=w.data_ptr(), bias=_ptr(bias), out=out.data_ptr(), gate=_ptr(gate), tok_idx=_ptr(tok_idx),
         lda=a.stride(-2), ldb=w.stride(0), ldo=out.stride(-2), gate_ld=(gate.stride(0) if gate is not None else 0),
         M=M, N=N, K=K, epilogue=epilogue, block_n=block_n, n_split=n_split, split_stride=split_stride,
-        a_split=a_split, a_split_stride=a_split_stride)
+        a_split=a_split, a_split_stride=a_split_stride, res=_ptr(res),
+        res_ld=(res.stride(-2) if res is not None else 0))
     check(_lib.load().yb_gemm_bf16(C.byref(args), _stream()), "yb_gemm_bf16")
     _launches += 1
     return out
@@ -238,3 +241,110 @@ def umma_probe(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
     d = torch.empty(128, 128, device=a.device, dtype=torch.float32)
     check(_lib.load().yb_umma_probe(a.data_ptr(), b.data_ptr(), d.data_ptr(), mode, _stream()), "yb_umma_probe")
     return d
+
+
+# ------------------------------------------------------------------------------------------------------------
+# VAE decoder ops (hyvideo/vae)
+# ------------------------------------------------------------------------------------------------------------
+YB_EPI_RES_BF16 = YB_EPI_RES_BF16
+
+
+def conv3d_causal(xpad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, T: int, H: int,
+                  W: int, epilogue: int = YB_EPI_BF16, res: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """xpad bf16 [T+2, H+2, W+2, Cp] (replicate padded, channels last), w bf16 [Cout, 27*Cp], out [T*H*W, >=Cout]."""
+    global _launches
+    _need(xpad, torch.bfloat16, "xpad")
+    _need(w, torch.bfloat16, "w")
+    Cp = xpad.shape[-1]
+    if tuple(xpad.shape[:3]) != (T + 2, H + 2, W + 2) or not xpad.is_contiguous() or w.shape[1] != 27 * Cp or not w.is_contiguous():
+        raise YumeB200Error("conv3d_causal: bad padded input / weight layout")
+    _need(out, torch.float32 if epilogue == YB_EPI_F32 else torch.bfloat16, "out")
+    if res is not None:
+        _need(res, torch.bfloat16, "res")
+    args = Conv3dArgs(xpad=xpad.data_ptr(), w=w.data_ptr(), bias=_ptr(bias), out=out.data_ptr(), res=_ptr(res),
+                      ldo=out.stride(0), res_ld=(res.stride(0) if res is not None else 0), T=T, H=H, W=W, Cp=Cp,
+                      Cout=w.shape[0], epilogue=epilogue)
+    check(_lib.load().yb_conv3d_causal(C.byref(args), _stream()), "yb_conv3d_causal")
+    _launches += 1
+    return out
+
+
+def gn_stats(x: torch.Tensor, groups: int) -> torch.Tensor:
+    """x bf16 [N, C] -> f64 [G, 2] (sum, sum of squares) per group."""
+    global _launches
+    _need(x, torch.bfloat16, "x")
+    stats = torch.zeros(groups, 2, device=x.device, dtype=torch.float64)
+    check(_lib.load().yb_gn_stats(x.data_ptr(), x.stride(0), stats.data_ptr(), x.shape[0], x.shape[1], groups, _stream()),
+          "yb_gn_stats")
+    _launches += 1
+    return stats
+
+
+def vae_pad_act(x: torch.Tensor, src_dims, out: torch.Tensor, pad: bool, up=(1, 1, 1), stats=None, gamma=None, beta=None,
+                groups: int = 32, eps: float = 1e-6, silu: bool = False) -> torch.Tensor:
+    """x bf16 [Ts*Hs*Ws, C] -> out bf16 [(T+2p), (H+2p), (W+2p), Cp] (see include/yume_b200.h)."""
+    global _launches
+    _need(x, torch.bfloat16, "x")
+    _need(out, torch.bfloat16, "out")
+    Ts, Hs, Ws = src_dims
+    if not out.is_contiguous():
+        raise YumeB200Error("vae_pad_act output must be contiguous")
+    check(_lib.load().yb_vae_pad_act(x.data_ptr(), x.stride(0), Ts, Hs, Ws, x.shape[1], out.data_ptr(), out.shape[-1],
+                                     1 if pad else 0, up[0], up[1], up[2], _ptr(stats), _ptr(gamma), _ptr(beta), groups,
+                                     eps, 1 if silu else 0, _stream()), "yb_vae_pad_act")
+    _launches += 1
+    return out
+
+
+def masked_softmax(S: torch.Tensor, P: torch.Tensor, L: int, hw: int) -> torch.Tensor:
+    global _launches
+    _need(S, torch.float32, "S")
+    _need(P, torch.bfloat16, "P")
+    check(_lib.load().yb_masked_softmax(S.data_ptr(), S.stride(0), P.data_ptr(), P.stride(0), L, hw, _stream()),
+          "yb_masked_softmax")
+    _launches += 1
+    return P
+
+
+def nchw_to_nhwc_bf16(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """x f32 [Cn, N] contiguous -> out bf16 [N, ldo] (extra columns zero)."""
+    global _launches
+    _need(x, torch.float32, "x")
+    _need(out, torch.bfloat16, "out")
+    if not (x.is_contiguous() and out.is_contiguous()):
+        raise YumeB200Error("nchw_to_nhwc_bf16 needs contiguous tensors")
+    check(_lib.load().yb_nchw_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), x.shape[1], x.shape[0], out.shape[1], _stream()),
+          "yb_nchw_to_nhwc_bf16")
+    _launches += 1
+    return out
+
+
+def nhwc_to_nchw_f32(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """x f32 [N, ldx] -> out f32 [Cn, N] contiguous."""
+    global _launches
+    _need(x, torch.float32, "x")
+    _need(out, torch.float32, "out")
+    check(_lib.load().yb_nhwc_to_nchw_f32(x.data_ptr(), x.stride(0), out.data_ptr(), x.shape[0], out.shape[0], _stream()),
+          "yb_nhwc_to_nchw_f32")
+    _launches += 1
+    return out
+
+
+def blend(a: torch.Tensor, b: torch.Tensor, dim: int, extent: int) -> torch.Tensor:
+    """In place on b (contiguous f32): cross-fade the first `extent` slices of b along `dim` with the last of a."""
+    global _launches
+    _need(a, torch.float32, "a")
+    _need(b, torch.float32, "b")
+    if not (a.is_contiguous() and b.is_contiguous()):
+        raise YumeB200Error("blend needs contiguous tiles")
+    extent = min(a.shape[dim], b.shape[dim], extent)
+    outer = 1
+    for d in b.shape[:dim]:
+        outer *= d
+    inner = 1
+    for d in b.shape[dim + 1:]:
+        inner *= d
+    check(_lib.load().yb_blend(a.data_ptr(), b.data_ptr(), outer, a.shape[dim], b.shape[dim], extent, inner, _stream()),
+          "yb_blend")
+    _launches += 1
+    return b
