@@ -309,8 +309,54 @@ def product_arm(args):
         dist.destroy_process_group()
 
 
+def vae_arm(args):
+    """Supplementary workload (BASELINE.json configs[4]): hyvideo causal 3D VAE tiled decode of z [1,16,21,90,160]
+    (81 frames 720x1280) with the upstream 884-16c config, random-init weights. Prints the same JSON schema."""
+    import math as _m
+
+    from yume_b200 import ops
+    from yume_b200.vae import CONFIG_884_16C, HyVaeDecoder, decoder_param_shapes
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    g = torch.Generator(device=dev).manual_seed(0)
+    sd = {}
+    for name, shape in decoder_param_shapes().items():
+        t = torch.randn(shape, generator=g, device=dev)
+        if name.endswith(".bias"):
+            t = 0.05 * t
+        elif len(shape) == 1:
+            t = 1 + 0.1 * t
+        else:
+            t = t * (1.5 / _m.sqrt(_m.prod(shape[1:])))
+        sd[name] = t
+    eng = HyVaeDecoder(sd, device=dev, **CONFIG_884_16C)
+    eng.enable_tiling()
+    T, H, W = (21, 90, 160) if not args.quick else (5, 40, 40)
+    z = torch.randn(1, 16, T, H, W, generator=g, device=dev)
+    for _ in range(args.warmup):
+        eng.decode(z)
+    torch.cuda.synchronize()
+    ops.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = eng.decode(z)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    frames = out.shape[2]
+    print(json.dumps({"metric": "decoded_frames_per_sec", "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": f"hyvideo AutoencoderKLCausal3D tiled decode z[1,16,{T},{H},{W}] -> {tuple(out.shape)}",
+                                 "tiles": "spatial 32x32 stride 24, temporal 17 stride 12 (upstream 884-16c)"},
+                      "gpu_launches": ops.launch_count(), "finite": bool(torch.isfinite(out).all())}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="dit", choices=["dit", "vae"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -318,7 +364,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="profiling runs: exact --warmup, no e2e leg, no CPU baseline")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "vae":
+        vae_arm(args)
+    elif args.impl == "reference":
         reference_arm(args)
     else:
         product_arm(args)

@@ -257,6 +257,46 @@ class HyVaeDecoder:
         return self.decode_tile(z[0])
 
 
+def decoder_param_shapes(block_out_channels=(128, 256, 512, 512), layers_per_block=2, latent_channels=16,
+                         out_channels=3) -> Dict[str, tuple]:
+    """State-dict keys / shapes of the decode half of AutoencoderKLCausal3D (vae.py:141-223 module tree)."""
+    boc = list(block_out_channels)
+    rev = boc[::-1]
+    s: Dict[str, tuple] = {"post_quant_conv.weight": (latent_channels, latent_channels, 1, 1, 1),
+                           "post_quant_conv.bias": (latent_channels,)}
+
+    def conv(p, ci, co, k=3):
+        s[p + ".conv.weight"], s[p + ".conv.bias"] = (co, ci, k, k, k), (co,)
+
+    def norm(p, c):
+        s[p + ".weight"], s[p + ".bias"] = (c,), (c,)
+
+    def resnet(p, ci, co):
+        norm(p + ".norm1", ci), conv(p + ".conv1", ci, co), norm(p + ".norm2", co), conv(p + ".conv2", co, co)
+        if ci != co:
+            conv(p + ".conv_shortcut", ci, co, 1)
+
+    c = rev[0]
+    conv("decoder.conv_in", latent_channels, c)
+    resnet("decoder.mid_block.resnets.0", c, c)
+    a = "decoder.mid_block.attentions.0"
+    norm(a + ".group_norm", c)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        s[f"{a}.{n}.weight"], s[f"{a}.{n}.bias"] = (c, c), (c,)
+    resnet("decoder.mid_block.resnets.1", c, c)
+    prev = c
+    for i in range(4):
+        co = rev[i]
+        for j in range(layers_per_block + 1):
+            resnet(f"decoder.up_blocks.{i}.resnets.{j}", prev if j == 0 else co, co)
+        if i < 3:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", co, co)
+        prev = co
+    norm("decoder.conv_norm_out", boc[0])
+    conv("decoder.conv_out", boc[0], out_channels)
+    return s
+
+
 def install_vae(vae, device="cuda"):
     """Attach a HyVaeDecoder to a live reference `AutoencoderKLCausal3D` and re-bind its `decode`
     (same signature and return convention as autoencoder_kl_causal_3d.py:315-341)."""
