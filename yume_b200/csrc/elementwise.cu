@@ -107,6 +107,73 @@ ln_modulate_kernel(const float* __restrict__ x, long long ldx, void* __restrict_
   }
 }
 
+// Warp-per-row variant for C = 128*NV (3072 -> NV 24, 5120 -> NV 40): the whole row lives in one warp's registers,
+// reductions are shuffles only (no block barrier), and every lane keeps NV*16 bytes of loads in flight.
+template <int NV, bool OUT_F32>
+__global__ void __launch_bounds__(256)
+ln_modulate_warp_kernel(const float* __restrict__ x, long long ldx, void* __restrict__ out, long long ldo,
+                        const float* __restrict__ scale, const float* __restrict__ shift, long long mod_ld,
+                        const int* __restrict__ tok_idx, const float* __restrict__ weight,
+                        const float* __restrict__ lnbias, int L, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= L) return;
+  constexpr int C = NV * 128;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = xr[lane + i * 32];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+  const long long u = tok_idx ? tok_idx[row] : 0;
+  const float4* sc4 = scale ? reinterpret_cast<const float4*>(scale + u * mod_ld) : nullptr;
+  const float4* sh4 = shift ? reinterpret_cast<const float4*>(shift + u * mod_ld) : nullptr;
+  const float4* w4 = weight ? reinterpret_cast<const float4*>(weight) : nullptr;
+  const float4* b4 = lnbias ? reinterpret_cast<const float4*>(lnbias) : nullptr;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + i * 32;
+    float4 y;
+    y.x = (v[i].x - mean) * rstd;
+    y.y = (v[i].y - mean) * rstd;
+    y.z = (v[i].z - mean) * rstd;
+    y.w = (v[i].w - mean) * rstd;
+    if (w4) {
+      const float4 w = __ldg(w4 + idx);
+      y.x *= w.x; y.y *= w.y; y.z *= w.z; y.w *= w.w;
+    }
+    if (b4) {
+      const float4 b = __ldg(b4 + idx);
+      y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w;
+    }
+    if (sc4) {
+      const float4 c = __ldg(sc4 + idx);
+      y.x *= (1.f + c.x); y.y *= (1.f + c.y); y.z *= (1.f + c.z); y.w *= (1.f + c.w);
+    }
+    if (sh4) {
+      const float4 h = __ldg(sh4 + idx);
+      y.x += h.x; y.y += h.y; y.z += h.z; y.w += h.w;
+    }
+    if (OUT_F32) {
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + static_cast<long long>(row) * ldo)[idx] = y;
+    } else {
+      uint2 w;
+      w.x = pack_bf16x2(y.x, y.y);
+      w.y = pack_bf16x2(y.z, y.w);
+      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + static_cast<long long>(row) * ldo)[idx] = w;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // WanRMSNorm over the full C row + weight + RoPE, in place on bf16 (reference: wan23/modules/model.py:121-137,
 // 38-118). One CTA (256 threads) per token; thread handles 8-element (16 B) chunks, i.e. 4 RoPE pairs.
@@ -175,6 +242,65 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ qk, long long ld, int piece_cols
       }
       *chunk_ptr(idx) = make_uint4(o[0], o[1], o[2], o[3]);
     }
+  }
+}
+
+// Warp-per-row variant for C = 256*NCH (3072 -> 12, 5120 -> 20): NCH 16-byte chunks per lane.
+template <int NCH>
+__global__ void __launch_bounds__(256)
+rmsnorm_rope_warp_kernel(__nv_bfloat16* __restrict__ qk, long long ld, int piece_cols, long long piece_stride,
+                         const float* __restrict__ weight, const float2* __restrict__ rope, int rope_len, int L, int D,
+                         float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= L) return;
+  constexpr int C = NCH * 256;
+  __nv_bfloat16* xrow = qk + static_cast<long long>(row) * ld;
+  auto chunk_ptr = [&](int i) -> uint4* {
+    const int col = (lane + i * 32) << 3;
+    const int piece = col / piece_cols;
+    return reinterpret_cast<uint4*>(xrow + piece * piece_stride + (col - piece * piece_cols));
+  };
+  uint4 raw[NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) raw[i] = *chunk_ptr(i);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(h[k]);
+      ss += f.x * f.x + f.y * f.y;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / C) + eps);
+  const bool rot = (rope != nullptr) && (row < rope_len);
+  const int half = D >> 1;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int col = (lane + i * 32) << 3;
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(weight + col));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(weight + col + 4));
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const int pair0 = (col % D) >> 1;
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(h[k]);
+      float a = f.x * rstd * wv[2 * k];
+      float b = f.y * rstd * wv[2 * k + 1];
+      if (rot) {
+        const float2 cs = __ldg(rope + static_cast<long long>(row) * half + pair0 + k);
+        const float ra = a * cs.x - b * cs.y;
+        const float rb = a * cs.y + b * cs.x;
+        a = ra;
+        b = rb;
+      }
+      o[k] = pack_bf16x2(a, b);
+    }
+    *chunk_ptr(i) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -344,6 +470,25 @@ extern "C" int yb_ln_modulate(const void* x, long long ldx, void* out, long long
   if (C % 8 != 0 || C > LN_THREADS * LN_MAX_VEC * 4) return YB_ERR_SHAPE;
   if ((ldx % 4) || (ldo % 8) || (mod_ld % 4)) return YB_ERR_ALIGNMENT;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+#define YB_LN_WARP(NV)                                                                                                  \
+  if (C == (NV) * 128) {                                                                                                \
+    const int grid = (L + 7) / 8;                                                                                       \
+    if (out_f32)                                                                                                        \
+      ln_modulate_warp_kernel<NV, true><<<grid, 256, 0, s>>>(                                                            \
+          static_cast<const float*>(x), ldx, out, ldo, static_cast<const float*>(scale), static_cast<const float*>(shift), \
+          mod_ld, static_cast<const int*>(tok_idx), static_cast<const float*>(weight), static_cast<const float*>(lnbias), \
+          L, eps);                                                                                                      \
+    else                                                                                                                \
+      ln_modulate_warp_kernel<NV, false><<<grid, 256, 0, s>>>(                                                           \
+          static_cast<const float*>(x), ldx, out, ldo, static_cast<const float*>(scale), static_cast<const float*>(shift), \
+          mod_ld, static_cast<const int*>(tok_idx), static_cast<const float*>(weight), static_cast<const float*>(lnbias), \
+          L, eps);                                                                                                      \
+    return check_launch("ln_modulate");                                                                                 \
+  }
+  YB_LN_WARP(24)
+  YB_LN_WARP(40)
+  YB_LN_WARP(2)
+#undef YB_LN_WARP
   if (out_f32)
     ln_modulate_kernel<true><<<L, LN_THREADS, 0, s>>>(static_cast<const float*>(x), ldx, out, ldo,
                                                       static_cast<const float*>(scale), static_cast<const float*>(shift),
@@ -366,6 +511,17 @@ extern "C" int yb_rmsnorm_rope_pieces(void* qk, long long ld, int piece_cols, lo
   if (C % 8 != 0 || C > RR_THREADS * RR_MAX_CHUNK * 8 || D % 8 != 0 || C % D != 0) return YB_ERR_SHAPE;
   if (piece_cols % 8 != 0 || C % piece_cols != 0) return YB_ERR_SHAPE;
   if ((ld % 8) || (piece_stride % 8) || (reinterpret_cast<uintptr_t>(qk) & 0xF)) return YB_ERR_ALIGNMENT;
+#define YB_RR_WARP(NCH)                                                                                              \
+  if (C == (NCH) * 256) {                                                                                            \
+    rmsnorm_rope_warp_kernel<NCH><<<(L + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(                  \
+        static_cast<__nv_bfloat16*>(qk), ld, piece_cols, piece_stride, static_cast<const float*>(weight),             \
+        static_cast<const float2*>(rope), rope_len, L, D, eps);                                                       \
+    return check_launch("rmsnorm_rope");                                                                             \
+  }
+  YB_RR_WARP(12)
+  YB_RR_WARP(20)
+  YB_RR_WARP(1)
+#undef YB_RR_WARP
   rmsnorm_rope_kernel<<<L, RR_THREADS, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
       static_cast<__nv_bfloat16*>(qk), ld, piece_cols, piece_stride, static_cast<const float*>(weight),
       static_cast<const float2*>(rope), rope_len, C, D, eps);
