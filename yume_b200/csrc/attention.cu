@@ -159,57 +159,39 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       issue_S(1, sKV);
       umma_commit(&s_full[1]);
       umma_commit(&kv_empty[0]);
-      // Event-driven issue: each query tile advances through (half0 -> PV_lo) and (half1 -> PV_hi, S(j+1)) whenever
-      // ITS barriers are complete; a tile whose softmax is still running never blocks the other tile's ready work.
-      int jx[2] = {0, 0};        // KV tile each query tile is working on
-      int stage[2] = {0, 0};     // 0: waiting for P half 0, 1: waiting for P half 1
-      uint32_t v_left = 0x2222u, k_left = 0x2222u;   // nibble j % 4: query tiles still to consume V_j / K_(j+1)
-      while (jx[0] < nkv || jx[1] < nkv) {
+      // (An event-driven variant that polls both tiles with mbarrier.test_wait was measured 30% slower: each probe
+      //  costs ~150 cycles against the ~60-cycle hardware wake-up of the blocking try_wait used here.)
+      for (int j = 0; j < nkv; ++j) {
+        const int iv = 2 * j + 1, ik = 2 * j + 2;
+        const int slot_v = iv % NS, slot_k = ik % NS;
+        const bool has_next = (j + 1 < nkv);
+        mbar_wait(&kv_full[slot_v], (iv / NS) & 1);
+        if (has_next) mbar_wait(&kv_full[slot_k], (ik / NS) & 1);
+        tc_fence_after();
+        const uint32_t vbase = sKV + slot_v * ATT_TILE_BYTES;
+        const uint32_t kbase = sKV + slot_k * ATT_TILE_BYTES;
 #pragma unroll
         for (int X = 0; X < 2; ++X) {
-          const int j = jx[X];
-          if (j >= nkv) continue;
-          const int iv = 2 * j + 1, ik = 2 * j + 2;
-          const int slot_v = iv % NS, slot_k = ik % NS;
-          const bool has_next = (j + 1 < nkv);
-          const uint32_t vbase = sKV + slot_v * ATT_TILE_BYTES;
           long long* tr = (p.trace != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && j >= 16 && j < 48)
                               ? p.trace + (j - 16) * 32 + 16 + X * 4 : nullptr;
-          if (stage[X] == 0) {
-            if (!mbar_test_wait(&p_half[2 * X], j & 1) || !mbar_test_wait(&kv_full[slot_v], (iv / NS) & 1)) continue;
-            if (tr) tr[1] = clock64();
-            tc_fence_after();
-            issue_PV(X, vbase, j > 0, 0);           // keys 0..63, while the softmax warps finish keys 64..127
-            stage[X] = 1;
+          if (tr) tr[0] = clock64();
+          mbar_wait(&p_half[2 * X], j & 1);
+          if (tr) tr[1] = clock64();
+          tc_fence_after();
+          issue_PV(X, vbase, j > 0, 0);             // keys 0..63 of the tile, while the softmax warps finish 64..127
+          mbar_wait(&p_half[2 * X + 1], j & 1);
+          tc_fence_after();
+          issue_PV(X, vbase, true, 1);
+          if (has_next) {
+            issue_S(X, kbase);
+            umma_commit(&s_full[X]);
           } else {
-            if (!mbar_test_wait(&p_half[2 * X + 1], j & 1)) continue;
-            if (has_next && !mbar_test_wait(&kv_full[slot_k], (ik / NS) & 1)) continue;
-            tc_fence_after();
-            issue_PV(X, vbase, true, 1);
-            if (has_next) {
-              issue_S(X, sKV + slot_k * ATT_TILE_BYTES);
-              umma_commit(&s_full[X]);
-            } else {
-              umma_commit(&o_done[X]);
-            }
-            if (tr) tr[2] = clock64();
-            const int sh = 4 * (j & 3);
-            v_left -= 1u << sh;
-            if (((v_left >> sh) & 0xFu) == 0) {     // both query tiles have issued their reads of V_j
-              umma_commit(&kv_empty[slot_v]);
-              v_left += 2u << sh;
-            }
-            if (has_next) {
-              k_left -= 1u << sh;
-              if (((k_left >> sh) & 0xFu) == 0) {
-                umma_commit(&kv_empty[slot_k]);
-                k_left += 2u << sh;
-              }
-            }
-            stage[X] = 0;
-            jx[X] = j + 1;
+            umma_commit(&o_done[X]);
           }
+          if (tr) tr[2] = clock64();
         }
+        umma_commit(&kv_empty[slot_v]);
+        if (has_next) umma_commit(&kv_empty[slot_k]);
       }
     }
   } else {
