@@ -159,8 +159,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       issue_S(1, sKV);
       umma_commit(&s_full[1]);
       umma_commit(&kv_empty[0]);
-      // (An event-driven variant that polls both tiles with mbarrier.test_wait was measured 30% slower: each probe
-      //  costs ~150 cycles against the ~60-cycle hardware wake-up of the blocking try_wait used here.)
+      // Measured alternatives (profiles/README.md): an event-driven loop polling both tiles with mbarrier.test_wait
+      // was 30% slower (each probe costs ~150 cycles vs the ~60-cycle wake-up of the blocking try_wait); one issuer
+      // thread per query tile was 30% slower as well — the tiles drift into phase (both in softmax, then both in MMA)
+      // and lose the ping-pong this single in-order issuer enforces.
       for (int j = 0; j < nkv; ++j) {
         const int iv = 2 * j + 1, ik = 2 * j + 2;
         const int slot_v = iv % NS, slot_k = ik % NS;
