@@ -188,7 +188,7 @@ def product_arm(args):
     del sd
     eng = model._yb_engine
     if world > 1:
-        eng.enable_sequence_parallel(dist.group.WORLD)
+        eng.enable_sequence_parallel(dist.group.WORLD, transport=args.sp_transport)
 
     g = torch.Generator().manual_seed(1)
     x_host = torch.randn(*LATENT, generator=g).pin_memory()
@@ -286,7 +286,8 @@ def product_arm(args):
             "config": {"workload": "Yume-5B-720P single denoise step (WanModel.forward, flag=False), 81-frame 704x1280 "
                                    "latent [48,21,44,80], L=18480 tokens, 512-token text context, t=500",
                        "model": "Yume-5B-720P (Wan2.2-TI2V-5B geometry: dim 3072, ffn 14336, 24 heads, 30 layers), random init",
-                       "parallelism": "single GPU" if world == 1 else f"ulysses sp{world}",
+                       "parallelism": "single GPU" if world == 1 else
+                       f"ulysses sp{world} ({'NVLink peer-memory exchange fused into kernels' if eng._sp_p2p else 'NCCL all-to-all'})",
                        "l2": "per-step working set (10 GB of bf16 weights + 1.5 GB activations) >> 126 MB L2; no flush needed",
                        "step_tflop": step_flops / 1e12},
             "step_tflops_achieved": step_flops / (ms_per_step * 1e-3) / 1e12,
@@ -362,6 +363,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="yume_b200", choices=["yume_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sp-transport", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--quick", action="store_true", help="profiling runs: exact --warmup, no e2e leg, no CPU baseline")
     args = ap.parse_args()
     if args.workload == "vae":

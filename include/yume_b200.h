@@ -135,6 +135,23 @@ int yb_attention_ex(const void* q, long long ldq, const void* k, long long ldk, 
                                wan/modules/model.py:380-387) */
 
 /* ---------------------------------------------------------------------------------------------
+ * Ulysses sequence parallelism fused with the NVLink exchange (design reference
+ * wan23/distributed/ulysses.py:9-47, sequence_parallel.py:147-176 — three NCCL all_to_alls in, one out).
+ * `peers[r]` are device pointers valid on THIS GPU to rank r's receive buffer (CUDA peer / symmetric memory).
+ *   yb_sp_scatter_qkv: per local token, RMSNorm+weight+RoPE on q and k (WanRMSNorm over all heads, model.py:121-137;
+ *     rope_apply :38-118), then every 16-byte chunk of q|k|v is stored into the receive buffer of the rank owning
+ *     that head: peers[h / (heads/P)][rank][t][part*Wh + ...], buffer layout [P(src), Lp, 3*Wh], Wh = C/P.
+ *   yb_attention_sp: attention over the gathered tokens for this rank's heads; output row g is stored into
+ *     out_peers[g / Lp][rank][g % Lp][:], buffer layout [P(src), Lp, heads_local*128] (row stride ldo).
+ * A cross-rank barrier (symmetric-memory signal) must separate each call from the consumer of the buffers.
+ * ------------------------------------------------------------------------------------------- */
+int yb_sp_scatter_qkv(const void* qkv, long long ld, const void* wq, const void* wk, const void* rope, int rope_len,
+                      int L, int C, int D, float eps, void* const* peers, int world, int rank, int Lp, void* stream);
+int yb_attention_sp(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                    void* const* out_peers, long long ldo, int Lq, int Lk, int heads, float scale, int world, int rank,
+                    int Lp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * patchify gather (bit-exact index op): x f32 [Cin, F, H, W] (element strides sc, sf, sh, sw) -> bf16 [F*(Hp)*(Wp), Cin*ph*pw] rows in
  * (f, h, w) token order, columns in Conv3d weight order (cin, ph, pw); H, W zero-padded up to a multiple
  * of the patch (convpadd, wan23/modules/model.py:918-931). Replaces the data movement of

@@ -30,7 +30,7 @@ def main():
         kw = synth.oracle_kwargs(cfg)
         variant = kw.pop("variant")
         eng = WanDiT(sd, variant, device=dev, **kw)
-        eng.enable_sequence_parallel(dist.group.WORLD)
+        eng.enable_sequence_parallel(dist.group.WORLD, transport=os.environ.get("YB_SP_TRANSPORT", "auto"))
         for name, c in g["cases"].items():
             inp = synth.make_inputs(cfg, c["seed"], c["frames"], c["H"], c["W"], c["ctx_len"])
             if variant == "5b":
@@ -43,7 +43,8 @@ def main():
             ok = out.shape == c["out"].shape and r < TOL
             bad += 0 if ok else 1
             if rank == 0 or not ok:
-                print(f"[rank {rank}] sp{dist.get_world_size()} {name}: rel {r:.3e} {'ok' if ok else 'MISMATCH'}", flush=True)
+                print(f"[rank {rank}] sp{dist.get_world_size()} ({eng.sp_transport}{'/p2p' if eng._sp_p2p else ''}) {name}: "
+                      f"rel {r:.3e} {'ok' if ok else 'MISMATCH'}", flush=True)
     t = torch.tensor([bad], device=dev)
     dist.all_reduce(t)
     dist.destroy_process_group()

@@ -64,6 +64,8 @@ SIGNATURES = {
     "yb_rmsnorm_rope_pieces": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "yb_attention": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _f, _i, _vp]),
     "yb_attention_ex": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _f, _i, _vp, _vp]),
+    "yb_sp_scatter_qkv": (_i, [_vp, _ll, _vp, _vp, _vp, _i, _i, _i, _i, _f, C.POINTER(C.c_void_p), _i, _i, _i, _vp]),
+    "yb_attention_sp": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, C.POINTER(C.c_void_p), _ll, _i, _i, _i, _f, _i, _i, _i, _vp]),
     "yb_patchify": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
     "yb_bcast_add": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "yb_unpatchify": (_i, [_vp, _ll, _vp, _i, _i, _i, _i, _i, _i, _vp]),

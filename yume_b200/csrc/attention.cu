@@ -30,6 +30,10 @@ struct AttParams {
   int Lq, Lk;
   int nkv;
   int accumulate;    // out += result (sum of two attention branches)
+  // Ulysses (sp_world > 1): output row g belongs to rank g / sp_Lp and is stored straight into that rank's
+  // [P(src), Lp, heads_local*128] receive buffer over NVLink (peer pointers) — the all-to-all is the epilogue itself.
+  __nv_bfloat16* out_peers[8];
+  int sp_world, sp_rank, sp_Lp;
   long long* trace;  // optional clock64 trace of CTA (1,0), KV tiles 16..47 (tests/tools only; null in production)
   float scale_log2;  // softmax scale * log2(e)
 };
@@ -334,6 +338,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float inv = 1.0f / l;
     const int q_row = q0 + X * 128 + row_in_tile;
     __nv_bfloat16* orow = p.out + static_cast<long long>(q_row) * p.ldo + head * 128;
+    if (p.sp_world > 1) {
+      const int owner = q_row / p.sp_Lp;
+      const int t = q_row - owner * p.sp_Lp;
+      if (owner < p.sp_world)
+        orow = p.out_peers[owner] + (static_cast<long long>(p.sp_rank) * p.sp_Lp + t) * p.ldo + head * 128;
+    }
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t o[32];
@@ -430,6 +440,9 @@ extern "C" int yb_attention_ex(const void* q, long long ldq, const void* k, long
   p.nkv = (Lk + 127) / 128;
   p.accumulate = (flags & YB_ATT_ACCUMULATE) ? 1 : 0;
   p.trace = static_cast<long long*>(trace);
+  p.sp_world = 1;
+  p.sp_rank = 0;
+  p.sp_Lp = 0;
   p.scale_log2 = scale * 1.4426950408889634f;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (flags & YB_ATT_P_SMEM) return launch_attention<false, 0>(tmQ, tmK, tmV, p, heads, stream);
@@ -439,4 +452,36 @@ extern "C" int yb_attention_ex(const void* q, long long ldq, const void* k, long
     case 3: return launch_attention<true, 2>(tmQ, tmK, tmV, p, heads, stream);
     default: return launch_attention<true, 0>(tmQ, tmK, tmV, p, heads, stream);
   }
+}
+
+
+// Ulysses attention: same kernel, output rows scattered to their owner ranks through peer pointers (see AttParams).
+extern "C" int yb_attention_sp(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                               void* const* out_peers, long long ldo, int Lq, int Lk, int heads, float scale, int world,
+                               int rank, int Lp, void* stream_) {
+  using namespace yb;
+  if (!q || !k || !v || !out_peers || world < 2 || world > 8 || rank < 0 || rank >= world || Lp <= 0) return YB_ERR_ARG;
+  if (Lq != world * Lp || Lk <= 0 || Lk > Lq || heads <= 0 || (ldo % 8)) return YB_ERR_ARG;
+  CUtensorMap tmQ, tmK, tmV;
+  const uint64_t cols = static_cast<uint64_t>(heads) * 128;
+  int rc = make_tmap_bf16_2d(&tmQ, q, Lq, cols, ldq, 128, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmK, k, Lk, cols, ldk, 128, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmV, v, Lk, cols, ldv, 128, 64);
+  if (rc) return rc;
+  AttParams p;
+  p.out = static_cast<__nv_bfloat16*>(out_peers[rank]);
+  p.ldo = ldo;
+  p.Lq = Lq;
+  p.Lk = Lk;
+  p.nkv = (Lk + 127) / 128;
+  p.accumulate = 0;
+  p.trace = nullptr;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  for (int i = 0; i < 8; ++i) p.out_peers[i] = i < world ? static_cast<__nv_bfloat16*>(out_peers[i]) : nullptr;
+  p.sp_world = world;
+  p.sp_rank = rank;
+  p.sp_Lp = Lp;
+  return launch_attention<true, 0>(tmQ, tmK, tmV, p, heads, reinterpret_cast<cudaStream_t>(stream_));
 }

@@ -304,6 +304,80 @@ rmsnorm_rope_warp_kernel(__nv_bfloat16* __restrict__ qk, long long ld, int piece
   }
 }
 
+// Ulysses send side fused with the exchange: one warp per local token reads its q | k | v row (standard [L, 3C]
+// layout), applies RMSNorm + weight + RoPE to q and k, and stores every 16-byte chunk DIRECTLY into the receive
+// buffer of the rank that owns that head ([P(src), Lp, q|k|v of heads/P] on the peer, NVLink peer pointer).
+// Replaces rmsnorm_rope + the q/k/v all-to-all (wan23/distributed/ulysses.py:32-34 does 3 NCCL all_to_alls).
+struct PeerPtrs {
+  __nv_bfloat16* p[8];
+};
+template <int NCH>
+__global__ void __launch_bounds__(256)
+sp_scatter_qkv_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, const float* __restrict__ wq,
+                      const float* __restrict__ wk, const float2* __restrict__ rope, int rope_len, int L, int D,
+                      float eps, const PeerPtrs peers, int rank, int Lp, int Wh) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= L) return;
+  constexpr int C = NCH * 256;
+  const int W3 = 3 * Wh;
+  const bool rot = (rope != nullptr) && (row < rope_len);
+  const int half = D >> 1;
+  const long long dst_row = (static_cast<long long>(rank) * Lp + row) * W3;
+#pragma unroll 1
+  for (int part = 0; part < 3; ++part) {
+    const __nv_bfloat16* src = qkv + static_cast<long long>(row) * ld + part * C;
+    uint4 raw[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) raw[i] = *reinterpret_cast<const uint4*>(src + ((lane + i * 32) << 3));
+    float rstd = 1.f;
+    if (part < 2) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(h[k]);
+          ss += f.x * f.x + f.y * f.y;
+        }
+      }
+      rstd = rsqrtf(warp_sum(ss) * (1.0f / C) + eps);
+    }
+    const float* weight = part == 0 ? wq : wk;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int col = (lane + i * 32) << 3;
+      uint4 o = raw[i];
+      if (part < 2) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(weight + col));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(weight + col + 4));
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const int pair0 = (col % D) >> 1;
+        uint32_t ov[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(h[k]);
+          float a = f.x * rstd * wv[2 * k];
+          float b = f.y * rstd * wv[2 * k + 1];
+          if (rot) {
+            const float2 cs = __ldg(rope + static_cast<long long>(row) * half + pair0 + k);
+            const float ra = a * cs.x - b * cs.y;
+            const float rb = a * cs.y + b * cs.x;
+            a = ra;
+            b = rb;
+          }
+          ov[k] = pack_bf16x2(a, b);
+        }
+        o = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+      }
+      const int peer = col / Wh;
+      *reinterpret_cast<uint4*>(peers.p[peer] + dst_row + part * Wh + (col - peer * Wh)) = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // patchify gather: x f32 [Cin, F, H, W] -> bf16 [L, Cin*ph*pw], token order (f, hp, wp), column order
 // (cin, i, j) = Conv3d weight.flatten(1) order for kernel (1, ph, pw). Out-of-range H/W read as zero (convpadd).
@@ -582,4 +656,29 @@ extern "C" int yb_linear_f32(const void* in, long long ldi, const void* W, const
       static_cast<const float*>(in), ldi, static_cast<const float*>(W), static_cast<const float*>(bias),
       static_cast<float*>(out), ldo, M, N, K);
   return check_launch("linear_f32");
+}
+
+
+extern "C" int yb_sp_scatter_qkv(const void* qkv, long long ld, const void* wq, const void* wk, const void* rope,
+                                 int rope_len, int L, int C, int D, float eps, void* const* peers, int world, int rank,
+                                 int Lp, void* stream_) {
+  if (!qkv || !wq || !wk || !peers || L <= 0 || world < 2 || world > 8 || rank < 0 || rank >= world) return YB_ERR_ARG;
+  if (C % (world * D) != 0 || (ld % 8)) return YB_ERR_SHAPE;
+  PeerPtrs pp;
+  for (int i = 0; i < 8; ++i) pp.p[i] = i < world ? static_cast<__nv_bfloat16*>(peers[i]) : nullptr;
+  const int Wh = C / world;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+#define YB_SC(NCH)                                                                                                   \
+  if (C == (NCH) * 256) {                                                                                            \
+    sp_scatter_qkv_kernel<NCH><<<(L + 7) / 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), ld,                \
+                                                          static_cast<const float*>(wq), static_cast<const float*>(wk), \
+                                                          static_cast<const float2*>(rope), rope_len, L, D, eps, pp,   \
+                                                          rank, Lp, Wh);                                              \
+    return check_launch("sp_scatter_qkv");                                                                           \
+  }
+  YB_SC(12)
+  YB_SC(20)
+  YB_SC(1)
+#undef YB_SC
+  return YB_ERR_SHAPE;
 }

@@ -138,6 +138,7 @@ class WanDiT:
         self._rope_cache: Dict[Tuple, Tensor] = {}
         self.timer = KernelTimer()          # bench.py switches it on to time individual kernels inside a live step
         self.sp_group, self.sp_world, self.sp_rank = None, 1, 0
+        self.sp_transport, self._sp_p2p = "auto", None
         self._repack(state_dict)
 
     # ------------------------------------------------------------------------------------------------------
@@ -205,10 +206,15 @@ class WanDiT:
             mods.append(f32(p + ".modulation").reshape(6 * C))
         self.block_mod = torch.stack(mods).contiguous()            # [layers, 6C]
 
-    def enable_sequence_parallel(self, group) -> None:
-        """Shard the token sequence Ulysses-style over `group` (one process per GPU). Builds the peer-major fused
-        q|k|v weight: rows ordered [peer p][q, k, v][heads p*H/P .. (p+1)*H/P) so that the QKV GEMM's `n_split`
-        epilogue emits exactly the chunks the all-to-all sends."""
+    def enable_sequence_parallel(self, group, transport: str = "auto") -> None:
+        """Shard the token sequence Ulysses-style over `group` (one process per GPU). transport: "p2p" = exchanges
+        fused into the kernels over NVLink peer memory (torch symmetric memory), "nccl" = NCCL all_to_all_single,
+        "auto" = p2p when symmetric memory is available. For the NCCL path builds the peer-major fused q|k|v weight:
+        rows ordered [peer p][q, k, v][heads p*H/P .. (p+1)*H/P) so that the QKV GEMM's `n_split` epilogue emits
+        exactly the chunks the all-to-all sends."""
+        if transport not in ("auto", "p2p", "nccl"):
+            raise YumeB200Error("transport must be auto, p2p or nccl")
+        self.sp_transport, self._sp_p2p = transport, None
         import torch.distributed as dist
         P = dist.get_world_size(group)
         if self.heads % P:
@@ -326,7 +332,70 @@ class WanDiT:
             ops.ln_modulate(h3, out[:n_img], None, None, None, *self.img["ln4"], eps=1e-5)
         return out
 
-    def _self_attention_sp(self, b: dict, h: Tensor, xs: Tensor, m: Tensor, tok_idx: Optional[Tensor], rope: Tensor,
+    def _sp_p2p_state(self, Lp: int):
+        """Symmetric-memory receive buffers (both layer parities) and every rank's peer pointers to them. Collective:
+        all ranks call it with the same Lp. Returns None (-> NCCL transport) if symmetric memory is unavailable."""
+        if self._sp_p2p is not None and self._sp_p2p["Lp"] == Lp:
+            return self._sp_p2p
+        if self.sp_transport == "nccl":
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            P, Wh = self.sp_world, (self.heads // self.sp_world) * self.head_dim
+            n_qkv, n_att = P * Lp * 3 * Wh, P * Lp * Wh
+            buf = symm.empty(2 * (n_qkv + n_att), dtype=_BF16, device=self.device)
+            hdl = symm.rendezvous(buf, self.sp_group)
+            bases = [int(x) for x in hdl.buffer_ptrs]
+            off_q = [0, n_qkv]
+            off_a = [2 * n_qkv, 2 * n_qkv + n_att]
+            self._sp_p2p = dict(
+                Lp=Lp, buf=buf, hdl=hdl,
+                qkv=[buf[o:o + n_qkv].view(P, Lp, 3 * Wh) for o in off_q],
+                att=[buf[o:o + n_att].view(P, Lp, Wh) for o in off_a],
+                qkv_ptrs=[[bp + 2 * o for bp in bases] for o in off_q],
+                att_ptrs=[[bp + 2 * o for bp in bases] for o in off_a])
+        except Exception as e:  # transport choice only: the NCCL path below runs the same kernels
+            if self.sp_transport == "p2p":
+                raise
+            import warnings
+            warnings.warn(f"yume_b200: symmetric memory unavailable ({type(e).__name__}: {e}); Ulysses uses NCCL all-to-all")
+            self.sp_transport = "nccl"
+            return None
+        return self._sp_p2p
+
+    def _self_attention_sp_p2p(self, i: int, st: dict, b: dict, h: Tensor, xs: Tensor, m: Tensor,
+                               tok_idx: Optional[Tensor], rope: Tensor, rope_len: int, L_true: int) -> None:
+        """Ulysses with the exchanges fused into the kernels over NVLink peer memory: the RMSNorm+RoPE kernel stores
+        q|k|v chunks straight into the owning rank's receive buffer, the attention epilogue stores each output row
+        straight into its owner's buffer; two symmetric-memory barriers per block, no NCCL on the data path. Receive
+        buffers alternate by layer parity so a fast rank's next-layer writes never land in a buffer a slow rank still
+        reads (it cannot be two barriers ahead)."""
+        C, D, P = self.dim, self.head_dim, self.sp_world
+        Hp = self.heads // P
+        Wh = Hp * D
+        Lp = xs.shape[0]
+        par = i & 1
+        T = self.timer
+        qkv = self._buf("qkv", (Lp, 3 * C), _BF16)
+        T.begin("gemm_qkv")
+        ops.gemm(h, b["w_qkv"], b["b_qkv"], qkv, ops.YB_EPI_BF16)
+        T.end("gemm_qkv")
+        T.begin("sp_scatter_qkv")
+        ops.sp_scatter_qkv(qkv, b["nq"], b["nk"], rope, rope_len, D, self.eps, st["qkv_ptrs"][par], self.sp_rank, Lp)
+        st["hdl"].barrier(channel=0)
+        T.end("sp_scatter_qkv")
+        full = st["qkv"][par].view(P * Lp, 3 * Wh)
+        T.begin("self_attention")
+        ops.attention_sp(full[:, :Wh], full[:L_true, Wh:2 * Wh], full[:L_true, 2 * Wh:], st["att_ptrs"][par], Wh, Hp,
+                         self.sp_rank, Lp)
+        st["hdl"].barrier(channel=0)
+        T.end("self_attention")
+        T.begin("gemm_o")
+        ops.gemm(st["att"][par], b["w_o"], b["b_o"], xs, ops.YB_EPI_GATE_RES, gate=m[:, 2], tok_idx=tok_idx,
+                 a_split=Wh, a_split_stride=Lp * Wh, shape=(Lp, C))
+        T.end("gemm_o")
+
+    def _self_attention_sp(self, i: int, b: dict, h: Tensor, xs: Tensor, m: Tensor, tok_idx: Optional[Tensor], rope: Tensor,
                            rope_len: int, L_true: int) -> None:
         """Ulysses self-attention on a token shard (design reference wan23/distributed/ulysses.py:9-47,
         sequence_parallel.py:147-176). xs/h hold this rank's Lp tokens. Two all-to-alls per block on the
@@ -336,6 +405,9 @@ class WanDiT:
           all-to-all -> [P*Lp tokens, q|k|v of my heads/P] ; attention over all L_true keys for my heads
           all-to-all -> [P, Lp, heads/P*128]; the o-projection reads it through a K-split 3-D TMA map."""
         import torch.distributed as dist
+        st = self._sp_p2p_state(xs.shape[0])
+        if st is not None:
+            return self._self_attention_sp_p2p(i, st, b, h, xs, m, tok_idx, rope, rope_len, L_true)
         C, D, P = self.dim, self.head_dim, self.sp_world
         Hp = self.heads // P
         Wh, W3 = Hp * D, 3 * Hp * D
@@ -382,7 +454,7 @@ class WanDiT:
         ops.ln_modulate(xs, h, m[:, 1], m[:, 0], tok_idx, eps=self.eps)
         T.end("ln_modulate")
         if self.sp_world > 1:
-            self._self_attention_sp(b, h, xs, m, tok_idx, rope, rope_len, L_true if L_true is not None else L)
+            self._self_attention_sp(i, b, h, xs, m, tok_idx, rope, rope_len, L_true if L_true is not None else L)
         else:
             self._self_attention_local(b, h, qkv, att, xs, m, tok_idx, rope, rope_len)
         self._cross_and_ffn(b, xs, h, qkv, att, m, tok_idx, ctx)

@@ -348,3 +348,36 @@ def blend(a: torch.Tensor, b: torch.Tensor, dim: int, extent: int) -> torch.Tens
           "yb_blend")
     _launches += 1
     return b
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Ulysses exchange fused into the kernels (NVLink peer pointers from torch symmetric memory)
+# ------------------------------------------------------------------------------------------------------------
+def _ptr_array(ptrs):
+    arr = (C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+    return arr
+
+
+def sp_scatter_qkv(qkv: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, rope: Optional[torch.Tensor], rope_len: int,
+                   head_dim: int, eps: float, peer_ptrs, rank: int, Lp: int) -> None:
+    """qkv bf16 [L_local, 3C] -> RMSNorm/RoPE on q,k and scatter q|k|v chunks into the peers' receive buffers."""
+    global _launches
+    _need(qkv, torch.bfloat16, "qkv")
+    L, C3 = qkv.shape
+    check(_lib.load().yb_sp_scatter_qkv(qkv.data_ptr(), qkv.stride(0), wq.data_ptr(), wk.data_ptr(), _ptr(rope), rope_len,
+                                        L, C3 // 3, head_dim, eps, _ptr_array(peer_ptrs), len(peer_ptrs), rank, Lp,
+                                        _stream()), "yb_sp_scatter_qkv")
+    _launches += 1
+
+
+def attention_sp(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out_peer_ptrs, ldo: int, heads: int, rank: int,
+                 Lp: int, scale: Optional[float] = None) -> None:
+    global _launches
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _need(t, torch.bfloat16, n)
+    if scale is None:
+        scale = 1.0 / math.sqrt(128.0)
+    check(_lib.load().yb_attention_sp(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                      _ptr_array(out_peer_ptrs), ldo, q.shape[0], k.shape[0], heads, scale,
+                                      len(out_peer_ptrs), rank, Lp, _stream()), "yb_attention_sp")
+    _launches += 1
