@@ -117,7 +117,8 @@ def cpu_reference_sample(budget_s: float, reps: int, warmup: int):
         return time.perf_counter() - t0
 
     ladder = [(18480, (21, 22, 40)), (9240, (21, 22, 20)), (4620, (21, 11, 20)), (2310, (21, 11, 10)), (1155, (21, 11, 5))]
-    probe = run(*ladder[-1])                                   # also the first warm-up
+    run(*ladder[-1])                                           # first touch of weights / thread pool: discarded
+    probe = run(*ladder[-1])
     per_flop = probe / block_flops(1155, C, F, S)
     choice = ladder[-1]
     for L, grid in ladder:
