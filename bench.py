@@ -32,6 +32,8 @@ sys.path.insert(0, str(ROOT))
 
 CFG_5B = dict(variant="5b", dim=3072, ffn_dim=14336, num_heads=24, num_layers=30, in_dim=48, out_dim=48,
               text_len=512, text_dim=4096, freq_dim=256)
+CFG_14B = dict(variant="14b", dim=5120, ffn_dim=13824, num_heads=40, num_layers=40, in_dim=36, out_dim=16,
+               text_len=512, text_dim=4096, freq_dim=256, clip_dim=1280)
 LATENT = (48, 21, 44, 80)          # 81 frames @ 704x1280 through the Wan2.2 VAE (stride 4,16,16)
 SEQ_LEN = 21 * 22 * 40             # 18 480 tokens
 CTX_LEN = 512
@@ -63,13 +65,22 @@ def synthetic_state_dict(cfg: dict, device, seed: int = 0):
     sd["time_embedding.0.weight"], sd["time_embedding.0.bias"] = rn(C, cfg["freq_dim"], std=1 / 16), rn(C, std=0.02)
     sd["time_embedding.2.weight"], sd["time_embedding.2.bias"] = rn(C, C, std=C ** -0.5), rn(C, std=0.02)
     sd["time_projection.1.weight"], sd["time_projection.1.bias"] = rn(6 * C, C, std=C ** -0.5), rn(6 * C, std=0.02)
+    img = cfg["variant"] == "14b"
+    if img:
+        cd = cfg["clip_dim"]
+        sd["img_emb.proj.0.weight"], sd["img_emb.proj.0.bias"] = 1 + rn(cd, std=0.1), rn(cd, std=0.02)
+        sd["img_emb.proj.1.weight"], sd["img_emb.proj.1.bias"] = rn(cd, cd, std=cd ** -0.5), rn(cd, std=0.02)
+        sd["img_emb.proj.3.weight"], sd["img_emb.proj.3.bias"] = rn(C, cd, std=cd ** -0.5), rn(C, std=0.02)
+        sd["img_emb.proj.4.weight"], sd["img_emb.proj.4.bias"] = 1 + rn(C, std=0.1), rn(C, std=0.02)
     for i in range(cfg["num_layers"]):
         p = f"blocks.{i}"
         for att in ("self_attn", "cross_attn"):
-            for pr in ("q", "k", "v", "o"):
+            for pr in ("q", "k", "v", "o") + (("k_img", "v_img") if (img and att == "cross_attn") else ()):
                 sd[f"{p}.{att}.{pr}.weight"], sd[f"{p}.{att}.{pr}.bias"] = rn(C, C, std=C ** -0.5), rn(C, std=0.02)
             sd[f"{p}.{att}.norm_q.weight"] = 1 + rn(C, std=0.1)
             sd[f"{p}.{att}.norm_k.weight"] = 1 + rn(C, std=0.1)
+            if img and att == "cross_attn":
+                sd[f"{p}.{att}.norm_k_img.weight"] = 1 + rn(C, std=0.1)
         sd[f"{p}.norm3.weight"], sd[f"{p}.norm3.bias"] = 1 + rn(C, std=0.1), rn(C, std=0.02)
         sd[f"{p}.ffn.0.weight"], sd[f"{p}.ffn.0.bias"] = rn(Fd, C, std=C ** -0.5), rn(Fd, std=0.02)
         sd[f"{p}.ffn.2.weight"], sd[f"{p}.ffn.2.bias"] = rn(C, Fd, std=Fd ** -0.5), rn(C, std=0.02)
@@ -311,6 +322,56 @@ def product_arm(args):
         dist.destroy_process_group()
 
 
+def chunk_arm(args):
+    """Supplementary workloads (BASELINE.json configs[2]/[3]): one FramePack-chunk denoise forward.
+      5b-chunk : Yume-5B, 13 latent frames @44x80 (5 history + 8 new), L = 9460, per-token t (0 / 900)
+      14b-chunk: Yume-I2V-540P (14B), 13 latent frames @68x120, latent_frame_zero 8, L = 21930, CLIP + text context"""
+    from yume_b200 import ops
+    from yume_b200.dit import WanDiT
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    five = args.config == "5b-chunk"
+    cfg = CFG_5B if five else CFG_14B
+    sd = synthetic_state_dict(cfg, dev, seed=0)
+    kw = {k: cfg[k] for k in ("dim", "ffn_dim", "num_heads", "num_layers", "in_dim", "out_dim", "text_len", "freq_dim")}
+    eng = WanDiT(sd, cfg["variant"], device=dev, **kw)
+    del sd
+    torch.cuda.empty_cache()
+    g = torch.Generator(device=dev).manual_seed(1)
+    ctx = torch.randn(CTX_LEN, cfg["text_dim"], generator=g, device=dev).to(torch.bfloat16)
+    if five:
+        x = torch.randn(48, 13, 44, 80, generator=g, device=dev)
+        fwd = lambda: eng.forward(x, torch.tensor([[0.0, 900.0]], device=dev), ctx, 0, latent_frame_zero=8, packed=True)  # noqa: E731
+        L, S = 9460, CTX_LEN
+    else:
+        x = torch.randn(16, 13, 68, 120, generator=g, device=dev)
+        y = torch.randn(20, 13, 68, 120, generator=g, device=dev)
+        clip = torch.randn(1, 257, 1280, generator=g, device=dev)
+        fwd = lambda: eng.forward(x, torch.tensor([500.0], device=dev), ctx, 0, y=y, clip_fea=clip, latent_frame_zero=8,  # noqa: E731
+                                  packed=True)
+        L, S = 21930, CTX_LEN + 257
+    for _ in range(max(3, args.warmup)):
+        out = fwd()
+    torch.cuda.synchronize()
+    ops.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = fwd()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    flops = cfg["num_layers"] * block_flops(L, cfg["dim"], cfg["ffn_dim"], S)
+    print(json.dumps({"metric": "latent_frames_per_sec", "value": 8 / (ms * 1e-3), "unit": "latent-frames/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
+                      "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": f"{args.config}: FramePack chunk forward, L={L}, out {tuple(out.shape)}",
+                                 "step_tflop": flops / 1e12},
+                      "step_tflops_achieved": flops / (ms * 1e-3) / 1e12, "gpu_launches": ops.launch_count(),
+                      "finite": bool(torch.isfinite(out).all())}), flush=True)
+
+
 def vae_arm(args):
     """Supplementary workload (BASELINE.json configs[4]): hyvideo causal 3D VAE tiled decode of z [1,16,21,90,160]
     (81 frames 720x1280) with the upstream 884-16c config, random-init weights. Prints the same JSON schema."""
@@ -359,6 +420,8 @@ def vae_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="dit", choices=["dit", "vae"])
+    ap.add_argument("--config", default="5b-720p", choices=["5b-720p", "5b-chunk", "14b-chunk"],
+                    help="5b-720p is the headline workload (BASELINE.json configs[1]); the others are supplementary")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -369,6 +432,8 @@ def main():
     args = ap.parse_args()
     if args.workload == "vae":
         vae_arm(args)
+    elif args.config != "5b-720p":
+        chunk_arm(args)
     elif args.impl == "reference":
         reference_arm(args)
     else:
