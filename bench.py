@@ -153,7 +153,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_sample(budget_s=150.0, reps=args.steps, warmup=max(1, args.warmup))
+    r = cpu_reference_sample(budget_s=args.ref_budget, reps=args.steps, warmup=max(1, args.warmup))
     value = LATENT[1] / r["t_step_s"]
     line = {
         "impl": "reference", "metric": "latent_frames_per_sec", "value": value, "unit": "latent-frames/s",
@@ -427,6 +427,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="yume_b200", choices=["yume_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds of CPU work for the whole run")
     ap.add_argument("--sp-transport", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--quick", action="store_true", help="profiling runs: exact --warmup, no e2e leg, no CPU baseline")
     args = ap.parse_args()
