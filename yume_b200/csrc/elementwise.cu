@@ -247,7 +247,7 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ qk, long long ld, int piece_cols
 
 // Warp-per-row variant for C = 256*NCH (3072 -> 12, 5120 -> 20): NCH 16-byte chunks per lane.
 template <int NCH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NCH <= 12) ? 2 : 1)   // C <= 3072: <= 128 registers, two CTAs per SM
 rmsnorm_rope_warp_kernel(__nv_bfloat16* __restrict__ qk, long long ld, int piece_cols, long long piece_stride,
                          const float* __restrict__ weight, const float2* __restrict__ rope, int rope_len, int L, int D,
                          float eps) {

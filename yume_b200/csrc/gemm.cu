@@ -197,8 +197,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tile_coords(tile, p.num_m_tiles, p.num_n_tiles, m_tile, n_tile);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
       // logical output row of tile row (quad*32 + lane): the matrix row, or the voxel index of a conv tile; -1 = none
       int my_row;
@@ -216,6 +214,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           my_row = row < p.M ? row : -1;
         }
       }
+      if (EPI == YB_EPI_GATE_RES && my_row >= 0) {
+        // The residual rows of this tile are cold in HBM and the 4 epilogue warps keep too few bytes in flight to pull
+        // them at speed: prefetch them into L2 while the accumulator of this tile is still being computed.
+        const char* xrow = reinterpret_cast<const char*>(reinterpret_cast<const float*>(p.out) +
+                                                         static_cast<long long>(my_row) * p.ldo + n_tile * BLOCK_N);
+        const int ncols = min(BLOCK_N, p.N - n_tile * BLOCK_N);
+        for (int b = 0; b < ncols * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow + b));
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
       int my_tok = 0;  // gate-table row of tile row `lane`
       if (EPI == YB_EPI_GATE_RES && p.gate != nullptr && p.tok_idx != nullptr && my_row >= 0)
         my_tok = p.tok_idx[my_row];

@@ -205,6 +205,14 @@ class WanDiT:
             self.blocks.append(blk)
             mods.append(f32(p + ".modulation").reshape(6 * C))
         self.block_mod = torch.stack(mods).contiguous()            # [layers, 6C]
+        # cross-attention K/V projections of all blocks as ONE [layers*2C, C] weight: the context is the same for
+        # every block, so one GEMM per forward replaces `layers` latency-bound 48-tile GEMMs (model.py:223-224 runs
+        # k(context), v(context) inside every block)
+        self.cw_kv_all = torch.cat([b.pop("cw_kv") for b in self.blocks], dim=0).contiguous()
+        self.cb_kv_all = torch.cat([b.pop("cb_kv") for b in self.blocks], dim=0).contiguous()
+        if self.variant == "14b":
+            self.cw_kv_img_all = torch.cat([b.pop("cw_kv_img") for b in self.blocks], dim=0).contiguous()
+            self.cb_kv_img_all = torch.cat([b.pop("cb_kv_img") for b in self.blocks], dim=0).contiguous()
 
     def enable_sequence_parallel(self, group, transport: str = "auto") -> None:
         """Shard the token sequence Ulysses-style over `group` (one process per GPU). transport: "p2p" = exchanges
@@ -439,6 +447,29 @@ class WanDiT:
                  a_split=Wh, a_split_stride=Lp * Wh, shape=(Lp, C))
         T.end("gemm_o")
 
+    def _cross_kv(self, ctx: Tensor):
+        """K | V of the embedded context for every block in one GEMM (+ the image branch for 14B), RMSNorm on the K
+        halves. Returns per-block (kv_text, kv_img or None) views of [S, 2C]."""
+        C, D = self.dim, self.head_dim
+        n_img = 257 if self.variant == "14b" else 0
+        ctx_txt = ctx[n_img:]
+        kv_all = self._buf("ckv_all", (ctx_txt.shape[0], self.layers * 2 * C), _BF16)
+        ops.gemm(ctx_txt, self.cw_kv_all, self.cb_kv_all, kv_all, ops.YB_EPI_BF16)
+        kvi_all = None
+        if n_img:
+            kvi_all = self._buf("ckv_img_all", (n_img, self.layers * 2 * C), _BF16)
+            ops.gemm(ctx[:n_img], self.cw_kv_img_all, self.cb_kv_img_all, kvi_all, ops.YB_EPI_BF16)
+        out = []
+        for i, b in enumerate(self.blocks):
+            kv = kv_all[:, i * 2 * C:(i + 1) * 2 * C]
+            ops.rmsnorm_rope(kv[:, :C], b["cnk"], None, D, self.eps)
+            kvi = None
+            if kvi_all is not None:
+                kvi = kvi_all[:, i * 2 * C:(i + 1) * 2 * C]
+                ops.rmsnorm_rope(kvi[:, :C], b["cnk_img"], None, D, self.eps)
+            out.append((kv, kvi))
+        return out
+
     def _block(self, i: int, xs: Tensor, mod: Tensor, tok_idx: Optional[Tensor], rope: Tensor, rope_len: int,
                ctx: Tensor, L_true: Optional[int] = None) -> None:
         """One WanAttentionBlock in place on the fp32 residual stream xs [L, C] (a token shard under Ulysses)."""
@@ -457,7 +488,7 @@ class WanDiT:
             self._self_attention_sp(i, b, h, xs, m, tok_idx, rope, rope_len, L_true if L_true is not None else L)
         else:
             self._self_attention_local(b, h, qkv, att, xs, m, tok_idx, rope, rope_len)
-        self._cross_and_ffn(b, xs, h, qkv, att, m, tok_idx, ctx)
+        self._cross_and_ffn(b, xs, h, qkv, att, m, tok_idx, ctx[i] if isinstance(ctx, list) else self._cross_kv(ctx)[i])
 
     def _self_attention_local(self, b, h, qkv, att, xs, m, tok_idx, rope, rope_len) -> None:
         C, H, D, T = self.dim, self.heads, self.head_dim, self.timer
@@ -483,18 +514,11 @@ class WanDiT:
         q2 = qkv[:, :C]
         ops.gemm(h, b["cw_q"], b["cb_q"], q2, ops.YB_EPI_BF16)
         ops.rmsnorm_rope(q2, b["cnq"], None, D, self.eps)
-        n_img = 257 if self.variant == "14b" else 0
-        ctx_txt = ctx[n_img:]
-        kv = self._buf("ckv", (ctx_txt.shape[0], 2 * C), _BF16)
-        ops.gemm(ctx_txt, b["cw_kv"], b["cb_kv"], kv, ops.YB_EPI_BF16)
-        ops.rmsnorm_rope(kv[:, :C], b["cnk"], None, D, self.eps)
+        kv, kvi = ctx                                            # this block's normalised K | V (see _cross_kv)
         T.begin("cross_attention")
         ops.attention(q2, kv[:, :C], kv[:, C:], att, H)
         T.end("cross_attention")
-        if n_img:
-            kvi = self._buf("ckv_img", (n_img, 2 * C), _BF16)
-            ops.gemm(ctx[:n_img], b["cw_kv_img"], b["cb_kv_img"], kvi, ops.YB_EPI_BF16)
-            ops.rmsnorm_rope(kvi[:, :C], b["cnk_img"], None, D, self.eps)
+        if kvi is not None:
             ops.attention(q2, kvi[:, :C], kvi[:, C:], att, H, accumulate=True)
         ops.gemm(att, b["cw_o"], b["cb_o"], xs, ops.YB_EPI_GATE_RES)
         # --- FFN ---
@@ -520,7 +544,7 @@ class WanDiT:
             e0, tok_idx = e.reshape(L, 6 * C).contiguous(), torch.arange(L, device=self.device, dtype=torch.int32)
         mod = ops.bcast_add(self.block_mod, e0).view(self.layers, e0.shape[0], 6, C)
         rope = self._rope_table([(grid[0], grid[1], grid[2], 0)])
-        ctx = context.to(device=self.device, dtype=_BF16).contiguous()
+        ctx = self._cross_kv(context.to(device=self.device, dtype=_BF16).contiguous())
         self._block(i, xs, mod, tok_idx, rope, rope.shape[0], ctx)
         return xs
 
@@ -619,7 +643,7 @@ class WanDiT:
         head_tab = head_parts[0] if len(head_parts) == 1 else torch.cat(head_parts, dim=0).contiguous()
 
         # ---- context -----------------------------------------------------------------------------------
-        ctx = self._context(context.to(device=dev), clip_fea)
+        ctx = self._cross_kv(self._context(context.to(device=dev), clip_fea))
 
         # ---- Ulysses: keep only this rank's contiguous token shard --------------------------------------
         L_true = L
