@@ -417,9 +417,50 @@ def vae_arm(args):
                       "gpu_launches": ops.launch_count(), "finite": bool(torch.isfinite(out).all())}), flush=True)
 
 
+def vae22_arm(args):
+    """Supplementary workload: Wan2.2 VAE decode of the 5B sampler's latent z [48,21,44,80]
+    -> video [3,81,704,1280] (vae2_2.py `Wan2_2_VAE.decode`), random-init weights at the real widths."""
+    from yume_b200 import ops
+    from yume_b200.vae22 import Wan22VaeDecoder, decoder_param_shapes
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    g = torch.Generator(device=dev).manual_seed(0)
+    sd = {}
+    for name, shape in decoder_param_shapes().items():
+        t = torch.randn(shape, generator=g, device=dev)
+        if name.endswith(".bias"):
+            t = 0.05 * t
+        elif name.endswith(".gamma"):
+            t = 1 + 0.1 * t
+        else:
+            t = t * (0.8 / math.sqrt(math.prod(shape[1:])))
+        sd[name] = t
+    eng = Wan22VaeDecoder(sd, device=dev)
+    T, H, W = (21, 44, 80) if not args.quick else (5, 16, 16)
+    z = torch.randn(48, T, H, W, generator=g, device=dev)
+    for _ in range(args.warmup):
+        eng.decode(z)
+    torch.cuda.synchronize()
+    ops.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = eng.decode(z)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({"metric": "decoded_frames_per_sec", "value": out.shape[1] / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": f"Wan2.2 VAE whole-sequence decode z[48,{T},{H},{W}] -> {tuple(out.shape)}"},
+                      "gpu_launches": ops.launch_count(), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
+                      "finite": bool(torch.isfinite(out).all())}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="dit", choices=["dit", "vae"])
+    ap.add_argument("--workload", default="dit", choices=["dit", "vae", "vae22"])
     ap.add_argument("--config", default="5b-720p", choices=["5b-720p", "5b-chunk", "14b-chunk"],
                     help="5b-720p is the headline workload (BASELINE.json configs[1]); the others are supplementary")
     ap.add_argument("--gpus", type=int, default=1)
@@ -433,6 +474,8 @@ def main():
     args = ap.parse_args()
     if args.workload == "vae":
         vae_arm(args)
+    elif args.workload == "vae22":
+        vae22_arm(args)
     elif args.config != "5b-720p":
         chunk_arm(args)
     elif args.impl == "reference":

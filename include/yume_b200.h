@@ -82,6 +82,15 @@ typedef struct yb_conv3d_args {
   long long ldo, res_ld;
   int T, H, W, Cp, Cout;
   int epilogue;
+  /* Generalisations used by the Wan2.2 VAE (wan23/modules/vae2_2.py); all-zero = the 3x3x3 replicate-padded form above.
+   *   kt, kh, kw     taps per axis, each 1 or 3 (0 = 3): Conv2d 3x3 is (1,3,3), Resample.time_conv is (3,1,1)
+   *   oob_zero_pad   1: `xpad` is the UNPADDED [T, H, W, Cp] activation and the causal zero padding (kt-1 in front,
+   *                  kh/2, kw/2 around; vae2_2.py:22-44) is TMA out-of-bounds zero fill — no padded buffer exists
+   *   out_t_mul/add  output frame of input frame t is t*out_t_mul + out_t_add (0 = identity): interleaves the two
+   *                  channel groups of time_conv into consecutive frames (vae2_2.py:151-154) */
+  int kt, kh, kw;
+  int oob_zero_pad;
+  int out_t_mul, out_t_add;
 } yb_conv3d_args;
 int yb_conv3d_causal(const yb_conv3d_args* args, void* stream);
 
@@ -203,6 +212,18 @@ int yb_nhwc_to_nchw_f32(const void* x, long long ldx, void* out, long long N, in
 /* Tile cross-fade (blend_v / blend_h / blend_t, autoencoder_kl_causal_3d.py:343-359) on contiguous f32 tiles:
  * b[o, y, i] = a[o, ea-ext+y, i] * (1 - y/ext) + b[o, y, i] * (y/ext) for y < ext; a is [outer, ea, inner], b [outer, eb, inner]. */
 int yb_blend(const void* a, void* b, long long outer, int ea, int eb, int ext, long long inner, void* stream);
+
+/* Wan2.2 VAE decoder glue (wan23/modules/vae2_2.py), channels-last bf16:
+ *   yb_vae_rms_act: out[T, Hs*up, Ws*up, Cp] = [SiLU]([RMS_norm over channels * gamma](x)) nearest-exact upsampled by
+ *     `up` in {1,2} (RMS_norm :47-61 = F.normalize * sqrt(C) * gamma; Upsample :64-70). gamma NULL = no norm.
+ *   yb_vae_dupup_add: main += DupUp3D(x) over the whole frame sequence, first ft-1 duplicated frames dropped
+ *     (:376-418, :499-503). main bf16 [ft*Ts-(ft-1), Hs*fs, Ws*fs, out_c], x bf16 [Ts, Hs, Ws, in_c], both dense.
+ *   yb_vae_unpatchify2_clamp: y f32 [T*H*W, ldy] (12 channels) -> out f32 [3, T, 2H, 2W] clamped to [-1,1]
+ *     (unpatchify :305-319; Wan2_2_VAE.decode :1066-1067). */
+int yb_vae_rms_act(const void* x, long long ldx, void* out, const void* gamma, int T, int Hs, int Ws, int C, int Cp, int up,
+                   int silu, void* stream);
+int yb_vae_dupup_add(void* main_, const void* x, int Ts, int Hs, int Ws, int in_c, int out_c, int ft, int fs, void* stream);
+int yb_vae_unpatchify2_clamp(const void* y, long long ldy, void* out, int T, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Self-test of the tcgen05 building blocks on one 128x128x128 tile (used by tests/, not by the product path).

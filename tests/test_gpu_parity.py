@@ -452,3 +452,97 @@ def test_vae_decode_real_width_tile_vs_oracle(dev):
     want = hyvae.HyVaeOracle(sd, **cfg).decode(z)
     got = HyVaeDecoder(sd, device=dev, **cfg).decode(z).cpu()
     assert got.shape == want.shape and rel(got, want) < VAE_TOL
+
+
+# ---- Wan2.2 VAE (wan23/modules/vae2_2.py) -------------------------------------------------------------------------
+@pytest.mark.parametrize("taps,T,H,W,ci,co,tm,ta", [((3, 3, 3), 3, 8, 8, 64, 64, 1, 0), ((1, 3, 3), 4, 6, 10, 128, 96, 1, 0),
+                                                     ((3, 1, 1), 3, 5, 8, 64, 128, 2, 1), ((3, 1, 1), 3, 5, 8, 64, 128, 2, 2),
+                                                     ((3, 3, 3), 1, 18, 32, 128, 32, 1, 0), ((3, 3, 3), 5, 40, 24, 64, 64, 1, 0),
+                                                     ((1, 3, 3), 2, 130, 9, 64, 64, 1, 0)])
+def test_conv3d_zero_pad_tap_modes(dev, taps, T, H, W, ci, co, tm, ta):
+    """CausalConv3d with ZERO padding taken from TMA out-of-bounds fill, (kt,kh,kw) taps and interleaved output frames."""
+    from yume_b200 import ops
+    kt, kh, kw = taps
+    g = torch.Generator(device="cpu").manual_seed(T * 100 + H + kt)
+    x = torch.randn(T, H, W, ci, generator=g).to(dev).bfloat16()
+    wt = (torch.randn(co, ci, kt, kh, kw, generator=g) / math.sqrt(kt * kh * kw * ci)).to(dev).bfloat16()
+    b = torch.randn(co, generator=g).to(dev)
+    wk = wt.permute(0, 2, 3, 4, 1).reshape(co, kt * kh * kw * ci).contiguous()
+    To = (T - 1) * tm + ta + 1
+    out = torch.full((To * H * W, co), 7.0, device=dev, dtype=torch.bfloat16)
+    ops.conv3d_causal(x, wk, b, out, T, H, W, ops.YB_EPI_BF16, taps=taps, oob_zero_pad=True, out_t_mul=tm, out_t_add=ta)
+    xn = torch.nn.functional.pad(x.float().permute(3, 0, 1, 2)[None], (kw // 2, kw // 2, kh // 2, kh // 2, kt - 1, 0))
+    ref = torch.nn.functional.conv3d(xn, wt.float(), b)[0].permute(1, 2, 3, 0)             # [T, H, W, co]
+    got = out.view(To, H, W, co).float()
+    written = torch.zeros(To, dtype=torch.bool)
+    written[ta::tm][:T] = True
+    assert rel(got[written.to(dev)], ref) < KERNEL_TOL
+    assert bool((got[(~written).to(dev)] == 7.0).all())                                     # other frames untouched
+
+
+def test_wan22_vae_glue_kernels(dev):
+    from oracle import wan22vae
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(21)
+    T, H, W, C = 3, 4, 6, 96
+    x = (torch.randn(T * H * W, C, generator=g) * 1.5).to(dev).bfloat16()
+    gamma = (1 + 0.1 * torch.randn(C, generator=g)).to(dev)
+    xn = x.float().view(T, H, W, C).permute(3, 0, 1, 2)[None]                              # [1, C, T, H, W]
+    # RMS_norm * gamma, SiLU, nearest-exact 2x, channel pad to 128
+    out = torch.empty(T, 2 * H, 2 * W, 128, device=dev, dtype=torch.bfloat16)
+    ops.vae_rms_act(x, (T, H, W), out, gamma, 2, True)
+    y = torch.nn.functional.silu(wan22vae.rms_norm(xn, gamma))[0].permute(1, 0, 2, 3)       # [T, C, H, W]
+    y = torch.nn.functional.interpolate(y, scale_factor=(2.0, 2.0), mode="nearest-exact").permute(0, 2, 3, 1)
+    assert rel(out[..., :C], y) < 6e-3 and bool((out[..., C:] == 0).all())
+    out1 = torch.empty(T, H, W, 128, device=dev, dtype=torch.bfloat16)
+    ops.vae_rms_act(x, (T, H, W), out1, None, 1, False)                                     # plain channel-pad copy
+    assert torch.equal(out1[..., :C].reshape(-1, C), x)
+    # DupUp3D shortcut add, both factor_t, against the oracle's whole-sequence form
+    for ft, co in ((2, 48), (1, 96), (2, 96)):
+        To = ft * T - (ft - 1)
+        main = torch.randn(To * 2 * H * 2 * W, co, generator=g).to(dev).bfloat16()
+        want = main.float().view(To, 2 * H, 2 * W, co) + wan22vae.Wan22VaeOracle.dup_up(xn, co, ft, 2)[0].permute(1, 2, 3, 0)
+        ops.vae_dupup_add(main, x, (T, H, W), C, co, ft, 2)
+        assert rel(main.view(To, 2 * H, 2 * W, co), want) < 6e-3
+    # head: [N, 32] f32 (12 used) -> unpatchify(2) + clamp
+    yh = (torch.randn(T * H * W, 32, generator=g) * 0.8).to(dev)
+    o = torch.empty(3, T, 2 * H, 2 * W, device=dev)
+    ops.vae_unpatchify2_clamp(yh, o, T, H, W)
+    v = yh[:, :12].view(T, H, W, 12).permute(3, 0, 1, 2)[None]
+    want = v.view(1, 3, 2, 2, T, H, W).permute(0, 1, 4, 5, 3, 6, 2).reshape(3, T, 2 * H, 2 * W).clamp(-1, 1)
+    assert torch.equal(o, want)
+
+
+@pytest.fixture(scope="module")
+def vae22_gold(dev, golden_dir):
+    from oracle import wan22vae
+    g = torch.load(golden_dir / "wan22vae_tiny.pt", weights_only=False)
+    return g, wan22vae.make_state_dict(g["seed_w"], **g["cfg"])
+
+
+@pytest.mark.parametrize("case", ["t1", "t2", "t5", "t3_wide"])
+def test_wan22_vae_decode_vs_reference_golden(dev, vae22_gold, case):
+    """One-pass whole-sequence decode on the GPU against the reference's own chunked / feature-cached decode."""
+    from yume_b200.vae22 import Wan22VaeDecoder
+    g, sd = vae22_gold
+    c = g["cases"][case]
+    eng = Wan22VaeDecoder(sd, mean=g["mean"], std=g["std"], device=dev, **g["cfg"])
+    z = torch.randn(g["cfg"]["z_dim"], c["T"], c["H"], c["W"], generator=torch.Generator().manual_seed(c["seed"]))
+    out = eng.decode(z).cpu()
+    assert tuple(out.shape) == c["shape"]
+    for name, got in (("sample", out[..., ::3, ::3]), ("rowsum", out.sum(-1)), ("colsum", out.sum(-2))):
+        assert float((got - c[name]).norm() / c[name].norm()) < VAE_TOL, name
+
+
+def test_wan22_vae_decode_real_width_vs_oracle(dev):
+    """Real channel widths (dec_dim 256, z_dim 48 -> 1024/1024/1024/512/256) on a small latent against the fp32 oracle."""
+    from oracle import wan22vae
+    from yume_b200.vae22 import Wan22VaeDecoder
+    cfg = dict(dec_dim=256, z_dim=48, dim_mult=(1, 2, 4, 4), num_res_blocks=2, temperal_upsample=(True, True, False))
+    sd = wan22vae.make_state_dict(31, **cfg)
+    gen = torch.Generator().manual_seed(6)
+    mean, std = 0.2 * torch.randn(48, generator=gen), 0.5 + torch.rand(48, generator=gen)
+    z = torch.randn(48, 2, 2, 4, generator=gen)
+    want = wan22vae.Wan22VaeOracle(sd, mean=mean, std=std, **cfg).decode(z)
+    got = Wan22VaeDecoder(sd, mean=mean, std=std, device=dev, **cfg).decode(z).cpu()
+    assert got.shape == want.shape and rel(got, want) < VAE_TOL

@@ -134,3 +134,37 @@ def test_mirror_state_dict_keys_match_reference_names():
         have = {k: tuple(v.shape) for k, v in m.state_dict().items()}
         want = synth.param_shapes(cfg)
         assert have == {k: tuple(v) for k, v in want.items()}
+
+
+def test_wan22_vae_repack_folds_are_exact():
+    """Host-side weight folding of the Wan2.2 VAE engine (no GPU): conv2 absorbs z*std+mean, proj absorbs the v bias."""
+    import torch
+    from oracle import wan22vae
+    from yume_b200.vae22 import Wan22VaeDecoder, decoder_param_shapes
+    cfg = dict(dec_dim=32, z_dim=16, dim_mult=(1, 2, 4, 4), num_res_blocks=2, temperal_upsample=(True, True, False))
+    assert decoder_param_shapes(**cfg) == wan22vae.param_shapes(**cfg)
+    assert decoder_param_shapes() == wan22vae.param_shapes()
+    sd = wan22vae.make_state_dict(3, **cfg)
+    g = torch.Generator().manual_seed(0)
+    mean, std = torch.randn(16, generator=g), 0.5 + torch.rand(16, generator=g)
+    eng = Wan22VaeDecoder(sd, mean=mean, std=std, device="cpu", **cfg)
+    z = torch.randn(7, 16, generator=g)
+    w2, b2 = eng.lin["conv2"]
+    want = (z * std + mean) @ sd["conv2.weight"].reshape(16, 16).T + sd["conv2.bias"]
+    got = z @ w2.float()[:16, :16].T + b2[:16]
+    assert float((got - want).norm() / want.norm()) < 1e-2          # bf16 weights
+    assert bool((w2.float()[16:] == 0).all()) and bool((w2.float()[:, 16:] == 0).all())
+    # time_conv split into two frame groups; Conv2d becomes (1,3,3) taps; every conv K is taps * Cp (Cp % 64 == 0)
+    p = "decoder.upsamples.0.upsamples.3"
+    assert eng.conv[p + ".time_conv.0"][2] == (3, 1, 1) and eng.conv[p + ".resample.1"][2] == (1, 3, 3)
+    wt = sd[p + ".time_conv.weight"]
+    C = wt.shape[1]
+    w0 = eng.conv[p + ".time_conv.1"][0].float().view(C, 3, -1)[:, :, :C]
+    assert torch.equal(w0, wt[C:, :, :, 0, 0].permute(0, 2, 1).bfloat16().float())
+    for name, (w, b, taps) in eng.conv.items():
+        assert w.shape[1] % (64 * taps[0] * taps[1] * taps[2]) == 0 and w.shape[0] % 32 == 0 and b.shape[0] == w.shape[0], name
+    # v bias folded through proj
+    a = "decoder.middle.1"
+    Cq = eng.dims[0]
+    Wo = sd[a + ".proj.weight"].reshape(Cq, Cq)
+    assert torch.allclose(eng.att["bo"], sd[a + ".proj.bias"] + Wo @ sd[a + ".to_qkv.bias"][2 * Cq:], atol=1e-6)

@@ -44,6 +44,8 @@ class Conv3dArgs(C.Structure):
         ("xpad", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p), ("res", C.c_void_p),
         ("ldo", C.c_longlong), ("res_ld", C.c_longlong),
         ("T", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cp", C.c_int), ("Cout", C.c_int), ("epilogue", C.c_int),
+        ("kt", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("oob_zero_pad", C.c_int), ("out_t_mul", C.c_int),
+        ("out_t_add", C.c_int),
     ]
 
 
@@ -59,6 +61,9 @@ SIGNATURES = {
     "yb_nchw_to_nhwc_bf16": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
     "yb_nhwc_to_nchw_f32": (_i, [_vp, _ll, _vp, _ll, _i, _vp]),
     "yb_blend": (_i, [_vp, _vp, _ll, _i, _i, _i, _ll, _vp]),
+    "yb_vae_rms_act": (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "yb_vae_dupup_add": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "yb_vae_unpatchify2_clamp": (_i, [_vp, _ll, _vp, _i, _i, _i, _vp]),
     "yb_ln_modulate": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp, _ll, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "yb_rmsnorm_rope": (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "yb_rmsnorm_rope_pieces": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp]),

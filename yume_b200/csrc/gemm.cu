@@ -47,6 +47,10 @@ struct GemmParams {
   int conv, cin_chunks;
   int TW, TH, TT, tiles_w, tiles_h;
   int cT, cH, cW;
+  int kh, kw;                   // spatial taps (tap = (dt*kh + dh)*kw + dw)
+  int off_t, off_h, off_w;      // subtracted from the box coordinates: 0 when the padding is materialised in the input,
+                                // (kt-1, kh/2, kw/2) when it is TMA out-of-bounds zero fill on the unpadded input
+  int out_t_mul, out_t_add;     // output frame of input frame t = t*out_t_mul + out_t_add (time_conv interleave)
   int num_m_tiles, num_n_tiles;
 };
 
@@ -131,11 +135,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // tap (dt, dh, dw) reads padded voxel (t + dt, h + dh, w + dw): P[tp][hp][wp] = X[max(tp-2,0)][clamp(hp-1)]
             // [clamp(wp-1)] — temporal pad 2 in front only (causal), replicate everywhere
             const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
-            const int dt = tap / 9, dh = (tap / 3) % 3, dw = tap % 3;
+            const int dt = tap / (p.kh * p.kw), dh = (tap / p.kw) % p.kh, dw = tap % p.kw;
             const int per_t = p.tiles_h * p.tiles_w;
             const int it = m_tile / per_t, rem = m_tile - it * per_t;
             const int ih = rem / p.tiles_w, iw = rem - ih * p.tiles_w;
-            tma_load_4d(sa, &tmA, &full_bar[stage], cc * GEMM_BLOCK_K, iw * p.TW + dw, ih * p.TH + dh, it * p.TT + dt);
+            tma_load_4d(sa, &tmA, &full_bar[stage], cc * GEMM_BLOCK_K, iw * p.TW + dw - p.off_w,
+                        ih * p.TH + dh - p.off_h, it * p.TT + dt - p.off_t);
           } else {
             const int chunk = kcol / p.a_split;
             tma_load_3d(sa, &tmA, &full_bar[stage], kcol - chunk * p.a_split, m_tile * GEMM_BLOCK_M, chunk);
@@ -208,7 +213,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int ih = rem / p.tiles_w, iw = rem - ih * p.tiles_w;
           const int tw = r % p.TW, th = (r / p.TW) % p.TH, tt = r / (p.TW * p.TH);
           const int t = it * p.TT + tt, h = ih * p.TH + th, w = iw * p.TW + tw;
-          my_row = (t < p.cT && h < p.cH && w < p.cW) ? (t * p.cH + h) * p.cW + w : -1;
+          my_row = (t < p.cT && h < p.cH && w < p.cW) ? ((t * p.out_t_mul + p.out_t_add) * p.cH + h) * p.cW + w : -1;
         } else {
           const int row = m_tile * GEMM_BLOCK_M + r;
           my_row = row < p.M ? row : -1;
@@ -452,12 +457,21 @@ extern "C" int yb_conv3d_causal(const yb_conv3d_args* a, void* stream_) {
   p.tiles_w = (a->W + p.TW - 1) / p.TW;
   p.tiles_h = (a->H + p.TH - 1) / p.TH;
   const int tiles_t = (a->T + p.TT - 1) / p.TT;
+  const int kt = a->kt > 0 ? a->kt : 3, kh = a->kh > 0 ? a->kh : 3, kw = a->kw > 0 ? a->kw : 3;
+  if ((kt != 1 && kt != 3) || (kh != 1 && kh != 3) || (kw != 1 && kw != 3)) return YB_ERR_SHAPE;
+  const int taps = kt * kh * kw;
   p.conv = 1;
   p.cin_chunks = a->Cp / 64;
   p.cT = a->T; p.cH = a->H; p.cW = a->W;
+  p.kh = kh; p.kw = kw;
+  p.off_t = a->oob_zero_pad ? kt - 1 : 0;
+  p.off_h = a->oob_zero_pad ? kh / 2 : 0;
+  p.off_w = a->oob_zero_pad ? kw / 2 : 0;
+  p.out_t_mul = a->out_t_mul > 0 ? a->out_t_mul : 1;
+  p.out_t_add = a->out_t_add;
   p.M = a->T * a->H * a->W;
   p.N = a->Cout;
-  p.K = 27 * a->Cp;
+  p.K = taps * a->Cp;
   p.num_m_tiles = tiles_t * p.tiles_h * p.tiles_w;
   p.bias = static_cast<const float*>(a->bias);
   p.out = a->out;
@@ -468,9 +482,11 @@ extern "C" int yb_conv3d_causal(const yb_conv3d_args* a, void* stream_) {
   p.res_ld = a->res_ld;
   const int block_n = (a->Cout % 256 == 0) ? 256 : 128;
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_bf16_4d(&tmA, a->xpad, a->T + 2, a->H + 2, a->W + 2, a->Cp, p.TT, p.TH, p.TW, 64);
+  const int padT = a->oob_zero_pad ? 0 : kt - 1, padH = a->oob_zero_pad ? 0 : kh - 1, padW = a->oob_zero_pad ? 0 : kw - 1;
+  int rc = make_tmap_bf16_4d(&tmA, a->xpad, a->T + padT, a->H + padH, a->W + padW, a->Cp, p.TT, p.TH, p.TW, 64);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmB, a->w, a->Cout, 27ull * a->Cp, 27ull * a->Cp, block_n, GEMM_BLOCK_K);
+  rc = make_tmap_bf16_2d(&tmB, a->w, a->Cout, static_cast<uint64_t>(taps) * a->Cp, static_cast<uint64_t>(taps) * a->Cp,
+                         block_n, GEMM_BLOCK_K);
   if (rc) return rc;
 #define YB_CONV_DISPATCH(BN)                                                                 \
   switch (a->epilogue) {                                                                     \

@@ -206,6 +206,108 @@ __global__ void blend_kernel(const float* __restrict__ a, float* __restrict__ b,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Wan2.2 VAE glue (wan23/modules/vae2_2.py).
+// rms_act: one warp per OUTPUT voxel: [RMS_norm over channels (F.normalize * sqrt(C) * gamma, :47-61)] -> [SiLU] ->
+// nearest-exact 2x spatial upsample (:64-70, Resample :95-101), written channels-last [T, H*f, W*f, Cp] (no padding:
+// the conv takes its zero padding from TMA out-of-bounds fill).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rms_act_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out, const float* __restrict__ gamma,
+               int T, int Hs, int Ws, int C, int Cp, int f, int silu) {
+  const int H = Hs * f, W = Ws * f;
+  const long long nvox = static_cast<long long>(T) * H * W;
+  const int lane = threadIdx.x & 31;
+  const int chunks = Cp >> 3;
+  for (long long v = blockIdx.x * 8LL + (threadIdx.x >> 5); v < nvox; v += gridDim.x * 8LL) {
+    const int w = static_cast<int>(v % W);
+    const int h = static_cast<int>((v / W) % H);
+    const int t = static_cast<int>(v / (static_cast<long long>(W) * H));
+    const long long src = (static_cast<long long>(t) * Hs + h / f) * Ws + w / f;
+    const __nv_bfloat16* xs = x + src * ldx;
+    float ss = 0.f;
+    if (gamma) {
+      for (int c = lane; c < (C >> 3); c += 32) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(xs + c * 8);
+        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = __bfloat1622float2(hh[k]);
+          ss += a.x * a.x + a.y * a.y;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    const float scl = gamma ? sqrtf(static_cast<float>(C)) / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+    for (int c = lane; c < chunks; c += 32) {
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (c * 8 < C) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(xs + c * 8);
+        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        float y[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = __bfloat1622float2(hh[k]);
+          y[2 * k] = a.x;
+          y[2 * k + 1] = a.y;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (gamma) y[k] = y[k] * scl * __ldg(gamma + c * 8 + k);
+          if (silu) y[k] = y[k] / (1.f + __expf(-y[k]));
+        }
+        o = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+      }
+      *reinterpret_cast<uint4*>(out + v * Cp + c * 8) = o;
+    }
+  }
+}
+
+// main[f', h', w', oc] += x[t, h, w, ci]: the DupUp3D shortcut (:376-418) of Up_ResidualBlock (:499-503) on the whole
+// sequence, first ft-1 duplicated frames dropped. d = f' + ft - 1, t = d / ft, a = d % ft, e = ((oc*ft + a)*fs + b)*fs + c,
+// ci = e / rep with rep = out_c*ft*fs*fs / in_c.
+__global__ void dupup_add_kernel(__nv_bfloat16* __restrict__ main_, const __nv_bfloat16* __restrict__ x, int Ts, int Hs,
+                                 int Ws, int in_c, int out_c, int ft, int fs) {
+  const int To = ft * Ts - (ft - 1), Ho = Hs * fs, Wo = Ws * fs;
+  const int rep = out_c * ft * fs * fs / in_c;
+  const long long total = static_cast<long long>(To) * Ho * Wo * out_c;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int oc = static_cast<int>(i % out_c);
+    long long v = i / out_c;
+    const int wo = static_cast<int>(v % Wo);
+    v /= Wo;
+    const int ho = static_cast<int>(v % Ho);
+    const int fo = static_cast<int>(v / Ho);
+    const int d = fo + ft - 1;
+    const int t = d / ft, a = d % ft;
+    const int e = ((oc * ft + a) * fs + (ho % fs)) * fs + (wo % fs);
+    const int ci = e / rep;
+    const float add = __bfloat162float(x[((static_cast<long long>(t) * Hs + ho / fs) * Ws + wo / fs) * in_c + ci]);
+    main_[i] = __float2bfloat16_rn(__bfloat162float(main_[i]) + add);
+  }
+}
+
+// y f32 [T*H*W, ldy] (12 valid channels) -> out f32 [3, T, 2H, 2W], clamp to [-1, 1]:
+// unpatchify 'b (c r q) f h w -> b c f (h q) (w r)' (:305-319) + Wan2_2_VAE.decode's clamp_ (:1066-1067)
+__global__ void unpatchify2_clamp_kernel(const float* __restrict__ y, long long ldy, float* __restrict__ out, int T, int H,
+                                         int W) {
+  const long long total = 3LL * T * (2 * H) * (2 * W);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int wo = static_cast<int>(i % (2 * W));
+    long long v = i / (2 * W);
+    const int ho = static_cast<int>(v % (2 * H));
+    v /= (2 * H);
+    const int f = static_cast<int>(v % T);
+    const int c = static_cast<int>(v / T);
+    const int q = ho & 1, r = wo & 1;
+    const float val = y[((static_cast<long long>(f) * H + (ho >> 1)) * W + (wo >> 1)) * ldy + (c * 2 + r) * 2 + q];
+    out[i] = fminf(fmaxf(val, -1.f), 1.f);
+  }
+}
+
 inline int grid_for(long long total) {
   long long b = (total + 255) / 256;
   const long long cap = 148LL * 16;
@@ -282,4 +384,36 @@ extern "C" int yb_blend(const void* a, void* b, long long outer, int ea, int eb,
       static_cast<const float*>(a), static_cast<float*>(b), outer, ea, eb, ext, inner,
       static_cast<long long>(ea) * inner, static_cast<long long>(eb) * inner);
   return check_launch("blend");
+}
+
+
+extern "C" int yb_vae_rms_act(const void* x, long long ldx, void* out, const void* gamma, int T, int Hs, int Ws, int C,
+                              int Cp, int up, int silu, void* stream_) {
+  if (!x || !out || T <= 0 || Hs <= 0 || Ws <= 0 || C <= 0) return YB_ERR_ARG;
+  if (C % 8 != 0 || Cp % 8 != 0 || Cp < C || (up != 1 && up != 2)) return YB_ERR_SHAPE;
+  if ((ldx % 8) || (reinterpret_cast<uintptr_t>(x) & 0xF) || (reinterpret_cast<uintptr_t>(out) & 0xF)) return YB_ERR_ALIGNMENT;
+  const long long nvox = static_cast<long long>(T) * Hs * up * Ws * up;
+  long long blocks = (nvox + 7) / 8;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  rms_act_kernel<<<static_cast<int>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), static_cast<const float*>(gamma), T, Hs,
+      Ws, C, Cp, up, silu);
+  return check_launch("vae_rms_act");
+}
+
+extern "C" int yb_vae_dupup_add(void* main_, const void* x, int Ts, int Hs, int Ws, int in_c, int out_c, int ft, int fs,
+                                void* stream_) {
+  if (!main_ || !x || Ts <= 0 || Hs <= 0 || Ws <= 0 || in_c <= 0 || out_c <= 0 || ft < 1 || fs < 1) return YB_ERR_ARG;
+  if ((out_c * ft * fs * fs) % in_c != 0) return YB_ERR_SHAPE;
+  const long long total = static_cast<long long>(ft * Ts - (ft - 1)) * Hs * fs * Ws * fs * out_c;
+  dupup_add_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<__nv_bfloat16*>(main_), static_cast<const __nv_bfloat16*>(x), Ts, Hs, Ws, in_c, out_c, ft, fs);
+  return check_launch("vae_dupup_add");
+}
+
+extern "C" int yb_vae_unpatchify2_clamp(const void* y, long long ldy, void* out, int T, int H, int W, void* stream_) {
+  if (!y || !out || T <= 0 || H <= 0 || W <= 0 || ldy < 12) return YB_ERR_ARG;
+  unpatchify2_clamp_kernel<<<grid_for(12LL * T * H * W), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const float*>(y), ldy, static_cast<float*>(out), T, H, W);
+  return check_launch("vae_unpatchify2_clamp");
 }

@@ -250,20 +250,26 @@ YB_EPI_RES_BF16 = YB_EPI_RES_BF16
 
 
 def conv3d_causal(xpad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, T: int, H: int,
-                  W: int, epilogue: int = YB_EPI_BF16, res: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """xpad bf16 [T+2, H+2, W+2, Cp] (replicate padded, channels last), w bf16 [Cout, 27*Cp], out [T*H*W, >=Cout]."""
+                  W: int, epilogue: int = YB_EPI_BF16, res: Optional[torch.Tensor] = None, taps=(3, 3, 3),
+                  oob_zero_pad: bool = False, out_t_mul: int = 1, out_t_add: int = 0) -> torch.Tensor:
+    """Implicit-GEMM causal conv. Default: xpad bf16 [T+2, H+2, W+2, Cp] replicate padded (hyvideo VAE). With
+    oob_zero_pad the input is the unpadded [T, H, W, Cp] and the zero padding is TMA out-of-bounds fill (Wan2.2 VAE).
+    w bf16 [Cout, kt*kh*kw*Cp]; out rows are output voxels (frame t -> t*out_t_mul + out_t_add)."""
     global _launches
     _need(xpad, torch.bfloat16, "xpad")
     _need(w, torch.bfloat16, "w")
     Cp = xpad.shape[-1]
-    if tuple(xpad.shape[:3]) != (T + 2, H + 2, W + 2) or not xpad.is_contiguous() or w.shape[1] != 27 * Cp or not w.is_contiguous():
-        raise YumeB200Error("conv3d_causal: bad padded input / weight layout")
+    kt, kh, kw = taps
+    want = (T, H, W) if oob_zero_pad else (T + kt - 1, H + kh - 1, W + kw - 1)
+    if tuple(xpad.shape[:3]) != want or not xpad.is_contiguous() or w.shape[1] != kt * kh * kw * Cp or not w.is_contiguous():
+        raise YumeB200Error("conv3d_causal: bad input / weight layout")
     _need(out, torch.float32 if epilogue == YB_EPI_F32 else torch.bfloat16, "out")
     if res is not None:
         _need(res, torch.bfloat16, "res")
     args = Conv3dArgs(xpad=xpad.data_ptr(), w=w.data_ptr(), bias=_ptr(bias), out=out.data_ptr(), res=_ptr(res),
                       ldo=out.stride(0), res_ld=(res.stride(0) if res is not None else 0), T=T, H=H, W=W, Cp=Cp,
-                      Cout=w.shape[0], epilogue=epilogue)
+                      Cout=w.shape[0], epilogue=epilogue, kt=kt, kh=kh, kw=kw, oob_zero_pad=1 if oob_zero_pad else 0,
+                      out_t_mul=out_t_mul, out_t_add=out_t_add)
     check(_lib.load().yb_conv3d_causal(C.byref(args), _stream()), "yb_conv3d_causal")
     _launches += 1
     return out
@@ -381,3 +387,39 @@ def attention_sp(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out_peer_ptr
                                       _ptr_array(out_peer_ptrs), ldo, q.shape[0], k.shape[0], heads, scale,
                                       len(out_peer_ptrs), rank, Lp, _stream()), "yb_attention_sp")
     _launches += 1
+
+
+def vae_rms_act(x: torch.Tensor, dims, out: torch.Tensor, gamma: Optional[torch.Tensor], up: int = 1, silu: bool = True) -> torch.Tensor:
+    """x bf16 [T*Hs*Ws, C] -> out bf16 [T, Hs*up, Ws*up, Cp] (contiguous): RMS_norm*gamma, SiLU, nearest 2x upsample."""
+    global _launches
+    _need(x, torch.bfloat16, "x")
+    _need(out, torch.bfloat16, "out")
+    T, Hs, Ws = dims
+    if not out.is_contiguous():
+        raise YumeB200Error("vae_rms_act output must be contiguous")
+    check(_lib.load().yb_vae_rms_act(x.data_ptr(), x.stride(0), out.data_ptr(), _ptr(gamma), T, Hs, Ws, x.shape[1],
+                                     out.shape[-1], up, 1 if silu else 0, _stream()), "yb_vae_rms_act")
+    _launches += 1
+    return out
+
+
+def vae_dupup_add(main: torch.Tensor, x: torch.Tensor, dims, in_c: int, out_c: int, ft: int, fs: int) -> torch.Tensor:
+    global _launches
+    _need(main, torch.bfloat16, "main")
+    _need(x, torch.bfloat16, "x")
+    if not (main.is_contiguous() and x.is_contiguous()):
+        raise YumeB200Error("vae_dupup_add needs dense tensors")
+    check(_lib.load().yb_vae_dupup_add(main.data_ptr(), x.data_ptr(), dims[0], dims[1], dims[2], in_c, out_c, ft, fs,
+                                       _stream()), "yb_vae_dupup_add")
+    _launches += 1
+    return main
+
+
+def vae_unpatchify2_clamp(y: torch.Tensor, out: torch.Tensor, T: int, H: int, W: int) -> torch.Tensor:
+    global _launches
+    _need(y, torch.float32, "y")
+    _need(out, torch.float32, "out")
+    check(_lib.load().yb_vae_unpatchify2_clamp(y.data_ptr(), y.stride(0), out.data_ptr(), T, H, W, _stream()),
+          "yb_vae_unpatchify2_clamp")
+    _launches += 1
+    return out
