@@ -212,54 +212,87 @@ __global__ void blend_kernel(const float* __restrict__ a, float* __restrict__ b,
 // nearest-exact 2x spatial upsample (:64-70, Resample :95-101), written channels-last [T, H*f, W*f, Cp] (no padding:
 // the conv takes its zero padding from TMA out-of-bounds fill).
 // ---------------------------------------------------------------------------------------------------------
+template <int NCH>   // 16-byte chunks per lane per voxel (C <= NCH * 256); a warp keeps U = 4 / NCH voxels in flight
 __global__ void __launch_bounds__(256)
 rms_act_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out, const float* __restrict__ gamma,
                int T, int Hs, int Ws, int C, int Cp, int f, int silu) {
+  constexpr int U = 4 / NCH;
   const int H = Hs * f, W = Ws * f;
   const long long nvox = static_cast<long long>(T) * H * W;
   const int lane = threadIdx.x & 31;
-  const int chunks = Cp >> 3;
-  for (long long v = blockIdx.x * 8LL + (threadIdx.x >> 5); v < nvox; v += gridDim.x * 8LL) {
-    const int w = static_cast<int>(v % W);
-    const int h = static_cast<int>((v / W) % H);
-    const int t = static_cast<int>(v / (static_cast<long long>(W) * H));
-    const long long src = (static_cast<long long>(t) * Hs + h / f) * Ws + w / f;
-    const __nv_bfloat16* xs = x + src * ldx;
-    float ss = 0.f;
-    if (gamma) {
-      for (int c = lane; c < (C >> 3); c += 32) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(xs + c * 8);
-        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  const int cch = C >> 3, pch = Cp >> 3;
+  const float sqrt_c = sqrtf(static_cast<float>(C));
+  for (long long v0 = (blockIdx.x * 8LL + (threadIdx.x >> 5)) * U; v0 < nvox; v0 += gridDim.x * 8LL * U) {
+    uint4 raw[U][NCH];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u;
+      const int w = static_cast<int>(v % W);
+      const int h = static_cast<int>((v / W) % H);
+      const int t = static_cast<int>(v / (static_cast<long long>(W) * H));
+      const __nv_bfloat16* xs = x + ((static_cast<long long>(t) * Hs + h / f) * Ws + w / f) * ldx;
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const int c = lane + 32 * j;
+        raw[u][j] = (v < nvox && c < cch) ? *reinterpret_cast<const uint4*>(xs + c * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    float scl[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw[u][j]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 a = __bfloat1622float2(hh[k]);
           ss += a.x * a.x + a.y * a.y;
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      scl[u] = ss;
     }
-    const float scl = gamma ? sqrtf(static_cast<float>(C)) / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
-    for (int c = lane; c < chunks; c += 32) {
-      uint4 o = make_uint4(0u, 0u, 0u, 0u);
-      if (c * 8 < C) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(xs + c * 8);
-        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
-        float y[8];
+    if (gamma) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 a = __bfloat1622float2(hh[k]);
-          y[2 * k] = a.x;
-          y[2 * k + 1] = a.y;
-        }
+      for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (gamma) y[k] = y[k] * scl * __ldg(gamma + c * 8 + k);
-          if (silu) y[k] = y[k] / (1.f + __expf(-y[k]));
-        }
-        o = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        for (int u = 0; u < U; ++u) scl[u] += __shfl_xor_sync(0xffffffffu, scl[u], o);
       }
-      *reinterpret_cast<uint4*>(out + v * Cp + c * 8) = o;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u;
+      if (v >= nvox) break;
+      const float sc = gamma ? sqrt_c / fmaxf(sqrtf(scl[u]), 1e-12f) : 1.f;
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const int c = lane + 32 * j;
+        if (c >= pch) continue;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (c < cch) {
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw[u][j]);
+          float y[8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 a = __bfloat1622float2(hh[k]);
+            y[2 * k] = a.x;
+            y[2 * k + 1] = a.y;
+          }
+          if (gamma) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8 + 4));
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) y[k] = y[k] * sc * gg[k];
+          }
+          if (silu) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) y[k] = y[k] / (1.f + __expf(-y[k]));
+          }
+          o = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        }
+        *reinterpret_cast<uint4*>(out + v * Cp + c * 8) = o;
+      }
     }
   }
 }
@@ -267,25 +300,39 @@ rms_act_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16
 // main[f', h', w', oc] += x[t, h, w, ci]: the DupUp3D shortcut (:376-418) of Up_ResidualBlock (:499-503) on the whole
 // sequence, first ft-1 duplicated frames dropped. d = f' + ft - 1, t = d / ft, a = d % ft, e = ((oc*ft + a)*fs + b)*fs + c,
 // ci = e / rep with rep = out_c*ft*fs*fs / in_c.
-__global__ void dupup_add_kernel(__nv_bfloat16* __restrict__ main_, const __nv_bfloat16* __restrict__ x, int Ts, int Hs,
-                                 int Ws, int in_c, int out_c, int ft, int fs) {
+__global__ void __launch_bounds__(256)
+dupup_add_kernel(__nv_bfloat16* __restrict__ main_, const __nv_bfloat16* __restrict__ x, int Ts, int Hs, int Ws, int in_c,
+                 int out_c, int ft, int fs) {
+  // one thread = 8 consecutive output channels of one output voxel: a 16-byte read-modify-write of main, eight gathers
+  // from the (8x..16x smaller, cache-resident) source voxel
   const int To = ft * Ts - (ft - 1), Ho = Hs * fs, Wo = Ws * fs;
   const int rep = out_c * ft * fs * fs / in_c;
-  const long long total = static_cast<long long>(To) * Ho * Wo * out_c;
+  const int chunks = out_c >> 3;
+  const int estep = ft * fs * fs;
+  const long long total = static_cast<long long>(To) * Ho * Wo * chunks;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int oc = static_cast<int>(i % out_c);
-    long long v = i / out_c;
-    const int wo = static_cast<int>(v % Wo);
-    v /= Wo;
-    const int ho = static_cast<int>(v % Ho);
-    const int fo = static_cast<int>(v / Ho);
+    const int v = static_cast<int>(i / chunks);
+    const int oc = static_cast<int>(i - static_cast<long long>(v) * chunks) << 3;
+    const int wo = v % Wo;
+    const int r = v / Wo;
+    const int ho = r % Ho;
+    const int fo = r / Ho;
     const int d = fo + ft - 1;
     const int t = d / ft, a = d % ft;
-    const int e = ((oc * ft + a) * fs + (ho % fs)) * fs + (wo % fs);
-    const int ci = e / rep;
-    const float add = __bfloat162float(x[((static_cast<long long>(t) * Hs + ho / fs) * Ws + wo / fs) * in_c + ci]);
-    main_[i] = __float2bfloat16_rn(__bfloat162float(main_[i]) + add);
+    const int e0 = ((oc * ft + a) * fs + (ho % fs)) * fs + (wo % fs);
+    const __nv_bfloat16* xs = x + ((static_cast<long long>(t) * Hs + ho / fs) * Ws + wo / fs) * in_c;
+    uint4* mp = reinterpret_cast<uint4*>(main_ + static_cast<long long>(v) * out_c + oc);
+    uint4 raw = *mp;
+    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 m = __bfloat1622float2(hh[k]);
+      const float a0 = __bfloat162float(xs[(e0 + (2 * k) * estep) / rep]);
+      const float a1 = __bfloat162float(xs[(e0 + (2 * k + 1) * estep) / rep]);
+      hh[k] = __floats2bfloat162_rn(m.x + a0, m.y + a1);
+    }
+    *mp = raw;
   }
 }
 
@@ -392,20 +439,32 @@ extern "C" int yb_vae_rms_act(const void* x, long long ldx, void* out, const voi
   if (!x || !out || T <= 0 || Hs <= 0 || Ws <= 0 || C <= 0) return YB_ERR_ARG;
   if (C % 8 != 0 || Cp % 8 != 0 || Cp < C || (up != 1 && up != 2)) return YB_ERR_SHAPE;
   if ((ldx % 8) || (reinterpret_cast<uintptr_t>(x) & 0xF) || (reinterpret_cast<uintptr_t>(out) & 0xF)) return YB_ERR_ALIGNMENT;
+  if (C > 1024) return YB_ERR_SHAPE;
+  if (gamma && (reinterpret_cast<uintptr_t>(gamma) & 0xF)) return YB_ERR_ALIGNMENT;
   const long long nvox = static_cast<long long>(T) * Hs * up * Ws * up;
-  long long blocks = (nvox + 7) / 8;
+  const int nch = C <= 256 ? 1 : (C <= 512 ? 2 : 4);
+  const int per_block = 8 * (4 / nch);
+  long long blocks = (nvox + per_block - 1) / per_block;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
-  rms_act_kernel<<<static_cast<int>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), static_cast<const float*>(gamma), T, Hs,
-      Ws, C, Cp, up, silu);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+#define YB_RMS_LAUNCH(NCH)                                                                                           \
+  rms_act_kernel<NCH><<<static_cast<int>(blocks), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx,            \
+                                                               static_cast<__nv_bfloat16*>(out),                       \
+                                                               static_cast<const float*>(gamma), T, Hs, Ws, C, Cp, up, silu)
+  if (nch == 1) YB_RMS_LAUNCH(1);
+  else if (nch == 2) YB_RMS_LAUNCH(2);
+  else YB_RMS_LAUNCH(4);
+#undef YB_RMS_LAUNCH
   return check_launch("vae_rms_act");
 }
 
 extern "C" int yb_vae_dupup_add(void* main_, const void* x, int Ts, int Hs, int Ws, int in_c, int out_c, int ft, int fs,
                                 void* stream_) {
   if (!main_ || !x || Ts <= 0 || Hs <= 0 || Ws <= 0 || in_c <= 0 || out_c <= 0 || ft < 1 || fs < 1) return YB_ERR_ARG;
-  if ((out_c * ft * fs * fs) % in_c != 0) return YB_ERR_SHAPE;
-  const long long total = static_cast<long long>(ft * Ts - (ft - 1)) * Hs * fs * Ws * fs * out_c;
+  if ((out_c * ft * fs * fs) % in_c != 0 || out_c % 8 != 0) return YB_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(main_) & 0xF) return YB_ERR_ALIGNMENT;
+  if (static_cast<long long>(ft * Ts - (ft - 1)) * Hs * fs * Ws * fs > 0x7fffffffLL) return YB_ERR_SHAPE;
+  const long long total = static_cast<long long>(ft * Ts - (ft - 1)) * Hs * fs * Ws * fs * (out_c / 8);
   dupup_add_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
       static_cast<__nv_bfloat16*>(main_), static_cast<const __nv_bfloat16*>(x), Ts, Hs, Ws, in_c, out_c, ft, fs);
   return check_launch("vae_dupup_add");

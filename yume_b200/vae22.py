@@ -85,11 +85,12 @@ class Wan22VaeDecoder:
         self.t_up, self.n_up = list(temperal_upsample), len(dim_mult)
         mean = torch.zeros(z_dim) if mean is None else mean
         std = torch.ones(z_dim) if std is None else std
-        self._repack(sd, mean.float().cpu(), std.float().cpu())
+        self._repack(sd, mean.detach().to(self.device, _F32), std.detach().to(self.device, _F32))
 
     # ---- weights -------------------------------------------------------------------------------------------
     def _repack(self, sd: Dict[str, Tensor], mean: Tensor, std: Tensor) -> None:
         dev = self.device
+        sd = {k: v.detach().to(dev, _F32) for k, v in sd.items()}       # packing runs on the target device
         self.conv: Dict[str, Tuple[Tensor, Tensor, tuple]] = {}    # name -> (w bf16 [cop, taps*cp], bias f32 [cop], taps)
         self.lin: Dict[str, Tuple[Tensor, Tensor]] = {}            # 1x1x1 convs as plain GEMM weights
         self.gamma: Dict[str, Tensor] = {}
@@ -100,9 +101,9 @@ class Wan22VaeDecoder:
                 w = w.unsqueeze(2)
             co, ci, kt, kh, kw = w.shape
             cop, cp = _rup(co, 32), _rup(ci, 64)
-            wt = torch.zeros(cop, kt * kh * kw, cp, dtype=_F32)
+            wt = torch.zeros(cop, kt * kh * kw, cp, dtype=_F32, device=dev)
             wt[:co, :, :ci] = w.permute(0, 2, 3, 4, 1).reshape(co, kt * kh * kw, ci)
-            bp = torch.zeros(cop, dtype=_F32)
+            bp = torch.zeros(cop, dtype=_F32, device=dev)
             bp[:co] = b.detach().float()
             self.conv[name] = (wt.reshape(cop, -1).to(dev, _BF16).contiguous(), bp.to(dev), (kt, kh, kw))
 
@@ -112,9 +113,9 @@ class Wan22VaeDecoder:
             elif k.endswith(".weight") and v.dim() == 5 and tuple(v.shape[2:]) == (1, 1, 1) and k != "conv2.weight":
                 name = k[:-7]                                       # ResidualBlock.shortcut: plain GEMM
                 co, ci = v.shape[:2]
-                w = torch.zeros(_rup(co, 32), _rup(ci, 8), dtype=_F32)
+                w = torch.zeros(_rup(co, 32), _rup(ci, 8), dtype=_F32, device=dev)
                 w[:co, :ci] = v.detach().float().reshape(co, ci)
-                b = torch.zeros(_rup(co, 32), dtype=_F32)
+                b = torch.zeros(_rup(co, 32), dtype=_F32, device=dev)
                 b[:co] = sd[name + ".bias"].detach().float()
                 self.lin[name] = (w.to(dev, _BF16).contiguous(), b.to(dev))
             elif k.endswith(".time_conv.weight"):
@@ -127,9 +128,9 @@ class Wan22VaeDecoder:
         # conv2 (1x1x1, z -> z) with the latent de-normalisation folded in: conv2(z*std + mean) = (W diag(std)) z + (W mean + b)
         zd = self.z_dim
         W2 = sd["conv2.weight"].detach().float().reshape(zd, zd)
-        w = torch.zeros(_rup(zd, 32), 64, dtype=_F32)
+        w = torch.zeros(_rup(zd, 32), 64, dtype=_F32, device=dev)
         w[:zd, :zd] = W2 * std[None, :]
-        b = torch.zeros(_rup(zd, 32), dtype=_F32)
+        b = torch.zeros(_rup(zd, 32), dtype=_F32, device=dev)
         b[:zd] = W2 @ mean + sd["conv2.bias"].detach().float()
         self.lin["conv2"] = (w.to(dev, _BF16).contiguous(), b.to(dev))
         # attention: scale folded into q; v bias folded through proj (softmax rows sum to 1)
