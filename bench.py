@@ -418,10 +418,16 @@ def vae_arm(args):
 
 
 def vae22_arm(args):
-    """Supplementary workload: Wan2.2 VAE decode of the 5B sampler's latent z [48,21,44,80]
-    -> video [3,81,704,1280] (vae2_2.py `Wan2_2_VAE.decode`), random-init weights at the real widths."""
+    """Supplementary workloads, random-init weights at the real widths:
+    vae22 — Wan2.2 VAE decode of the 5B sampler's latent z [48,21,44,80] -> video [3,81,704,1280] (`Wan2_2_VAE.decode`);
+    vae21 — Wan2.1 VAE decode of the 14B sampler's 540p latent z [16,21,68,120] -> [3,81,544,960] (`WanVAE.decode`)."""
     from yume_b200 import ops
-    from yume_b200.vae22 import Wan22VaeDecoder, decoder_param_shapes
+    if args.workload == "vae22":
+        from yume_b200.vae22 import Wan22VaeDecoder as Decoder, decoder_param_shapes
+        zc, full, label = 48, (21, 44, 80), "Wan2.2 VAE"
+    else:
+        from yume_b200.vae21 import Wan21VaeDecoder as Decoder, decoder_param_shapes
+        zc, full, label = 16, (21, 68, 120), "Wan2.1 VAE"
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
@@ -436,9 +442,9 @@ def vae22_arm(args):
         else:
             t = t * (0.8 / math.sqrt(math.prod(shape[1:])))
         sd[name] = t
-    eng = Wan22VaeDecoder(sd, device=dev)
-    T, H, W = (21, 44, 80) if not args.quick else (5, 16, 16)
-    z = torch.randn(48, T, H, W, generator=g, device=dev)
+    eng = Decoder(sd, device=dev)
+    T, H, W = full if not args.quick else (5, 16, 16)
+    z = torch.randn(zc, T, H, W, generator=g, device=dev)
     for _ in range(args.warmup):
         eng.decode(z)
     torch.cuda.synchronize()
@@ -453,14 +459,14 @@ def vae22_arm(args):
     print(json.dumps({"metric": "decoded_frames_per_sec", "value": out.shape[1] / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                       "dtype": "bf16", "data": "synthetic",
-                      "config": {"workload": f"Wan2.2 VAE whole-sequence decode z[48,{T},{H},{W}] -> {tuple(out.shape)}"},
+                      "config": {"workload": f"{label} whole-sequence decode z[{zc},{T},{H},{W}] -> {tuple(out.shape)}"},
                       "gpu_launches": ops.launch_count(), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
                       "finite": bool(torch.isfinite(out).all())}), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="dit", choices=["dit", "vae", "vae22"])
+    ap.add_argument("--workload", default="dit", choices=["dit", "vae", "vae22", "vae21"])
     ap.add_argument("--config", default="5b-720p", choices=["5b-720p", "5b-chunk", "14b-chunk"],
                     help="5b-720p is the headline workload (BASELINE.json configs[1]); the others are supplementary")
     ap.add_argument("--gpus", type=int, default=1)
@@ -474,7 +480,7 @@ def main():
     args = ap.parse_args()
     if args.workload == "vae":
         vae_arm(args)
-    elif args.workload == "vae22":
+    elif args.workload in ("vae22", "vae21"):
         vae22_arm(args)
     elif args.config != "5b-720p":
         chunk_arm(args)

@@ -209,6 +209,9 @@ int yb_masked_softmax(const void* S, long long ldS, void* P, long long ldP, int 
 /* z f32 [Cn, N] (NCDHW, N = T*H*W) -> bf16 [N, ldo] channels-last (columns >= Cn zero), and back for f32. */
 int yb_nchw_to_nhwc_bf16(const void* x, void* out, long long N, int Cn, int ldo, void* stream);
 int yb_nhwc_to_nchw_f32(const void* x, long long ldx, void* out, long long N, int Cn, void* stream);
+/* Same with clamp to [lo, hi] fused: the tail of `WanVAE.decode` (wan/modules/vae.py:655-663: head conv output ->
+ * `.float().clamp_(-1, 1)`) on the channels-last f32 head output. */
+int yb_nhwc_to_nchw_f32_clamp(const void* x, long long ldx, void* out, long long N, int Cn, float lo, float hi, void* stream);
 /* Tile cross-fade (blend_v / blend_h / blend_t, autoencoder_kl_causal_3d.py:343-359) on contiguous f32 tiles:
  * b[o, y, i] = a[o, ea-ext+y, i] * (1 - y/ext) + b[o, y, i] * (y/ext) for y < ext; a is [outer, ea, inner], b [outer, eb, inner]. */
 int yb_blend(const void* a, void* b, long long outer, int ea, int eb, int ext, long long inner, void* stream);

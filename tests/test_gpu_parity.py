@@ -546,3 +546,39 @@ def test_wan22_vae_decode_real_width_vs_oracle(dev):
     want = wan22vae.Wan22VaeOracle(sd, mean=mean, std=std, **cfg).decode(z)
     got = Wan22VaeDecoder(sd, mean=mean, std=std, device=dev, **cfg).decode(z).cpu()
     assert got.shape == want.shape and rel(got, want) < VAE_TOL
+
+
+# ---- Wan2.1 VAE (wan/modules/vae.py) ------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def vae21_gold(dev, golden_dir):
+    from oracle import wan21vae
+    g = torch.load(golden_dir / "wan21vae_tiny.pt", weights_only=False)
+    return g, wan21vae.make_state_dict(g["seed_w"], **g["cfg"])
+
+
+@pytest.mark.parametrize("case", ["t1", "t2", "t5", "t3_wide"])
+def test_wan21_vae_decode_vs_reference_golden(dev, vae21_gold, case):
+    from yume_b200.vae21 import Wan21VaeDecoder
+    g, sd = vae21_gold
+    c = g["cases"][case]
+    eng = Wan21VaeDecoder(sd, mean=g["mean"], std=g["std"], device=dev, **g["cfg"])
+    z = torch.randn(g["cfg"]["z_dim"], c["T"], c["H"], c["W"], generator=torch.Generator().manual_seed(c["seed"]))
+    out = eng.decode(z).cpu()
+    assert tuple(out.shape) == c["shape"]
+    for name, got in (("sample", out[..., ::3, ::3]), ("rowsum", out.sum(-1)), ("colsum", out.sum(-2))):
+        assert float((got - c[name]).norm() / c[name].norm()) < VAE_TOL, name
+
+
+def test_wan21_vae_decode_real_width_vs_oracle(dev):
+    """Real channel widths (dim 96 -> 384/192/96, z16) on a small latent against the fp32 oracle."""
+    from oracle import wan21vae
+    from yume_b200.vae21 import Wan21VaeDecoder
+    cfg = dict(dim=96, z_dim=16, dim_mult=(1, 2, 4, 4), num_res_blocks=2, temperal_upsample=(True, True, False))
+    sd = wan21vae.make_state_dict(41, **cfg)
+    gen = torch.Generator().manual_seed(7)
+    mean, std = 0.2 * torch.randn(16, generator=gen), 0.5 + torch.rand(16, generator=gen)
+    z = torch.randn(16, 3, 4, 6, generator=gen)
+    want = wan21vae.Wan21VaeOracle(sd, mean=mean, std=std, **cfg).decode(z)
+    got = Wan21VaeDecoder(sd, mean=mean, std=std, device=dev, **cfg).decode(z).cpu()
+    assert got.shape == want.shape and rel(got, want) < VAE_TOL
+    assert float(got.min()) >= -1.0 and float(got.max()) <= 1.0

@@ -168,3 +168,13 @@ def test_wan22_vae_repack_folds_are_exact():
     Cq = eng.dims[0]
     Wo = sd[a + ".proj.weight"].reshape(Cq, Cq)
     assert torch.allclose(eng.att["bo"], sd[a + ".proj.bias"] + Wo @ sd[a + ".to_qkv.bias"][2 * Cq:], atol=1e-6)
+
+
+def test_wan21_vae_plan_and_shapes_match_oracle():
+    from oracle import wan21vae
+    from yume_b200.vae21 import decoder_param_shapes, upsample_plan
+    for dim in (96, 32):
+        assert decoder_param_shapes(dim) == wan21vae.param_shapes(dim)
+        assert upsample_plan(dim) == wan21vae.layer_plan(dim)
+    kinds = [k for _, k, _, _ in upsample_plan()]
+    assert kinds.count("upsample3d") == 2 and kinds.count("upsample2d") == 1 and kinds.count("res") == 12

@@ -177,13 +177,13 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
 
 // x f32 [N, ldx] channels-last -> out f32 [Cn, N]
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, long long ldx, float* __restrict__ out, long long N,
-                                    int Cn) {
+                                    int Cn, float lo, float hi) {
   const long long total = N * Cn;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long v = i % N;
     const int c = static_cast<int>(i / N);
-    out[i] = x[v * ldx + c];
+    out[i] = fminf(fmaxf(x[v * ldx + c], lo), hi);
   }
 }
 
@@ -420,8 +420,16 @@ extern "C" int yb_nchw_to_nhwc_bf16(const void* x, void* out, long long N, int C
 extern "C" int yb_nhwc_to_nchw_f32(const void* x, long long ldx, void* out, long long N, int Cn, void* stream_) {
   if (!x || !out || N <= 0 || Cn <= 0 || ldx < Cn) return YB_ERR_ARG;
   nhwc_to_nchw_kernel<<<grid_for(N * Cn), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const float*>(x), ldx, static_cast<float*>(out), N, Cn);
+      static_cast<const float*>(x), ldx, static_cast<float*>(out), N, Cn, -INFINITY, INFINITY);
   return check_launch("nhwc_to_nchw");
+}
+
+extern "C" int yb_nhwc_to_nchw_f32_clamp(const void* x, long long ldx, void* out, long long N, int Cn, float lo, float hi,
+                                         void* stream_) {
+  if (!x || !out || N <= 0 || Cn <= 0 || ldx < Cn || !(lo <= hi)) return YB_ERR_ARG;
+  nhwc_to_nchw_kernel<<<grid_for(N * Cn), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const float*>(x), ldx, static_cast<float*>(out), N, Cn, lo, hi);
+  return check_launch("nhwc_to_nchw_clamp");
 }
 
 extern "C" int yb_blend(const void* a, void* b, long long outer, int ea, int eb, int ext, long long inner,

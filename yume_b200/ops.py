@@ -325,11 +325,16 @@ def nchw_to_nhwc_bf16(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def nhwc_to_nchw_f32(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-    """x f32 [N, ldx] -> out f32 [Cn, N] contiguous."""
+def nhwc_to_nchw_f32(x: torch.Tensor, out: torch.Tensor, clamp: Optional[tuple] = None) -> torch.Tensor:
+    """x f32 [N, ldx] -> out f32 [Cn, N] contiguous (optionally clamped to clamp=(lo, hi))."""
     global _launches
     _need(x, torch.float32, "x")
     _need(out, torch.float32, "out")
+    if clamp is not None:
+        check(_lib.load().yb_nhwc_to_nchw_f32_clamp(x.data_ptr(), x.stride(0), out.data_ptr(), x.shape[0], out.shape[0],
+                                                    float(clamp[0]), float(clamp[1]), _stream()), "yb_nhwc_to_nchw_f32_clamp")
+        _launches += 1
+        return out
     check(_lib.load().yb_nhwc_to_nchw_f32(x.data_ptr(), x.stride(0), out.data_ptr(), x.shape[0], out.shape[0], _stream()),
           "yb_nhwc_to_nchw_f32")
     _launches += 1
