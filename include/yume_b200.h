@@ -235,7 +235,7 @@ int yb_vae_unpatchify2_clamp(const void* y, long long ldy, void* out, int T, int
  *   mode 2: A in TMEM (bf16x2 packed), B MN-major D = A * Bmn
  * A, B bf16 [128,128] row-major; D f32 [128,128].
  * ------------------------------------------------------------------------------------------- */
-int yb_umma_probe(const void* A, const void* B, void* D, int mode, void* stream);
+int yb_umma_probe(const void* A, const void* B, void* D, int mode, void* stream);  /* modes >= 3: A rows shifted by (mode - 2) */
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,20 @@ def test_umma_probe(dev, mode):
     assert rel(d, ref) < 1e-5
 
 
+@pytest.mark.parametrize("shift", [1, 2, 3, 7, 8])
+def test_umma_probe_row_shifted_a(dev, shift):
+    """The conv kernel reuses one TMA halo box for the three kw taps by moving the A descriptor's start address by whole
+    128-byte rows inside the 128B-swizzled tile; D[m] must equal A[m + shift] . B^T (rows past the end are TMA zeros)."""
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(30 + shift)
+    a = torch.randn(128, 128, generator=g).to(dev).bfloat16()
+    b = torch.randn(128, 128, generator=g).to(dev).bfloat16()
+    d = ops.umma_probe(a, b, 2 + shift)
+    ash = torch.zeros_like(a)
+    ash[:128 - shift] = a[shift:]
+    assert rel(d, ash.float() @ b.float().t()) < 1e-5
+
+
 @pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 0), (300, 384, 192, 0), (1000, 3072, 3072, 0), (512, 128, 4096, 128),
                                        (77, 96, 144, 0), (4097, 768, 256, 256)])
 def test_gemm_bf16_matches_fp32_reference(dev, M, N, K, bn):

@@ -11,9 +11,13 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const __nv_bfloat16* __restrict__ Ag, float* __restrict__ D, int mode) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;           // 2 slabs x 16 KB
-  uint8_t* sB = smem + 32768;   // 2 slabs x 16 KB
-  uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + 65536);
+  // modes 0..2: A = 2 slabs x 16 KB. modes >= 3 (row-shifted A, shift = mode - 2 rows): A = 2 slabs x 17 KB holding a
+  // 136-row TMA box; the MMA reads rows [shift, shift + 128) by moving the descriptor start address by shift * 128 B.
+  const int shift = mode >= 3 ? mode - 2 : 0;
+  const uint32_t a_slab = shift ? 17408u : 16384u;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 36864;   // 2 slabs x 16 KB
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + 69632);
   uint64_t* bar_mma = bar_load + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_mma + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -33,9 +37,9 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr;
 
   if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(bar_load, 65536);
+    mbar_arrive_expect_tx(bar_load, 32768 + 2 * a_slab);
     tma_load_2d(sA, &tmA, bar_load, 0, 0);
-    tma_load_2d(sA + 16384, &tmA, bar_load, 64, 0);
+    tma_load_2d(sA + a_slab, &tmA, bar_load, 64, 0);
     tma_load_2d(sB, &tmB, bar_load, 0, 0);
     tma_load_2d(sB + 16384, &tmB, bar_load, 64, 0);
   }
@@ -58,11 +62,12 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_wait(bar_load, 0);
     tc_fence_after();
     const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-    if (mode == 0) {
+    if (mode == 0 || mode >= 3) {
       constexpr uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
       for (int kk = 0; kk < 8; ++kk) {
         const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-        umma_ss(tmem_base, make_smem_desc_sw128(a0 + off, 16, 1024), make_smem_desc_sw128(b0 + off, 16, 1024), idesc,
+        const uint32_t offa = (kk >> 2) * a_slab + (kk & 3) * 32 + shift * 128;
+        umma_ss(tmem_base, make_smem_desc_sw128(a0 + offa, 16, 1024), make_smem_desc_sw128(b0 + off, 16, 1024), idesc,
                 kk != 0);
       }
     } else if (mode == 1) {
@@ -105,13 +110,13 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 extern "C" int yb_umma_probe(const void* A, const void* B, void* D, int mode, void* stream_) {
   using namespace yb;
-  if (!A || !B || !D || mode < 0 || mode > 2) return YB_ERR_ARG;
+  if (!A || !B || !D || mode < 0 || mode > 10) return YB_ERR_ARG;
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_bf16_2d(&tmA, A, 128, 128, 128, 128, 64);
+  int rc = make_tmap_bf16_2d(&tmA, A, 128, 128, 128, mode >= 3 ? 136 : 128, 64);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, B, 128, 128, 128, 128, 64);
   if (rc) return rc;
-  const int smem = 65536 + 1024 + 64;
+  const int smem = 69632 + 1024 + 64;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {

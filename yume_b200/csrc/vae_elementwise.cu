@@ -74,31 +74,45 @@ struct PadActParams {
 };
 
 __global__ void __launch_bounds__(256) pad_act_kernel(const PadActParams p) {
+  // GroupNorm folded to one fma per element: y = x * a[c] + b[c], a = rstd_g * gamma, b = beta - mean_g * a, built once
+  // per block in shared memory; all index math is 32-bit (the host rejects buffers with >= 2^31 16-byte chunks).
+  __shared__ float s_a[1024], s_b[1024];
   const int chunks = p.Cp >> 3;
   const int Tp = p.T + 2 * p.pad, Hp = p.H + 2 * p.pad, Wp = p.W + 2 * p.pad;
-  const long long total = static_cast<long long>(Tp) * Hp * Wp * chunks;
-  const int cg = p.G > 0 ? p.C / p.G : 1;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int chunk = static_cast<int>(i % chunks);
-    long long v = i / chunks;
-    const int wp = static_cast<int>(v % Wp);
+  const int total = Tp * Hp * Wp * chunks;
+  if (p.stats) {
+    const int cg = p.C / p.G;
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+      const int g = c / cg;
+      const double mean = p.stats[2 * g] * p.inv_count;
+      const double var = p.stats[2 * g + 1] * p.inv_count - mean * mean;
+      const float a = rsqrtf(static_cast<float>(var) + p.eps) * __ldg(p.gamma + c);
+      s_a[c] = a;
+      s_b[c] = __ldg(p.beta + c) - static_cast<float>(mean) * a;
+    }
+    __syncthreads();
+  }
+  const bool plain = (p.stats == nullptr && !p.silu);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int chunk = i % chunks;
+    int v = i / chunks;
+    const int wp = v % Wp;
     v /= Wp;
-    const int hp = static_cast<int>(v % Hp);
-    const int tp = static_cast<int>(v / Hp);
+    const int hp = v % Hp;
+    const int tp = v / Hp;
     // output (unpadded) coordinate, clamped = replicate padding; temporal pad is 2 frames in FRONT only (causal)
     int t = p.pad ? max(tp - 2, 0) : tp;
     int h = p.pad ? min(max(hp - 1, 0), p.H - 1) : hp;
     int w = p.pad ? min(max(wp - 1, 0), p.W - 1) : wp;
     if (p.ft == 2) t = (t == 0) ? 0 : 1 + ((t - 1) >> 1);
-    h /= p.fh;
-    w /= p.fw;
+    if (p.fh == 2) h >>= 1; else h /= p.fh;
+    if (p.fw == 2) w >>= 1; else w /= p.fw;
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
     const int c0 = chunk * 8;
     if (c0 < p.C) {
       const long long src = (static_cast<long long>(t) * p.Hs + h) * p.Ws + w;
       const uint4 raw = *reinterpret_cast<const uint4*>(p.x + src * p.ldx + c0);
-      if (p.stats == nullptr && !p.silu) {
+      if (plain) {
         o = raw;
       } else {
         const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
@@ -111,13 +125,7 @@ __global__ void __launch_bounds__(256) pad_act_kernel(const PadActParams p) {
         }
         if (p.stats) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int g = (c0 + k) / cg;
-            const double mean = p.stats[2 * g] * p.inv_count;
-            const double var = p.stats[2 * g + 1] * p.inv_count - mean * mean;
-            const float rstd = rsqrtf(static_cast<float>(var) + p.eps);
-            f[k] = (f[k] - static_cast<float>(mean)) * rstd * __ldg(p.gamma + c0 + k) + __ldg(p.beta + c0 + k);
-          }
+          for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], s_a[c0 + k], s_b[c0 + k]);
         }
         if (p.silu) {
 #pragma unroll
@@ -126,7 +134,7 @@ __global__ void __launch_bounds__(256) pad_act_kernel(const PadActParams p) {
         o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
       }
     }
-    *reinterpret_cast<uint4*>(p.out + i * 8) = o;
+    *reinterpret_cast<uint4*>(p.out + static_cast<long long>(i) * 8) = o;
   }
 }
 
@@ -212,28 +220,37 @@ __global__ void blend_kernel(const float* __restrict__ a, float* __restrict__ b,
 // nearest-exact 2x spatial upsample (:64-70, Resample :95-101), written channels-last [T, H*f, W*f, Cp] (no padding:
 // the conv takes its zero padding from TMA out-of-bounds fill).
 // ---------------------------------------------------------------------------------------------------------
-template <int NCH>   // 16-byte chunks per lane per voxel (C <= NCH * 256); a warp keeps U = 4 / NCH voxels in flight
+// NCH = 16-byte chunks per lane per voxel, G = lanes per voxel (G < 32 only with NCH == 1: narrow rows share a warp).
+// A warp keeps U * (32 / G) voxels in flight, U = 4 / NCH. All index math is 32-bit and the f == 1 path has none.
+template <int NCH, int G>
 __global__ void __launch_bounds__(256)
 rms_act_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out, const float* __restrict__ gamma,
                int T, int Hs, int Ws, int C, int Cp, int f, int silu) {
   constexpr int U = 4 / NCH;
+  constexpr int SUB = 32 / G;                     // voxels side by side in one warp
+  constexpr int VPI = U * SUB;                    // voxels per warp iteration
   const int H = Hs * f, W = Ws * f;
-  const long long nvox = static_cast<long long>(T) * H * W;
+  const int nvox = T * H * W;
   const int lane = threadIdx.x & 31;
+  const int gl = lane % G, sub = lane / G;
   const int cch = C >> 3, pch = Cp >> 3;
   const float sqrt_c = sqrtf(static_cast<float>(C));
-  for (long long v0 = (blockIdx.x * 8LL + (threadIdx.x >> 5)) * U; v0 < nvox; v0 += gridDim.x * 8LL * U) {
+  const int stride = gridDim.x * 8 * VPI;
+  for (int v0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * VPI; v0 < nvox; v0 += stride) {
     uint4 raw[U][NCH];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long v = v0 + u;
-      const int w = static_cast<int>(v % W);
-      const int h = static_cast<int>((v / W) % H);
-      const int t = static_cast<int>(v / (static_cast<long long>(W) * H));
-      const __nv_bfloat16* xs = x + ((static_cast<long long>(t) * Hs + h / f) * Ws + w / f) * ldx;
+      const int v = v0 + u * SUB + sub;
+      int src = v;
+      if (f != 1) {
+        const int w = v % W, r = v / W;
+        const int h = r % H, t = r / H;
+        src = (t * Hs + h / f) * Ws + w / f;
+      }
+      const __nv_bfloat16* xs = x + static_cast<long long>(src) * ldx;
 #pragma unroll
       for (int j = 0; j < NCH; ++j) {
-        const int c = lane + 32 * j;
+        const int c = gl + G * j;
         raw[u][j] = (v < nvox && c < cch) ? *reinterpret_cast<const uint4*>(xs + c * 8) : make_uint4(0u, 0u, 0u, 0u);
       }
     }
@@ -254,19 +271,19 @@ rms_act_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16
     }
     if (gamma) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = G / 2; o > 0; o >>= 1) {
 #pragma unroll
         for (int u = 0; u < U; ++u) scl[u] += __shfl_xor_sync(0xffffffffu, scl[u], o);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long v = v0 + u;
-      if (v >= nvox) break;
+      const int v = v0 + u * SUB + sub;
+      if (v >= nvox) continue;
       const float sc = gamma ? sqrt_c / fmaxf(sqrtf(scl[u]), 1e-12f) : 1.f;
 #pragma unroll
       for (int j = 0; j < NCH; ++j) {
-        const int c = lane + 32 * j;
+        const int c = gl + G * j;
         if (c >= pch) continue;
         uint4 o = make_uint4(0u, 0u, 0u, 0u);
         if (c < cch) {
@@ -291,7 +308,7 @@ rms_act_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16
           }
           o = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
         }
-        *reinterpret_cast<uint4*>(out + v * Cp + c * 8) = o;
+        *reinterpret_cast<uint4*>(out + static_cast<long long>(v) * Cp + c * 8) = o;
       }
     }
   }
@@ -399,6 +416,7 @@ extern "C" int yb_vae_pad_act(const void* x, long long ldx, int Ts, int Hs, int 
   p.eps = eps;
   p.inv_count = stats ? 1.0 / (static_cast<double>(Ts) * Hs * Ws * (C / G)) : 0.0;
   const long long total = static_cast<long long>(p.T + 2 * p.pad) * (p.H + 2 * p.pad) * (p.W + 2 * p.pad) * (Cp / 8);
+  if (total > 0x7fffffffLL - (1LL << 26) || (stats && C > 1024)) return YB_ERR_SHAPE;   // 32-bit indices, smem scale table
   pad_act_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(p);
   return check_launch("vae_pad_act");
 }
@@ -450,18 +468,22 @@ extern "C" int yb_vae_rms_act(const void* x, long long ldx, void* out, const voi
   if (C > 1024) return YB_ERR_SHAPE;
   if (gamma && (reinterpret_cast<uintptr_t>(gamma) & 0xF)) return YB_ERR_ALIGNMENT;
   const long long nvox = static_cast<long long>(T) * Hs * up * Ws * up;
+  if (nvox > 0x7fffffffLL - (1LL << 24)) return YB_ERR_SHAPE;                      // 32-bit voxel indices in the kernel
   const int nch = C <= 256 ? 1 : (C <= 512 ? 2 : 4);
-  const int per_block = 8 * (4 / nch);
+  const int g = nch > 1 ? 32 : (Cp <= 64 ? 8 : (Cp <= 128 ? 16 : 32));         // lanes per voxel
+  const int per_block = 8 * (4 / nch) * (32 / g);
   long long blocks = (nvox + per_block - 1) / per_block;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
-#define YB_RMS_LAUNCH(NCH)                                                                                           \
-  rms_act_kernel<NCH><<<static_cast<int>(blocks), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx,            \
-                                                               static_cast<__nv_bfloat16*>(out),                       \
-                                                               static_cast<const float*>(gamma), T, Hs, Ws, C, Cp, up, silu)
-  if (nch == 1) YB_RMS_LAUNCH(1);
-  else if (nch == 2) YB_RMS_LAUNCH(2);
-  else YB_RMS_LAUNCH(4);
+#define YB_RMS_LAUNCH(NCH, G)                                                                                        \
+  rms_act_kernel<NCH, G><<<static_cast<int>(blocks), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx,         \
+                                                                  static_cast<__nv_bfloat16*>(out),                    \
+                                                                  static_cast<const float*>(gamma), T, Hs, Ws, C, Cp, up, silu)
+  if (nch == 4) YB_RMS_LAUNCH(4, 32);
+  else if (nch == 2) YB_RMS_LAUNCH(2, 32);
+  else if (g == 32) YB_RMS_LAUNCH(1, 32);
+  else if (g == 16) YB_RMS_LAUNCH(1, 16);
+  else YB_RMS_LAUNCH(1, 8);
 #undef YB_RMS_LAUNCH
   return check_launch("vae_rms_act");
 }
