@@ -87,10 +87,14 @@ typedef struct yb_conv3d_args {
    *   oob_zero_pad   1: `xpad` is the UNPADDED [T, H, W, Cp] activation and the causal zero padding (kt-1 in front,
    *                  kh/2, kw/2 around; vae2_2.py:22-44) is TMA out-of-bounds zero fill — no padded buffer exists
    *   out_t_mul/add  output frame of input frame t is t*out_t_mul + out_t_add (0 = identity): interleaves the two
-   *                  channel groups of time_conv into consecutive frames (vae2_2.py:151-154) */
+   *                  channel groups of time_conv into consecutive frames (vae2_2.py:151-154)
+   *   fuse_w         tile-shape policy for kw == 3: 0 = automatic, 1 = never, 2 = always use the kw-fused kernel (one
+   *                  130-voxel TMA halo row feeds all three kw taps through row-shifted UMMA descriptors); results are
+   *                  identical either way — the knob exists for tests and profiling */
   int kt, kh, kw;
   int oob_zero_pad;
   int out_t_mul, out_t_add;
+  int fuse_w;
 } yb_conv3d_args;
 int yb_conv3d_causal(const yb_conv3d_args* args, void* stream);
 

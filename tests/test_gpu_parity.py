@@ -372,8 +372,9 @@ VAE_TOL = 3e-2   # ~35 bf16 conv/norm layers deep; fp32 oracle / reference fixtu
 
 
 @pytest.mark.parametrize("T,H,W,ci,co", [(3, 8, 8, 64, 64), (2, 6, 10, 128, 128), (5, 32, 32, 64, 256), (1, 18, 32, 128, 96),
-                                         (9, 4, 4, 64, 32)])
-def test_conv3d_causal_matches_torch(dev, T, H, W, ci, co):
+                                         (9, 4, 4, 64, 32), (2, 3, 200, 64, 128), (3, 2, 256, 128, 256)])
+@pytest.mark.parametrize("fuse_w", [1, 2])
+def test_conv3d_causal_matches_torch(dev, T, H, W, ci, co, fuse_w):
     from yume_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(T * 100 + H)
     x = torch.randn(T * H * W, ci, generator=g).to(dev).bfloat16()
@@ -387,11 +388,11 @@ def test_conv3d_causal_matches_torch(dev, T, H, W, ci, co):
     assert torch.equal(xpad.float().permute(3, 0, 1, 2)[None], want_pad)            # replicate padding is bit-exact
     wk = wt.permute(0, 2, 3, 4, 1).reshape(co, 27 * ci).contiguous()
     out = torch.empty(T * H * W, co, device=dev, dtype=torch.bfloat16)
-    ops.conv3d_causal(xpad, wk, b, out, T, H, W, ops.YB_EPI_RES_BF16, res)
+    ops.conv3d_causal(xpad, wk, b, out, T, H, W, ops.YB_EPI_RES_BF16, res, fuse_w=fuse_w)
     ref = torch.nn.functional.conv3d(want_pad, wt.float(), b)[0].permute(1, 2, 3, 0).reshape(T * H * W, co) + res.float()
     assert rel(out, ref) < KERNEL_TOL
     o32 = torch.empty(T * H * W, co, device=dev)
-    ops.conv3d_causal(xpad, wk, None, o32, T, H, W, ops.YB_EPI_F32)
+    ops.conv3d_causal(xpad, wk, None, o32, T, H, W, ops.YB_EPI_F32, fuse_w=fuse_w)
     assert rel(o32, ref - res.float() - b) < 1e-4
 
 
@@ -472,8 +473,10 @@ def test_vae_decode_real_width_tile_vs_oracle(dev):
 @pytest.mark.parametrize("taps,T,H,W,ci,co,tm,ta", [((3, 3, 3), 3, 8, 8, 64, 64, 1, 0), ((1, 3, 3), 4, 6, 10, 128, 96, 1, 0),
                                                      ((3, 1, 1), 3, 5, 8, 64, 128, 2, 1), ((3, 1, 1), 3, 5, 8, 64, 128, 2, 2),
                                                      ((3, 3, 3), 1, 18, 32, 128, 32, 1, 0), ((3, 3, 3), 5, 40, 24, 64, 64, 1, 0),
-                                                     ((1, 3, 3), 2, 130, 9, 64, 64, 1, 0)])
-def test_conv3d_zero_pad_tap_modes(dev, taps, T, H, W, ci, co, tm, ta):
+                                                     ((1, 3, 3), 2, 130, 9, 64, 64, 1, 0), ((3, 3, 3), 2, 5, 300, 128, 256, 1, 0),
+                                                     ((1, 3, 3), 3, 4, 129, 64, 96, 1, 0)])
+@pytest.mark.parametrize("fuse_w", [1, 2])
+def test_conv3d_zero_pad_tap_modes(dev, taps, T, H, W, ci, co, tm, ta, fuse_w):
     """CausalConv3d with ZERO padding taken from TMA out-of-bounds fill, (kt,kh,kw) taps and interleaved output frames."""
     from yume_b200 import ops
     kt, kh, kw = taps
@@ -484,7 +487,8 @@ def test_conv3d_zero_pad_tap_modes(dev, taps, T, H, W, ci, co, tm, ta):
     wk = wt.permute(0, 2, 3, 4, 1).reshape(co, kt * kh * kw * ci).contiguous()
     To = (T - 1) * tm + ta + 1
     out = torch.full((To * H * W, co), 7.0, device=dev, dtype=torch.bfloat16)
-    ops.conv3d_causal(x, wk, b, out, T, H, W, ops.YB_EPI_BF16, taps=taps, oob_zero_pad=True, out_t_mul=tm, out_t_add=ta)
+    ops.conv3d_causal(x, wk, b, out, T, H, W, ops.YB_EPI_BF16, taps=taps, oob_zero_pad=True, out_t_mul=tm, out_t_add=ta,
+                      fuse_w=fuse_w)
     xn = torch.nn.functional.pad(x.float().permute(3, 0, 1, 2)[None], (kw // 2, kw // 2, kh // 2, kh // 2, kt - 1, 0))
     ref = torch.nn.functional.conv3d(xn, wt.float(), b)[0].permute(1, 2, 3, 0)             # [T, H, W, co]
     got = out.view(To, H, W, co).float()

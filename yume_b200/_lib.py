@@ -45,7 +45,7 @@ class Conv3dArgs(C.Structure):
         ("ldo", C.c_longlong), ("res_ld", C.c_longlong),
         ("T", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cp", C.c_int), ("Cout", C.c_int), ("epilogue", C.c_int),
         ("kt", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("oob_zero_pad", C.c_int), ("out_t_mul", C.c_int),
-        ("out_t_add", C.c_int),
+        ("out_t_add", C.c_int), ("fuse_w", C.c_int),
     ]
 
 

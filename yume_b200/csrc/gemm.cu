@@ -54,16 +54,28 @@ struct GemmParams {
   int num_m_tiles, num_n_tiles;
 };
 
-template <int BLOCK_N>
+// CONVW = 1: kw-fused implicit-GEMM conv. The three kw taps of one (dt, dh, channel-chunk) group read the SAME TMA halo
+// box of 130 voxels along W; tap dw is fed to the MMA by moving the A descriptor's start address by dw 128-byte rows
+// inside the swizzled slab (the swizzle is a function of the absolute smem address, so whole-row shifts stay
+// consistent with what TMA wrote — probe modes >= 3). A and B then live in separate rings: one A slab per group, one B
+// tile per tap. Cuts the A operand's L2 -> smem traffic 3x, which is what bounds the narrow (<= 128 channel) convs.
+constexpr int CONVW_ROWS = GEMM_BLOCK_M + 2;
+constexpr int CONVW_A_SLAB = 17 * 1024;  // 130 rows x 128 B = 16640 B, padded to the 1024-B swizzle pattern
+constexpr int CONVW_A_STAGES = 4;
+
+template <int BLOCK_N, int CONVW = 0>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = CONVW ? B_BYTES : A_BYTES + B_BYTES;   // CONVW: the ring holds B tiles only
   static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int A_STAGES = CONVW ? CONVW_A_STAGES : 0;
+  static constexpr int A_RING_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = A_RING_OFF + A_STAGES * CONVW_A_SLAB;
   static constexpr int STAGE_OFF = BAR_OFF + 256;                // epilogue transpose buffers: 4 warps x 32 x 36 floats
   static constexpr int SMEM_BYTES = STAGE_OFF + 4 * 32 * 36 * 4 + 1024 /*align slack*/;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 512 or 256: power of two
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ void tile_coords(int tile, int num_m_tiles, int num_n_tiles, int& m_tile, int& n_tile) {
@@ -76,15 +88,17 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m_tiles, int num_n
   n_tile = n_first + (r - m_tile * n_in_group);
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int CONVW = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, CONVW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  uint64_t* a_full = empty_bar + Cfg::STAGES;          // CONVW only (A_STAGES == 0 otherwise)
+  uint64_t* a_empty = a_full + Cfg::A_STAGES;
+  uint64_t* tmem_full = a_empty + Cfg::A_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -99,6 +113,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int i = 0; i < Cfg::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < Cfg::A_STAGES; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -117,7 +135,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
+    if (CONVW && lane == 0) {
+      int stage = 0, a_stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      const int groups = num_kb / 3;                      // (dt, dh, channel chunk)
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_tile, n_tile;
+        tile_coords(tile, p.num_m_tiles, p.num_n_tiles, m_tile, n_tile);
+        const int per_t = p.tiles_h * p.tiles_w;
+        const int it = m_tile / per_t, rem = m_tile - it * per_t;
+        const int ih = rem / p.tiles_w, iw = rem - ih * p.tiles_w;
+        for (int g = 0; g < groups; ++g) {
+          const int tdh = g / p.cin_chunks, cc = g - tdh * p.cin_chunks;
+          const int dt = tdh / p.kh, dh = tdh - dt * p.kh;
+          mbar_wait(&a_empty[a_stage], a_phase ^ 1);
+          mbar_arrive_expect_tx(&a_full[a_stage], CONVW_ROWS * GEMM_BLOCK_K * 2);
+          tma_load_4d(smem + Cfg::A_RING_OFF + a_stage * CONVW_A_SLAB, &tmA, &a_full[a_stage], cc * GEMM_BLOCK_K,
+                      iw * GEMM_BLOCK_M - p.off_w, ih + dh - p.off_h, it + dt - p.off_t);
+          if (++a_stage == Cfg::A_STAGES) {
+            a_stage = 0;
+            a_phase ^= 1;
+          }
+#pragma unroll 1
+          for (int dw = 0; dw < 3; ++dw) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::B_BYTES);
+            tma_load_2d(smem + stage * Cfg::STAGE_BYTES, &tmB, &full_bar[stage],
+                        ((tdh * 3 + dw) * p.cin_chunks + cc) * GEMM_BLOCK_K, n_tile * BLOCK_N);
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    } else if (!CONVW && lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -155,7 +207,45 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
+    if (CONVW && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, BLOCK_N, 0, 0);
+      int stage = 0, a_stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      int local = 0;
+      const int groups = num_kb / 3;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait(&a_full[a_stage], a_phase);
+          const uint32_t sa = smem_u32(smem + Cfg::A_RING_OFF + a_stage * CONVW_A_SLAB);
+#pragma unroll 1
+          for (int dw = 0; dw < 3; ++dw) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = make_smem_desc_sw128(sa + dw * 128, 16, 1024);   // tap dw = rows [dw, dw + 128)
+            const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + stage * Cfg::STAGE_BYTES), 16, 1024);
+#pragma unroll
+            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
+              umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (g | dw | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit(&a_empty[a_stage]);
+          if (++a_stage == Cfg::A_STAGES) {
+            a_stage = 0;
+            a_phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    } else if (!CONVW && lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -356,10 +446,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int CONVW = 0>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
-  auto kern = gemm_kernel<BLOCK_N, EPI>;
+  using Cfg = GemmCfg<BLOCK_N, CONVW>;
+  auto kern = gemm_kernel<BLOCK_N, EPI, CONVW>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -467,13 +557,25 @@ extern "C" int yb_conv3d_causal(const yb_conv3d_args* a, void* stream_) {
       }
     }
   }
+  const int kt = a->kt > 0 ? a->kt : 3, kh = a->kh > 0 ? a->kh : 3, kw = a->kw > 0 ? a->kw : 3;
+  if ((kt != 1 && kt != 3) || (kh != 1 && kh != 3) || (kw != 1 && kw != 3)) return YB_ERR_SHAPE;
+  const int block_n = (a->Cout % 256 == 0) ? 256 : 128;
+  // kw-fused mode (one 130-voxel halo box feeds the three kw taps): needs the one-row 128-voxel tile; taken when that
+  // tile shape costs little utilisation — always worth it for 128-wide N tiles (A-traffic bound), only when nearly free
+  // for 256-wide ones (MMA bound). a->fuse_w: 0 = auto, 1 = off, 2 = force (tests).
+  bool fuse_w = false;
+  if (kw == 3 && a->fuse_w != 1 && (a->W >= 64 || a->fuse_w == 2)) {
+    const double util128 = static_cast<double>(a->W) / (((a->W + 127) / 128) * 128.0);
+    const double best = static_cast<double>(a->T) * a->H * a->W /
+                        (128.0 * ((a->W + p.TW - 1) / p.TW) * ((a->H + p.TH - 1) / p.TH) * ((a->T + p.TT - 1) / p.TT));
+    fuse_w = a->fuse_w == 2 || util128 >= (block_n == 128 ? 0.70 : 0.95) * best;
+  }
+  if (fuse_w) { p.TW = 128; p.TH = 1; p.TT = 1; }
   p.tiles_w = (a->W + p.TW - 1) / p.TW;
   p.tiles_h = (a->H + p.TH - 1) / p.TH;
   const int tiles_t = (a->T + p.TT - 1) / p.TT;
-  const int kt = a->kt > 0 ? a->kt : 3, kh = a->kh > 0 ? a->kh : 3, kw = a->kw > 0 ? a->kw : 3;
-  if ((kt != 1 && kt != 3) || (kh != 1 && kh != 3) || (kw != 1 && kw != 3)) return YB_ERR_SHAPE;
   const int taps = kt * kh * kw;
-  p.conv = 1;
+  p.conv = fuse_w ? 2 : 1;
   p.cin_chunks = a->Cp / 64;
   p.cT = a->T; p.cH = a->H; p.cW = a->W;
   p.kh = kh; p.kw = kw;
@@ -493,24 +595,28 @@ extern "C" int yb_conv3d_causal(const yb_conv3d_args* a, void* stream_) {
   p.a_split = p.K; p.n_split = 0; p.split_stride = 0;
   p.res = static_cast<const __nv_bfloat16*>(a->res);
   p.res_ld = a->res_ld;
-  const int block_n = (a->Cout % 256 == 0) ? 256 : 128;
   CUtensorMap tmA, tmB;
   const int padT = a->oob_zero_pad ? 0 : kt - 1, padH = a->oob_zero_pad ? 0 : kh - 1, padW = a->oob_zero_pad ? 0 : kw - 1;
-  int rc = make_tmap_bf16_4d(&tmA, a->xpad, a->T + padT, a->H + padH, a->W + padW, a->Cp, p.TT, p.TH, p.TW, 64);
+  int rc = make_tmap_bf16_4d(&tmA, a->xpad, a->T + padT, a->H + padH, a->W + padW, a->Cp, p.TT, p.TH,
+                             fuse_w ? CONVW_ROWS : p.TW, 64);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, a->w, a->Cout, static_cast<uint64_t>(taps) * a->Cp, static_cast<uint64_t>(taps) * a->Cp,
                          block_n, GEMM_BLOCK_K);
   if (rc) return rc;
-#define YB_CONV_DISPATCH(BN)                                                                 \
+#define YB_CONV_DISPATCH(BN, CW)                                                              \
   switch (a->epilogue) {                                                                     \
-    case YB_EPI_BF16: return launch_gemm<BN, YB_EPI_BF16>(tmA, tmB, p, stream);               \
-    case YB_EPI_F32: return launch_gemm<BN, YB_EPI_F32>(tmA, tmB, p, stream);                 \
-    default: return launch_gemm<BN, YB_EPI_RES_BF16>(tmA, tmB, p, stream);                    \
+    case YB_EPI_BF16: return launch_gemm<BN, YB_EPI_BF16, CW>(tmA, tmB, p, stream);           \
+    case YB_EPI_F32: return launch_gemm<BN, YB_EPI_F32, CW>(tmA, tmB, p, stream);             \
+    default: return launch_gemm<BN, YB_EPI_RES_BF16, CW>(tmA, tmB, p, stream);                \
   }
-  if (block_n == 256) {
-    YB_CONV_DISPATCH(256)
+  if (block_n == 256 && fuse_w) {
+    YB_CONV_DISPATCH(256, 1)
+  } else if (block_n == 256) {
+    YB_CONV_DISPATCH(256, 0)
+  } else if (fuse_w) {
+    YB_CONV_DISPATCH(128, 1)
   } else {
-    YB_CONV_DISPATCH(128)
+    YB_CONV_DISPATCH(128, 0)
   }
 #undef YB_CONV_DISPATCH
 }

@@ -251,7 +251,7 @@ YB_EPI_RES_BF16 = YB_EPI_RES_BF16
 
 def conv3d_causal(xpad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, T: int, H: int,
                   W: int, epilogue: int = YB_EPI_BF16, res: Optional[torch.Tensor] = None, taps=(3, 3, 3),
-                  oob_zero_pad: bool = False, out_t_mul: int = 1, out_t_add: int = 0) -> torch.Tensor:
+                  oob_zero_pad: bool = False, out_t_mul: int = 1, out_t_add: int = 0, fuse_w: int = 0) -> torch.Tensor:
     """Implicit-GEMM causal conv. Default: xpad bf16 [T+2, H+2, W+2, Cp] replicate padded (hyvideo VAE). With
     oob_zero_pad the input is the unpadded [T, H, W, Cp] and the zero padding is TMA out-of-bounds fill (Wan2.2 VAE).
     w bf16 [Cout, kt*kh*kw*Cp]; out rows are output voxels (frame t -> t*out_t_mul + out_t_add)."""
@@ -269,7 +269,7 @@ def conv3d_causal(xpad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tens
     args = Conv3dArgs(xpad=xpad.data_ptr(), w=w.data_ptr(), bias=_ptr(bias), out=out.data_ptr(), res=_ptr(res),
                       ldo=out.stride(0), res_ld=(res.stride(0) if res is not None else 0), T=T, H=H, W=W, Cp=Cp,
                       Cout=w.shape[0], epilogue=epilogue, kt=kt, kh=kh, kw=kw, oob_zero_pad=1 if oob_zero_pad else 0,
-                      out_t_mul=out_t_mul, out_t_add=out_t_add)
+                      out_t_mul=out_t_mul, out_t_add=out_t_add, fuse_w=fuse_w)
     check(_lib.load().yb_conv3d_causal(C.byref(args), _stream()), "yb_conv3d_causal")
     _launches += 1
     return out
