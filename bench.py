@@ -272,7 +272,10 @@ def product_arm(args):
         ach = att_flops / (att["mean_ms"] * 1e-3) / 1e12
         peak = peaks["bf16_sustained"] or peaks["bf16_tflops"]
         roof = {"bound": "tensor", "kernel": "attention_kernel<true> (self-attention)", "achieved": ach, "peak": peak,
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": ach / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one N=1 launch from the ncu --set full capture
+                # (profiles/r01_final_ncu_attention.md: 343.6 MB + 104.6 MB; algorithmic Q+K+V+O bytes = 454 MB)
+                "traffic": (448.2e6 if world == 1 else None), "traffic_unit": "bytes/launch",
                 "peak_source": peaks["source"] + ", sustained cuBLAS bf16 (kernel timed inside a long step)",
                 "mean_launch_ms": att["mean_ms"], "launches_timed": att["count"],
                 "share_of_step": att["total_ms"] / total_ms}
