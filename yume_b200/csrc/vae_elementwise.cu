@@ -324,6 +324,7 @@ dupup_add_kernel(__nv_bfloat16* __restrict__ main_, const __nv_bfloat16* __restr
   // from the (8x..16x smaller, cache-resident) source voxel
   const int To = ft * Ts - (ft - 1), Ho = Hs * fs, Wo = Ws * fs;
   const int rep = out_c * ft * fs * fs / in_c;
+  const int rsh = (rep & (rep - 1)) == 0 ? 31 - __clz(rep) : -1;   // rep is 2, 4 or 8 in both Wan VAEs: shift, no division
   const int chunks = out_c >> 3;
   const int estep = ft * fs * fs;
   const long long total = static_cast<long long>(To) * Ho * Wo * chunks;
@@ -345,8 +346,9 @@ dupup_add_kernel(__nv_bfloat16* __restrict__ main_, const __nv_bfloat16* __restr
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 m = __bfloat1622float2(hh[k]);
-      const float a0 = __bfloat162float(xs[(e0 + (2 * k) * estep) / rep]);
-      const float a1 = __bfloat162float(xs[(e0 + (2 * k + 1) * estep) / rep]);
+      const int ea = e0 + (2 * k) * estep, eb = ea + estep;
+      const float a0 = __bfloat162float(xs[rsh >= 0 ? (ea >> rsh) : ea / rep]);
+      const float a1 = __bfloat162float(xs[rsh >= 0 ? (eb >> rsh) : eb / rep]);
       hh[k] = __floats2bfloat162_rn(m.x + a0, m.y + a1);
     }
     *mp = raw;
