@@ -112,6 +112,35 @@ def _sdpa(q, k, v, heads):
     return o.transpose(0, 1).reshape(Lq, heads * 128)
 
 
+@pytest.mark.parametrize("split", [2, 3, 4])
+@pytest.mark.parametrize("Lq,Lk,heads", [(300, 1000, 2), (1000, 777, 3), (257, 2049, 1), (512, 512, 2)])
+def test_attention_kv_split_matches_unsplit(dev, Lq, Lk, heads, split):
+    """KV-split path (partial O / max / sum per segment + combine kernel) against the single-pass kernel and fp32."""
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(Lq + Lk + split)
+    q = torch.randn(Lq, heads * 128, generator=g).to(dev).bfloat16()
+    k = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
+    v = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
+    one = ops.attention(q, k, v, torch.empty_like(q), heads, split=1)
+    two = ops.attention(q, k, v, torch.full_like(q, 9.0), heads, split=split)
+    assert rel(two, one) < 3e-3                      # both bf16-rounded; segments change the fp32 summation order only
+    qh, kh, vh = (x.float().view(-1, heads, 128).transpose(0, 1) for x in (q, k, v))
+    ref = torch.softmax(qh @ kh.transpose(1, 2) / math.sqrt(128.0), dim=-1) @ vh
+    assert rel(two, ref.transpose(0, 1).reshape(Lq, heads * 128)) < KERNEL_TOL
+
+
+def test_attention_auto_tail_split_full_size_properties(dev):
+    """The 8-GPU Ulysses shape (3 heads, L = 18 480: 219 units on 148 SMs) takes the automatic tail split; compare the
+    whole output with the never-split launch."""
+    from yume_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(5)
+    L, heads = 18480, 3
+    q, k, v = (torch.randn(L, heads * 128, generator=g, device=dev).bfloat16() for _ in range(3))
+    a = ops.attention(q, k, v, torch.empty_like(q), heads, split=1)
+    b = ops.attention(q, k, v, torch.full_like(q, 7.0), heads, split=0)
+    assert bool(torch.isfinite(b.float()).all()) and rel(b, a) < 3e-3
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("Lq,Lk,heads", [(128, 128, 1), (300, 200, 2), (1000, 512, 3), (777, 1500, 2), (257, 257, 2),
                                          (1, 1, 1), (130, 769, 2)])

@@ -232,6 +232,22 @@ def sec_atttune():
         print(f"attention emu={emu}: {ms:.3f} ms = {fl/ms/1e9:.0f} TF/s   rel/max {rel(out[idx], ref)}")
 
 
+def sec_attsplit():
+    """Tail split of the attention launch: the per-rank shape of 8-GPU Ulysses (3 of 24 heads) and neighbours."""
+    from yume_b200 import ops
+    L = 18480
+    for heads in (3, 6, 24):
+        g = torch.Generator(device=dev).manual_seed(heads)
+        q, k, v = (torch.randn(L, heads * 128, generator=g, device=dev).bfloat16() for _ in range(3))
+        o = torch.empty_like(q)
+        fl = 4.0 * L * L * heads * 128
+        line = f"attsplit heads={heads} units={heads * ((L + 255) // 256)}:"
+        for name, split in (("never", 1), ("auto", 0), ("force2", 2)):
+            ms = timeit(lambda: ops.attention(q, k, v, o, heads, split=split), 10)
+            line += f"  {name} {ms:.3f} ms ({fl / ms / 1e9:.0f} TF/s)"
+        print(line, flush=True)
+
+
 def sec_atttrace():
     from yume_b200 import _lib
     heads, L = 24, 18480
@@ -264,7 +280,7 @@ def sec_atttrace():
     print("raw rows 0..2:", (t[:3] - base).tolist())
 
 
-SECTIONS = {"atttrace": sec_atttrace, "atttune": sec_atttune, "probe": sec_probe, "gemm": sec_gemm, "attention": sec_attention, "elementwise": sec_elementwise}
+SECTIONS = {"attsplit": sec_attsplit, "atttrace": sec_atttrace, "atttune": sec_atttune, "probe": sec_probe, "gemm": sec_gemm, "attention": sec_attention, "elementwise": sec_elementwise}
 if __name__ == "__main__":
     names = sys.argv[1:] or list(SECTIONS)
     print(torch.cuda.get_device_name(0))

@@ -16,6 +16,11 @@
 // TMEM columns: [0,128) S_0 / P_0, [128,256) S_1 / P_1, [256,384) O_0, [384,512) O_1.
 // Issue order per KV tile j: PV_0(j), S_0(j+1), PV_1(j), S_1(j+1) — while the tensor core works on tile X
 // the softmax warps of tile 1-X run. O is rescaled lazily (only when a row max grows by > 2^8).
+//
+// Tail split: a launch is U = heads x ceil(Lq/256) equal work units on 148 SMs. When the last wave is at most half
+// full (8-GPU Ulysses: 3 heads x 73 = 219 units = 1.48 waves) its T units are each cut into ns = floor(148 / T) KV
+// segments that run as separate CTAs and leave (unnormalised O, row max, row sum) in a workspace; a small combine
+// kernel merges the segments and performs the normal epilogue (bf16 store / Ulysses peer scatter). 2 waves -> 1.5.
 #include "yb_host.h"
 #include "yb_ptx.cuh"
 
@@ -36,6 +41,11 @@ struct AttParams {
   int sp_world, sp_rank, sp_Lp;
   long long* trace;  // optional clock64 trace of CTA (1,0), KV tiles 16..47 (tests/tools only; null in production)
   float scale_log2;  // softmax scale * log2(e)
+  // work decomposition: unit u = head * nq + q_block. CTAs [0, full_units) run whole units; CTA full_units + r runs KV
+  // segment r % ns of unit full_units + r / ns and writes a partial result to the workspace
+  int nq, full_units, ns;
+  float* ws_o;       // [tail CTAs, 256, 128] unnormalised O
+  float* ws_ml;      // [tail CTAs, 256, 2]   (row max in the log2 domain, row sum)
 };
 
 template <bool P_TMEM>
@@ -69,9 +79,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int q0 = blockIdx.x * 256;
-  const int nkv = p.nkv;
+  // Work decomposition (see AttParams): every role decodes it again INSIDE its own branch from an opaque copy of
+  // blockIdx.x, so that none of these values stays live across the register-starved softmax loop.
+  auto decode = [&](int& unit, int& kv_begin, int& nkv) {
+    int bx = blockIdx.x;
+    asm volatile("" : "+r"(bx));
+    unit = bx;
+    kv_begin = 0;
+    nkv = p.nkv;
+    if (bx >= p.full_units) {  // KV segment of a tail unit; kv_begin is even: barrier parities follow the global tile index
+      const int r = bx - p.full_units;
+      unit = p.full_units + r / p.ns;
+      const int per = (((p.nkv + p.ns - 1) / p.ns) + 1) & ~1;
+      kv_begin = (r % p.ns) * per;
+      nkv = min(per, p.nkv - kv_begin);
+    }
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -103,6 +126,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     setmaxnreg_dec<80>();
     if (warp == 0 && lane == 0) {
       // ------------------------------- TMA producer -------------------------------
+      int unit, kv_begin, nkv;
+      decode(unit, kv_begin, nkv);
+      const int head = unit / p.nq;
+      const int q0 = (unit - head * p.nq) * 256;
       mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
       for (int x = 0; x < 2; ++x)
         for (int s = 0; s < 2; ++s)
@@ -115,12 +142,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_arrive_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
         const CUtensorMap* tm = (it & 1) ? &tmV : &tmK;
         uint8_t* dst = smem + Cfg::KV_OFF + slot * ATT_TILE_BYTES;
-        const int j = it >> 1;
+        const int j = kv_begin + (it >> 1);
         tma_load_2d(dst, tm, &kv_full[slot], head * 128, j * 128);
         tma_load_2d(dst + 16384, tm, &kv_full[slot], head * 128 + 64, j * 128);
       }
     } else if (warp == 1 && lane == 0) {
       // ------------------------------- MMA issuer -------------------------------
+      int unit, kv_begin, nkv;
+      decode(unit, kv_begin, nkv);
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);
       const uint32_t sQ = smem_u32(smem + Cfg::Q_OFF);
@@ -130,14 +159,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // (compile-time) tile offsets: one 64-bit add per operand per MMA keeps the issue loop short.
       const uint64_t kdesc0 = make_smem_desc_sw128(0, 16, 1024);      // K-major tiles (Q, K, P-in-smem)
       const uint64_t vdesc0 = make_smem_desc_sw128(0, 16384, 1024);   // MN-major V tile
-      const uint64_t qdesc[2] = {kdesc0 + (sQ >> 4), kdesc0 + ((sQ + ATT_TILE_BYTES) >> 4)};
-      const uint64_t pdesc[2] = {kdesc0 + (sP >> 4), kdesc0 + ((sP + ATT_TILE_BYTES) >> 4)};
+      // tile X of Q / P sits ATT_TILE_BYTES after tile 0: + X * (ATT_TILE_BYTES >> 4) in the address field (scalars, not
+      // arrays: an array indexed by X lands in local memory whenever the X loop is not unrolled)
+      const uint64_t qdesc0 = kdesc0 + (sQ >> 4);
+      const uint64_t pdesc0 = kdesc0 + (sP >> 4);
+      constexpr uint64_t kTileStep = ATT_TILE_BYTES >> 4;
       auto issue_S = [&](int X, uint32_t kbase) {
         const uint64_t kd = kdesc0 + (kbase >> 4);
-#pragma unroll
+        uint64_t qd = qdesc0 + X * kTileStep;
+        asm volatile("" : "+l"(qd));   // opaque: keeps the 16 per-kk Q descriptors from being hoisted out of the KV loop
+#pragma unroll                         // (they do not fit next to the softmax branch's registers and would be spilled)
         for (int kk = 0; kk < 8; ++kk) {
           const uint32_t off16 = ((kk >> 2) * 16384 + (kk & 3) * 32) >> 4;
-          umma_ss(tmem_base + X * 128, qdesc[X] + off16, kd + off16, idesc_s, kk != 0 ? 1u : 0u);
+          umma_ss(tmem_base + X * 128, qd + off16, kd + off16, idesc_s, kk != 0 ? 1u : 0u);
         }
       };
       auto issue_PV = [&](int X, uint32_t vbase, bool acc, int half) {
@@ -151,7 +185,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     (acc || kk != 0) ? 1u : 0u);
           } else {
             const uint32_t off16 = ((kk >> 2) * 16384 + (kk & 3) * 32) >> 4;
-            umma_ss(tmem_base + 256 + X * 128, pdesc[X] + off16, bdesc, idesc_pv, (acc || kk != 0) ? 1u : 0u);
+            umma_ss(tmem_base + 256 + X * 128, pdesc0 + X * kTileStep + off16, bdesc, idesc_pv, (acc || kk != 0) ? 1u : 0u);
           }
         }
       };
@@ -178,7 +212,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t kbase = sKV + slot_k * ATT_TILE_BYTES;
 #pragma unroll
         for (int X = 0; X < 2; ++X) {
-          long long* tr = (p.trace != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && j >= 16 && j < 48)
+          long long* tr = (p.trace != nullptr && blockIdx.x == 1 && j >= 16 && j < 48)
                               ? p.trace + (j - 16) * 32 + 16 + X * 4 : nullptr;
           if (tr) tr[0] = clock64();
           mbar_wait(&p_half[2 * X], j & 1);
@@ -213,9 +247,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     float m_used = -INFINITY;
     float l = 0.f;
 
-    for (int j = 0; j < nkv; ++j) {
-      long long* tr = (p.trace != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && (warp & 3) == 0 && lane == 0 &&
-                       j >= 16 && j < 48) ? p.trace + (j - 16) * 32 + X * 8 : nullptr;
+    int kv_begin, kv_end;
+    {
+      int unit, nkv;
+      decode(unit, kv_begin, nkv);
+      kv_end = kv_begin + nkv;
+    }
+    for (int j = kv_begin; j < kv_end; ++j) {   // global KV tile index (kv_begin is even: parity of j == local parity)
+      long long* tr = (p.trace != nullptr && blockIdx.x == 1 && (warp & 3) == 0 && lane == 0 && j >= 16 && j < 48)
+                          ? p.trace + (j - 16) * 32 + X * 8 : nullptr;
       if (tr) tr[0] = clock64();
       mbar_wait(&s_full[X], j & 1);
       if (tr) tr[1] = clock64();
@@ -258,7 +298,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         asm volatile("" ::"f"(ms));
         tr[3] = clock64();
       }
-      if (j == 0) {
+      if (j == kv_begin) {
         m_used = ms;
       } else {
         const bool need = ms > m_used + 8.0f;
@@ -335,6 +375,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // epilogue: O / l -> bf16 -> global [Lq, heads*128]
     mbar_wait(&o_done[X], 0);
     tc_fence_after();
+    if (static_cast<int>(blockIdx.x) >= p.full_units) {
+      // KV segment of a tail unit: leave (O, m, l) for attention_combine_kernel
+      const long long prow = static_cast<long long>(blockIdx.x - p.full_units) * 256 + X * 128 + row_in_tile;
+      float* wo = p.ws_o + prow * 128;
+      *reinterpret_cast<float2*>(p.ws_ml + prow * 2) = make_float2(m_used, l);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tO + c * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<uint4*>(wo + c * 32 + 4 * i) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+      }
+    } else {
+    int unit, kvb, nk;
+    decode(unit, kvb, nk);
+    const int head = unit / p.nq;
+    const int q0 = (unit - head * p.nq) * 256;
     const float inv = 1.0f / l;
     const int q_row = q0 + X * 128 + row_in_tile;
     __nv_bfloat16* orow = p.out + static_cast<long long>(q_row) * p.ldo + head * 128;
@@ -375,6 +434,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
     }
+    }  // !partial
   }
 
   tc_fence_before();
@@ -385,9 +445,70 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
+// Merge the ns KV-segment partials of every tail unit and do the normal epilogue. One warp per query row, 4 columns per
+// lane: out = sum_s O_s 2^(m_s - M) / sum_s l_s 2^(m_s - M).
+__global__ void __launch_bounds__(256) attention_combine_kernel(const AttParams p, int tail_units) {
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gw >= tail_units * 256) return;
+  const int tu = gw >> 8, r = gw & 255;
+  const int unit = p.full_units + tu;
+  const int head = unit / p.nq;
+  const int q_row = (unit - head * p.nq) * 256 + r;
+  if (q_row >= p.Lq) return;
+  float M = -INFINITY;
+  for (int sgm = 0; sgm < p.ns; ++sgm) M = fmaxf(M, p.ws_ml[((static_cast<long long>(tu) * p.ns + sgm) * 256 + r) * 2]);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float lsum = 0.f;
+  for (int sgm = 0; sgm < p.ns; ++sgm) {
+    const long long prow = (static_cast<long long>(tu) * p.ns + sgm) * 256 + r;
+    const float2 ml = *reinterpret_cast<const float2*>(p.ws_ml + prow * 2);
+    const float w = exp2f(ml.x - M);
+    const float4 o = *reinterpret_cast<const float4*>(p.ws_o + prow * 128 + lane * 4);
+    acc.x += o.x * w; acc.y += o.y * w; acc.z += o.z * w; acc.w += o.w * w;
+    lsum += ml.y * w;
+  }
+  const float inv = 1.0f / lsum;
+  __nv_bfloat16* orow = p.out + static_cast<long long>(q_row) * p.ldo + head * 128;
+  if (p.sp_world > 1) {
+    const int owner = q_row / p.sp_Lp;
+    const int t = q_row - owner * p.sp_Lp;
+    if (owner < p.sp_world)
+      orow = p.out_peers[owner] + (static_cast<long long>(p.sp_rank) * p.sp_Lp + t) * p.ldo + head * 128;
+  }
+  *reinterpret_cast<uint2*>(orow + lane * 4) = make_uint2(pack_bf16x2(acc.x * inv, acc.y * inv), pack_bf16x2(acc.z * inv, acc.w * inv));
+}
+
+// Workspace of the tail split (<= 148 partial CTAs x 256 rows x 130 floats = 19.7 MB): owned by the library, grown on
+// demand, one per device. First use must not be inside a CUDA-graph capture (the engine warms up first).
+static int split_workspace(size_t ctas, float** ws_o, float** ws_ml, cudaStream_t stream) {
+  static float* buf[16] = {nullptr};
+  static size_t cap[16] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return YB_ERR_LAUNCH;
+  const size_t need = ctas * 256 * 130 * sizeof(float);
+  if (cap[dev] < need) {
+    if (buf[dev]) {
+      cudaStreamSynchronize(stream);
+      cudaFree(buf[dev]);
+      buf[dev] = nullptr;
+      cap[dev] = 0;
+    }
+    if (cudaMalloc(&buf[dev], need) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return YB_ERR_LAUNCH;
+    }
+    cap[dev] = need;
+  }
+  *ws_o = buf[dev];
+  *ws_ml = buf[dev] + ctas * 256 * 128;
+  return YB_OK;
+}
+
+// force_ns: 0 = automatic tail split, 1 = never, 2..4 = split EVERY unit into that many KV segments (tests)
 template <bool P_TMEM, int EMU>
 static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
-                            const AttParams& p, int heads, cudaStream_t stream) {
+                            AttParams p, int heads, cudaStream_t stream, int force_ns = 0) {
   using Cfg = AttCfg<P_TMEM>;
   auto kern = attention_kernel<P_TMEM, EMU>;
   static bool attr_set = false;
@@ -400,9 +521,38 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, cons
     }
     attr_set = true;
   }
-  dim3 grid((p.Lq + 255) / 256, heads);
-  kern<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
-  return check_launch("attention");
+  if (const char* env = getenv("YB_ATT_FORCE_SPLIT")) {   // tools/tests: "1" = off, "2".."4" = force
+    const int v = atoi(env);
+    if (v >= 1 && v <= 4) force_ns = v;
+  }
+  p.nq = (p.Lq + 255) / 256;
+  const int units = p.nq * heads;
+  const int sms = sm_count();
+  int tail = 0;
+  p.full_units = units;
+  p.ns = 1;
+  p.ws_o = p.ws_ml = nullptr;
+  const bool allowed = !p.accumulate && p.trace == nullptr && force_ns != 1;
+  if (allowed && force_ns >= 2 && p.nkv >= 2 * force_ns) {
+    tail = units;
+    p.ns = force_ns;
+  } else if (allowed && units > sms && units % sms != 0 && 2 * (units % sms) <= sms && p.nkv >= 16) {
+    tail = units % sms;
+    p.ns = sms / tail < 4 ? sms / tail : 4;
+  }
+  // every KV segment must own at least one tile (segment length is rounded up to an even tile count)
+  while (p.ns > 1 && (p.ns - 1) * ((((p.nkv + p.ns - 1) / p.ns) + 1) & ~1) >= p.nkv) --p.ns;
+  if (p.ns == 1) tail = 0;
+  if (tail > 0) {
+    p.full_units = units - tail;
+    const int rc = split_workspace(static_cast<size_t>(tail) * p.ns, &p.ws_o, &p.ws_ml, stream);
+    if (rc) return rc;
+  }
+  kern<<<p.full_units + tail * p.ns, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  int rc = check_launch("attention");
+  if (rc || tail == 0) return rc;
+  attention_combine_kernel<<<tail * 32, 256, 0, stream>>>(p, tail);
+  return check_launch("attention_combine");
 }
 
 }  // namespace yb
@@ -445,12 +595,14 @@ extern "C" int yb_attention_ex(const void* q, long long ldq, const void* k, long
   p.sp_Lp = 0;
   p.scale_log2 = scale * 1.4426950408889634f;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (flags & YB_ATT_P_SMEM) return launch_attention<false, 0>(tmQ, tmK, tmV, p, heads, stream);
+  const int force_ns = (flags >> YB_ATT_SPLIT_SHIFT) & 7;
+  if (force_ns > 4) return YB_ERR_ARG;
+  if (flags & YB_ATT_P_SMEM) return launch_attention<false, 0>(tmQ, tmK, tmV, p, heads, stream, force_ns);
   switch ((flags >> 2) & 3) {
-    case 1: return launch_attention<true, 4>(tmQ, tmK, tmV, p, heads, stream);
-    case 2: return launch_attention<true, 3>(tmQ, tmK, tmV, p, heads, stream);
-    case 3: return launch_attention<true, 2>(tmQ, tmK, tmV, p, heads, stream);
-    default: return launch_attention<true, 0>(tmQ, tmK, tmV, p, heads, stream);
+    case 1: return launch_attention<true, 4>(tmQ, tmK, tmV, p, heads, stream, force_ns);
+    case 2: return launch_attention<true, 3>(tmQ, tmK, tmV, p, heads, stream, force_ns);
+    case 3: return launch_attention<true, 2>(tmQ, tmK, tmV, p, heads, stream, force_ns);
+    default: return launch_attention<true, 0>(tmQ, tmK, tmV, p, heads, stream, force_ns);
   }
 }
 
