@@ -178,3 +178,65 @@ def test_wan21_vae_plan_and_shapes_match_oracle():
         assert upsample_plan(dim) == wan21vae.layer_plan(dim)
     kinds = [k for _, k, _, _ in upsample_plan()]
     assert kinds.count("upsample3d") == 2 and kinds.count("upsample2d") == 1 and kinds.count("res") == 12
+
+
+class _FakeVaeModel:
+    def __init__(self, sd, **attrs):
+        self._sd = sd
+        self.__dict__.update(attrs)
+
+    def state_dict(self):
+        return self._sd
+
+
+def test_install_wan_vae_hooks_rebind_decode_with_reference_contract():
+    """install_wan22_vae / install_wan21_vae read the wrapper's own attributes (vae2_2.py:748-792,909-1040;
+    wan/modules/vae.py:484-500,618-645) and keep decode's list-in / list-out contract. No GPU: packing only."""
+    import torch
+    from oracle import wan21vae, wan22vae
+    from yume_b200.vae21 import install_wan21_vae
+    from yume_b200.vae22 import install_wan22_vae
+
+    cfg22 = dict(dec_dim=32, z_dim=16, dim_mult=(1, 2, 4, 4), num_res_blocks=2, temperal_upsample=(True, True, False))
+    sd = wan22vae.make_state_dict(5, **cfg22)
+    sd["encoder.conv1.weight"] = torch.zeros(4, 4, 3, 3, 3)          # encoder-side keys are ignored by the decode engine
+
+    class W22:
+        pass
+
+    w = W22()
+    w.model = _FakeVaeModel(sd, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2, temperal_upsample=[True, True, False])
+    mean, std = torch.randn(16), 0.5 + torch.rand(16)
+    w.scale = [mean, 1.0 / std]
+    install_wan22_vae(w, device="cpu")
+    eng = w._yb_decoder
+    assert eng.dims == [128, 128, 128, 64, 32] and eng.z_dim == 16
+    assert w.decode("not a list") is None                            # Wan2_2_VAE.decode logs a TypeError and returns None
+    assert w.decode([]) == []
+    w2, _ = eng.lin["conv2"]
+    assert torch.allclose(w2.float()[:16, :16], (sd["conv2.weight"].reshape(16, 16) * std[None, :]).bfloat16().float())
+
+    cfg21 = dict(dim=32, z_dim=16, dim_mult=(1, 2, 4, 4), num_res_blocks=2, temperal_upsample=(True, True, False))
+    sd21 = wan21vae.make_state_dict(6, **cfg21)
+
+    class W21:
+        pass
+
+    v = W21()
+    v.model = _FakeVaeModel(sd21, dim=32, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2,
+                            temperal_upsample=[True, True, False])
+    v.mean, v.std = torch.randn(16), 0.5 + torch.rand(16)
+    install_wan21_vae(v, device="cpu")
+    assert v.decode([]) == [] and len(v._yb_decoder.plan) == 15
+    with pytest.raises(Exception):
+        v._yb_decoder.decode(torch.zeros(3, 1, 4, 4))               # wrong latent channel count is an error, not a guess
+
+
+def test_wan_vae_param_shapes_match_reference_module_trees(golden_dir):
+    """decoder_param_shapes() of both Wan VAE engines == the reference's own module trees at the real sizes
+    (fixture: tools/make_golden_vae_shapes.py, built from vae2_2.py / vae.py on the meta device)."""
+    import json
+    from yume_b200 import vae21, vae22
+    ref = json.loads((golden_dir / "wan_vae_shapes.json").read_text())
+    assert {k: list(v) for k, v in vae22.decoder_param_shapes().items()} == ref["wan22"]
+    assert {k: list(v) for k, v in vae21.decoder_param_shapes().items()} == ref["wan21"]

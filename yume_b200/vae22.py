@@ -90,7 +90,8 @@ class Wan22VaeDecoder:
     # ---- weights -------------------------------------------------------------------------------------------
     def _repack(self, sd: Dict[str, Tensor], mean: Tensor, std: Tensor) -> None:
         dev = self.device
-        sd = {k: v.detach().to(dev, _F32) for k, v in sd.items()}       # packing runs on the target device
+        # decode-side modules only (`conv2`, `decoder.*`); a live WanVAE_ also carries `encoder.*` and `conv1.*`
+        sd = {k: v.detach().to(dev, _F32) for k, v in sd.items() if k.startswith(("decoder.", "conv2."))}
         self.conv: Dict[str, Tuple[Tensor, Tensor, tuple]] = {}    # name -> (w bf16 [cop, taps*cp], bias f32 [cop], taps)
         self.lin: Dict[str, Tuple[Tensor, Tensor]] = {}            # 1x1x1 convs as plain GEMM weights
         self.gamma: Dict[str, Tensor] = {}
