@@ -97,6 +97,9 @@ typedef struct yb_conv3d_args {
   int fuse_w;
 } yb_conv3d_args;
 int yb_conv3d_causal(const yb_conv3d_args* args, void* stream);
+/* Host-only: the tile plan yb_conv3d_causal would use (no device access; pins the chooser in the CPU test-suite).
+ * out4 = {TW, TH, TT, kw-fused?}: the 128-voxel output tile is a TT x TH x TW box; fused = one-row tile + 130-voxel halo. */
+int yb_conv3d_plan(int T, int H, int W, int Cout, int kw, int fuse_w, int* out4);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused LayerNorm (no affine, eps) + adaLN modulate -> bf16:  h = LN(x) * (1 + scale) + shift
@@ -149,6 +152,10 @@ int yb_attention_ex(const void* q, long long ldq, const void* k, long long ldk, 
 #define YB_ATT_SPLIT_SHIFT 4 /* flags bits 4-6: KV split policy. 0 = automatic (the units of a last wave that is at most
                                half full are cut into KV segments and merged by a combine kernel), 1 = never, 2..4 = cut
                                EVERY unit into that many segments (tests). Results are identical up to fp32 rounding. */
+/* Host-only: the work decomposition yb_attention would use on a GPU with `sms` SMs (no device access; the CPU test-suite
+ * pins the scheduler with it). out4 = {CTAs running whole units, tail units that are split, KV segments per tail unit,
+ * 128-key tiles per segment}. flags as for yb_attention (ACCUMULATE disables the split; bits 4-6 force it). */
+int yb_attention_plan(int Lq, int Lk, int heads, int sms, int flags, int* out4);
 
 /* ---------------------------------------------------------------------------------------------
  * Ulysses sequence parallelism fused with the NVLink exchange (design reference

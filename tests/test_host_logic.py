@@ -240,3 +240,64 @@ def test_wan_vae_param_shapes_match_reference_module_trees(golden_dir):
     ref = json.loads((golden_dir / "wan_vae_shapes.json").read_text())
     assert {k: list(v) for k, v in vae22.decoder_param_shapes().items()} == ref["wan22"]
     assert {k: list(v) for k, v in vae21.decoder_param_shapes().items()} == ref["wan21"]
+
+
+def test_attention_tail_split_plan():
+    """Scheduler of the attention launch (host arithmetic exported as yb_attention_plan): the Ulysses per-rank shapes of
+    the 720p step and the invariants the kernel relies on."""
+    import ctypes as C
+    from yume_b200 import _lib
+    lib = _lib.load()
+
+    def plan(Lq, Lk, heads, sms=148, flags=0):
+        out = (C.c_int * 4)()
+        assert lib.yb_attention_plan(Lq, Lk, heads, sms, flags, out) == 0
+        return tuple(out)
+
+    L = 18480
+    assert plan(L, L, 3) == (148, 71, 2, 74)              # 8 GPUs: 219 units = 1.48 waves -> 71 tail units in two KV halves
+    for heads in (24, 12, 6):                             # 1 / 2 / 4 GPUs: last wave more than half full, no split
+        full, tail, ns, per = plan(L, L, heads)
+        assert (tail, ns) == (0, 1) and full == heads * 73 and per == 145
+    assert plan(L, L, 3, flags=2)[1] == 0                 # YB_ATT_ACCUMULATE launches never split
+    assert plan(L, L, 3, flags=1 << 4)[1] == 0            # split policy 1 = never
+    assert plan(300, 512, 2, flags=2 << 4) == (0, 4, 2, 2)    # forced: every unit, 4 key tiles -> 2 + 2
+    assert plan(300, 256, 2, flags=2 << 4)[1] == 0            # too few key tiles to split
+    assert lib.yb_attention_plan(0, 1, 1, 148, 0, (C.c_int * 4)()) != 0
+    import itertools
+    for Lq, Lk, heads, sms, force in itertools.product((1, 255, 257, 5000, 18480, 40000), (1, 129, 2049, 18480, 33000),
+                                                       (1, 3, 5, 24), (1, 132, 148), (0, 2, 3, 4)):
+        full, tail, ns, per = plan(Lq, Lk, heads, sms, flags=force << 4)
+        units, nkv = ((Lq + 255) // 256) * heads, (Lk + 127) // 128
+        assert full + tail == units and 1 <= ns <= 4 and (tail == 0) == (ns == 1)
+        if ns > 1:
+            assert per % 2 == 0 and (ns - 1) * per < nkv <= ns * per      # even segments, none empty, all keys covered
+            if force == 0:
+                assert full % sms == 0 and tail * ns <= sms               # the split tail fits in one wave
+
+
+def test_conv_tile_plan():
+    """Tile chooser of the implicit-GEMM conv (host arithmetic exported as yb_conv3d_plan) on the shapes of the three VAEs."""
+    import ctypes as C
+    from yume_b200 import _lib
+    lib = _lib.load()
+
+    def plan(T, H, W, cout, kw=3, fuse=0):
+        out = (C.c_int * 4)()
+        assert lib.yb_conv3d_plan(T, H, W, cout, kw, fuse, out) == 0
+        return tuple(out)
+
+    assert plan(21, 44, 80, 1024) == (16, 4, 2, 0)        # Wan2.2 level 0: a 128-wide row tile would waste 38 %
+    assert plan(81, 176, 320, 512) == (64, 2, 1, 0)       # 256-wide N tile: fused only when the row tile is ~free
+    assert plan(81, 352, 640, 256) == (128, 1, 1, 1)      # W multiple of 128: kw-fused halo mode
+    assert plan(81, 544, 960, 96) == (128, 1, 1, 1)       # Wan2.1 96-channel level: fused (6 % ragged edge accepted)
+    assert plan(81, 544, 960, 96, fuse=1)[3] == 0
+    assert plan(40, 88, 160, 1024, kw=1)[3] == 0          # time_conv (3,1,1) has no kw taps to fuse
+    assert plan(3, 8, 8, 64, fuse=2) == (128, 1, 1, 1)    # forced (tests): correct at any width, just wasteful
+    assert plan(17, 256, 256, 128) == (128, 1, 1, 1)      # hyvideo last level
+    for T, H, W, co in ((1, 1, 1, 32), (5, 3, 7, 64), (9, 4, 4, 32), (2, 130, 9, 64), (17, 32, 32, 512), (81, 720, 1280, 128)):
+        tw, th, tt, fused = plan(T, H, W, co)
+        assert tw * th * tt == 128 and tw <= max(128, 1)
+        tiles = -(-W // tw) * -(-H // th) * -(-T // tt)
+        assert tiles * 128 >= T * H * W
+    assert lib.yb_conv3d_plan(1, 1, 1, 32, 2, 0, (C.c_int * 4)()) != 0

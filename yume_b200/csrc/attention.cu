@@ -479,6 +479,29 @@ __global__ void __launch_bounds__(256) attention_combine_kernel(const AttParams 
   *reinterpret_cast<uint2*>(orow + lane * 4) = make_uint2(pack_bf16x2(acc.x * inv, acc.y * inv), pack_bf16x2(acc.z * inv, acc.w * inv));
 }
 
+// Work decomposition of one launch (pure host arithmetic; exported as yb_attention_plan for the CPU test-suite).
+//   units        heads x ceil(Lq / 256) equal work units
+//   force_ns     0 = automatic, 1 = never split, 2..4 = split every unit into that many KV segments
+// Automatic rule: when the last wave on `sms` SMs is at most half full and there is more than one wave, its `tail` units
+// are cut into ns = min(4, sms / tail) KV segments. Segment length is rounded up to an EVEN number of 128-key tiles (the
+// kernel takes barrier parities from the global tile index) and every segment must own at least one tile.
+static void attention_plan(int units, int nkv, int sms, bool allowed, int force_ns, int* full_units, int* tail, int* ns) {
+  *full_units = units;
+  *tail = 0;
+  *ns = 1;
+  if (!allowed || force_ns == 1) return;
+  if (force_ns >= 2 && nkv >= 2 * force_ns) {
+    *tail = units;
+    *ns = force_ns;
+  } else if (force_ns == 0 && units > sms && units % sms != 0 && 2 * (units % sms) <= sms && nkv >= 16) {
+    *tail = units % sms;
+    *ns = sms / *tail < 4 ? sms / *tail : 4;
+  }
+  while (*ns > 1 && (*ns - 1) * ((((nkv + *ns - 1) / *ns) + 1) & ~1) >= nkv) --*ns;
+  if (*ns == 1) *tail = 0;
+  *full_units = units - *tail;
+}
+
 // Workspace of the tail split (<= 148 partial CTAs x 256 rows x 130 floats = 19.7 MB): owned by the library, grown on
 // demand, one per device. First use must not be inside a CUDA-graph capture (the engine warms up first).
 static int split_workspace(size_t ctas, float** ws_o, float** ws_ml, cudaStream_t stream) {
@@ -527,24 +550,10 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, cons
   }
   p.nq = (p.Lq + 255) / 256;
   const int units = p.nq * heads;
-  const int sms = sm_count();
   int tail = 0;
-  p.full_units = units;
-  p.ns = 1;
   p.ws_o = p.ws_ml = nullptr;
-  const bool allowed = !p.accumulate && p.trace == nullptr && force_ns != 1;
-  if (allowed && force_ns >= 2 && p.nkv >= 2 * force_ns) {
-    tail = units;
-    p.ns = force_ns;
-  } else if (allowed && units > sms && units % sms != 0 && 2 * (units % sms) <= sms && p.nkv >= 16) {
-    tail = units % sms;
-    p.ns = sms / tail < 4 ? sms / tail : 4;
-  }
-  // every KV segment must own at least one tile (segment length is rounded up to an even tile count)
-  while (p.ns > 1 && (p.ns - 1) * ((((p.nkv + p.ns - 1) / p.ns) + 1) & ~1) >= p.nkv) --p.ns;
-  if (p.ns == 1) tail = 0;
+  attention_plan(units, p.nkv, sm_count(), !p.accumulate && p.trace == nullptr, force_ns, &p.full_units, &tail, &p.ns);
   if (tail > 0) {
-    p.full_units = units - tail;
     const int rc = split_workspace(static_cast<size_t>(tail) * p.ns, &p.ws_o, &p.ws_ml, stream);
     if (rc) return rc;
   }
@@ -560,6 +569,20 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, cons
 extern "C" int yb_attention_ex(const void* q, long long ldq, const void* k, long long ldk, const void* v,
                                long long ldv, void* out, long long ldo, int Lq, int Lk, int heads, float scale,
                                int flags, void* trace, void* stream_);
+
+extern "C" int yb_attention_plan(int Lq, int Lk, int heads, int sms, int flags, int* out4) {
+  if (Lq <= 0 || Lk <= 0 || heads <= 0 || sms <= 0 || !out4) return YB_ERR_ARG;
+  const int force_ns = (flags >> YB_ATT_SPLIT_SHIFT) & 7;
+  if (force_ns > 4) return YB_ERR_ARG;
+  const int nkv = (Lk + 127) / 128;
+  int full_units, tail, ns;
+  yb::attention_plan(((Lq + 255) / 256) * heads, nkv, sms, !(flags & YB_ATT_ACCUMULATE), force_ns, &full_units, &tail, &ns);
+  out4[0] = full_units;
+  out4[1] = tail;
+  out4[2] = ns;
+  out4[3] = ns > 1 ? ((((nkv + ns - 1) / ns) + 1) & ~1) : nkv;   // KV tiles per segment
+  return YB_OK;
+}
 
 extern "C" int yb_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                             void* out, long long ldo, int Lq, int Lk, int heads, float scale, int flags,

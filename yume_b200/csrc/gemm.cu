@@ -468,7 +468,43 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   return check_launch("gemm");
 }
 
+// Tile plan of one conv launch (pure host arithmetic; exported as yb_conv3d_plan for the CPU test-suite).
+// The 128-voxel output tile is a TT x TH x TW box (powers of two): pick the shape that wastes the fewest rows on ragged
+// edges (W = 80 / 160 / 320 of the 720p Wan2.2 decode would lose 38 / 38 / 17 % with a fixed 128-wide row tile); ties go
+// to the widest box (fewest halo re-reads).
+// kw-fused mode (one 130-voxel halo box feeds the three kw taps) needs the one-row 128-voxel tile; it is taken when that
+// tile shape costs little utilisation — generously for 128-wide N tiles (operand-fetch bound), only when nearly free for
+// 256-wide ones (MMA bound). fuse_policy: 0 = auto, 1 = off, 2 = force (tests).
+static void conv_plan(int T, int H, int W, int block_n, int kw, int fuse_policy, int* TW, int* TH, int* TT, bool* fused) {
+  auto pow2_ge = [](int v) { int p = 1; while (p < v) p <<= 1; return p; };
+  double best = -1.0;
+  const double vox = static_cast<double>(T) * H * W;
+  for (int tw = 128; tw >= 1; tw >>= 1) {
+    if (tw > pow2_ge(W)) continue;
+    for (int th = 128 / tw; th >= 1; th >>= 1) {
+      const int tt = 128 / (tw * th);
+      const double tiles = static_cast<double>((W + tw - 1) / tw) * ((H + th - 1) / th) * ((T + tt - 1) / tt);
+      const double util = vox / (tiles * 128.0);
+      if (util > best + 1e-9) { best = util; *TW = tw; *TH = th; *TT = tt; }
+    }
+  }
+  *fused = false;
+  if (kw == 3 && fuse_policy != 1 && (W >= 64 || fuse_policy == 2)) {
+    const double util128 = static_cast<double>(W) / (((W + 127) / 128) * 128.0);
+    *fused = fuse_policy == 2 || util128 >= (block_n == 128 ? 0.70 : 0.95) * best;
+  }
+  if (*fused) { *TW = 128; *TH = 1; *TT = 1; }
+}
+
 }  // namespace yb
+
+extern "C" int yb_conv3d_plan(int T, int H, int W, int Cout, int kw, int fuse_w, int* out4) {
+  if (T <= 0 || H <= 0 || W <= 0 || Cout <= 0 || (kw != 1 && kw != 3) || fuse_w < 0 || fuse_w > 2 || !out4) return YB_ERR_ARG;
+  bool fused = false;
+  yb::conv_plan(T, H, W, (Cout % 256 == 0) ? 256 : 128, kw, fuse_w, &out4[0], &out4[1], &out4[2], &fused);
+  out4[3] = fused ? 1 : 0;
+  return YB_OK;
+}
 
 extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
   using namespace yb;
@@ -539,38 +575,12 @@ extern "C" int yb_conv3d_causal(const yb_conv3d_args* a, void* stream_) {
   if (a->epilogue != YB_EPI_BF16 && a->epilogue != YB_EPI_F32 && a->epilogue != YB_EPI_RES_BF16) return YB_ERR_ARG;
   if (a->epilogue == YB_EPI_RES_BF16 && (!a->res || (a->res_ld % 8))) return YB_ERR_ARG;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  auto pow2_ge = [](int v) { int p = 1; while (p < v) p <<= 1; return p; };
   GemmParams p;
-  // 128-voxel output tile = TT x TH x TW box (powers of two): pick the shape that wastes the fewest rows on ragged edges
-  // (W = 80 / 160 / 320 of the 720p Wan2.2 decode would lose 38 / 38 / 17 % with a fixed 128-wide row tile); ties go to
-  // the widest box (fewest halo re-reads)
-  {
-    double best = -1.0;
-    const double vox = static_cast<double>(a->T) * a->H * a->W;
-    for (int tw = 128; tw >= 1; tw >>= 1) {
-      if (tw > pow2_ge(a->W)) continue;
-      for (int th = 128 / tw; th >= 1; th >>= 1) {
-        const int tt = 128 / (tw * th);
-        const double tiles = static_cast<double>((a->W + tw - 1) / tw) * ((a->H + th - 1) / th) * ((a->T + tt - 1) / tt);
-        const double util = vox / (tiles * 128.0);
-        if (util > best + 1e-9) { best = util; p.TW = tw; p.TH = th; p.TT = tt; }
-      }
-    }
-  }
   const int kt = a->kt > 0 ? a->kt : 3, kh = a->kh > 0 ? a->kh : 3, kw = a->kw > 0 ? a->kw : 3;
   if ((kt != 1 && kt != 3) || (kh != 1 && kh != 3) || (kw != 1 && kw != 3)) return YB_ERR_SHAPE;
   const int block_n = (a->Cout % 256 == 0) ? 256 : 128;
-  // kw-fused mode (one 130-voxel halo box feeds the three kw taps): needs the one-row 128-voxel tile; taken when that
-  // tile shape costs little utilisation — always worth it for 128-wide N tiles (A-traffic bound), only when nearly free
-  // for 256-wide ones (MMA bound). a->fuse_w: 0 = auto, 1 = off, 2 = force (tests).
   bool fuse_w = false;
-  if (kw == 3 && a->fuse_w != 1 && (a->W >= 64 || a->fuse_w == 2)) {
-    const double util128 = static_cast<double>(a->W) / (((a->W + 127) / 128) * 128.0);
-    const double best = static_cast<double>(a->T) * a->H * a->W /
-                        (128.0 * ((a->W + p.TW - 1) / p.TW) * ((a->H + p.TH - 1) / p.TH) * ((a->T + p.TT - 1) / p.TT));
-    fuse_w = a->fuse_w == 2 || util128 >= (block_n == 128 ? 0.70 : 0.95) * best;
-  }
-  if (fuse_w) { p.TW = 128; p.TH = 1; p.TT = 1; }
+  conv_plan(a->T, a->H, a->W, block_n, kw, a->fuse_w, &p.TW, &p.TH, &p.TT, &fuse_w);
   p.tiles_w = (a->W + p.TW - 1) / p.TW;
   p.tiles_h = (a->H + p.TH - 1) / p.TH;
   const int tiles_t = (a->T + p.TT - 1) / p.TT;
