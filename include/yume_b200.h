@@ -249,6 +249,10 @@ int yb_vae_unpatchify2_clamp(const void* y, long long ldy, void* out, int T, int
  *   mode 2: A in TMEM (bf16x2 packed), B MN-major D = A * Bmn
  * A, B bf16 [128,128] row-major; D f32 [128,128].
  * ------------------------------------------------------------------------------------------- */
+/* EXPERIMENTAL (not on the product path, not yet run on hardware; tests skipped unless YB_RUN_EXPERIMENTAL=1): SM-pair
+ * (`tcgen05.mma.cta_group::2`) GEMM, out bf16 [M, N] = A[M, K] x B[N, K]^T + bias — yume_b200/csrc/gemm2cta.cu. */
+int yb_gemm_bf16_2cta(const void* A, long long lda, const void* B, long long ldb, const void* bias, void* out,
+                      long long ldo, int M, int N, int K, void* stream);
 int yb_umma_probe(const void* A, const void* B, void* D, int mode, void* stream);  /* modes >= 3: A rows shifted by (mode - 2) */
 
 #ifdef __cplusplus

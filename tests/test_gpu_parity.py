@@ -8,6 +8,7 @@ Tolerances (bf16 path vs fp32-weight oracle, SURVEY.md §8c / BASELINE.md §3):
   * whole tiny model output: rel-Frobenius <= 1.5e-2
 """
 import math
+import os
 
 import pytest
 import torch
@@ -48,6 +49,19 @@ def test_umma_probe(dev, mode):
     d = ops.umma_probe(a, b, mode)
     ref = a.float() @ (b.float().t() if mode == 0 else b.float())
     assert rel(d, ref) < 1e-5
+
+
+@pytest.mark.skipif(os.environ.get("YB_RUN_EXPERIMENTAL") != "1",
+                    reason="SM-pair GEMM is experimental: written without GPU time left, never run on hardware yet")
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (300, 512, 192), (4097, 768, 256), (1000, 3072, 3072)])
+def test_experimental_gemm_2cta_matches_fp32_reference(dev, M, N, K):
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev).bfloat16()
+    b = torch.randn(N, generator=g).to(dev)
+    out = ops.gemm_2cta(a, w, b, torch.empty(M, N, device=dev, dtype=torch.bfloat16))
+    assert rel(out, a.float() @ w.float().t() + b) < KERNEL_TOL
 
 
 @pytest.mark.parametrize("shift", [1, 2, 3, 7, 8])

@@ -248,6 +248,21 @@ def sec_attsplit():
         print(line, flush=True)
 
 
+def sec_gemm2cta():
+    """EXPERIMENTAL SM-pair GEMM against the product GEMM and cuBLAS on the DiT shapes (run with a short timeout)."""
+    L, C, F = 18480, 3072, 14336
+    for name, (M, N, K) in (("qkv", (L, 3 * C, C)), ("o", (L, C, C)), ("ffn1", (L, F, C)), ("ffn2", (L, C, F))):
+        a = torch.randn(M, K, device=dev).bfloat16()
+        w = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
+        o1, o2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16), torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        fl = 2.0 * M * N * K
+        t1 = timeit(lambda: ops.gemm(a, w, None, o1, ops.YB_EPI_BF16), 5)
+        t2 = timeit(lambda: ops.gemm_2cta(a, w, None, o2), 5)
+        t3 = timeit(lambda: torch.matmul(a, w.t()), 5)
+        print(f"gemm2cta {name}: 1-CTA {t1:.3f} ms ({fl/t1/1e9:.0f} TF/s)  2-CTA {t2:.3f} ms ({fl/t2/1e9:.0f} TF/s)  "
+              f"cuBLAS {t3:.3f} ms ({fl/t3/1e9:.0f} TF/s)  rel(2cta,1cta) {rel(o2, o1)}", flush=True)
+
+
 def sec_atttrace():
     from yume_b200 import _lib
     heads, L = 24, 18480
@@ -280,9 +295,9 @@ def sec_atttrace():
     print("raw rows 0..2:", (t[:3] - base).tolist())
 
 
-SECTIONS = {"attsplit": sec_attsplit, "atttrace": sec_atttrace, "atttune": sec_atttune, "probe": sec_probe, "gemm": sec_gemm, "attention": sec_attention, "elementwise": sec_elementwise}
+SECTIONS = {"gemm2cta": sec_gemm2cta, "attsplit": sec_attsplit, "atttrace": sec_atttrace, "atttune": sec_atttune, "probe": sec_probe, "gemm": sec_gemm, "attention": sec_attention, "elementwise": sec_elementwise}
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(SECTIONS)
+    names = sys.argv[1:] or [n for n in SECTIONS if n != "gemm2cta"]   # experimental sections only on request
     print(torch.cuda.get_device_name(0))
     for n in names:
         print(f"===== {n} =====", flush=True)

@@ -60,6 +60,7 @@ SIGNATURES = {
     "yb_masked_softmax": (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp]),
     "yb_nchw_to_nhwc_bf16": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
     "yb_nhwc_to_nchw_f32": (_i, [_vp, _ll, _vp, _ll, _i, _vp]),
+    "yb_gemm_bf16_2cta": (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _vp]),
     "yb_conv3d_plan": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(C.c_int)]),
     "yb_attention_plan": (_i, [_i, _i, _i, _i, _i, C.POINTER(C.c_int)]),
     "yb_nhwc_to_nchw_f32_clamp": (_i, [_vp, _ll, _vp, _ll, _i, C.c_float, C.c_float, _vp]),

@@ -134,6 +134,24 @@ def rmsnorm_rope(qk: torch.Tensor, weight: torch.Tensor, rope: Optional[torch.Te
     return qk
 
 
+def gemm_2cta(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+    """EXPERIMENTAL SM-pair GEMM (yb_gemm_bf16_2cta): out bf16 = a[M,K] @ w[N,K]^T + bias. Not on the product path."""
+    global _launches
+    _need(a, torch.bfloat16, "a")
+    _need(w, torch.bfloat16, "w")
+    _need(out, torch.bfloat16, "out")
+    if bias is not None:
+        _need(bias, torch.float32, "bias")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K or tuple(out.shape) != (M, N):
+        raise YumeB200Error("gemm_2cta: shape mismatch")
+    check(_lib.load().yb_gemm_bf16_2cta(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), out.data_ptr(),
+                                        out.stride(0), M, N, K, _stream()), "yb_gemm_bf16_2cta")
+    _launches += 1
+    return out
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, heads: int,
               scale: Optional[float] = None, variant: int = 0, accumulate: bool = False, emu: int = 0,
               split: int = 0) -> torch.Tensor:
