@@ -149,6 +149,8 @@ int yb_attention_ex(const void* q, long long ldq, const void* k, long long ldk, 
                                0 = none, 1 = 1/4, 2 = 1/3, 3 = 1/2 (tuning knob; results agree to < 2e-4 relative) */
 #define YB_ATT_ACCUMULATE 2 /* flags bit 1: out += result (WanI2VCrossAttention sums the text and image branches,
                                wan/modules/model.py:380-387) */
+#define YB_ATT_Q64 128      /* flags bit 7: EXPERIMENTAL kernel variant (Q resident in TMEM, 64-key tiles; attention64.cu) — not
+                               yet run on hardware, never set by the product path */
 #define YB_ATT_SPLIT_SHIFT 4 /* flags bits 4-6: KV split policy. 0 = automatic (the units of a last wave that is at most
                                half full are cut into KV segments and merged by a combine kernel), 1 = never, 2..4 = cut
                                EVERY unit into that many segments (tests). Results are identical up to fp32 rounding. */

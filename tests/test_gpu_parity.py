@@ -126,6 +126,24 @@ def _sdpa(q, k, v, heads):
     return o.transpose(0, 1).reshape(Lq, heads * 128)
 
 
+@pytest.mark.skipif(os.environ.get("YB_RUN_EXPERIMENTAL") != "1",
+                    reason="Q-in-TMEM attention is experimental: written without GPU time left, never run on hardware yet")
+@pytest.mark.parametrize("emu", [0, 2])
+@pytest.mark.parametrize("Lq,Lk,heads", [(128, 64, 1), (128, 128, 1), (300, 200, 2), (1000, 512, 3), (777, 1500, 2), (257, 257, 2)])
+def test_experimental_attention_q64_matches_fp32_reference(dev, Lq, Lk, heads, emu):
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(Lq * 7 + Lk + emu)
+    q = torch.randn(Lq, heads * 128, generator=g).to(dev).bfloat16()
+    k = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
+    v = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
+    out = ops.attention(q, k, v, torch.full_like(q, 5.0), heads, variant=2, emu=emu)
+    qh, kh, vh = (x.float().view(-1, heads, 128).transpose(0, 1) for x in (q, k, v))
+    ref = torch.softmax(qh @ kh.transpose(1, 2) / math.sqrt(128.0), dim=-1) @ vh
+    assert rel(out, ref.transpose(0, 1).reshape(Lq, heads * 128)) < KERNEL_TOL
+    acc = ops.attention(q, k, v, out.clone(), heads, variant=2, accumulate=True)     # out += result
+    assert rel(acc, 2 * ref.transpose(0, 1).reshape(Lq, heads * 128)) < 2 * KERNEL_TOL
+
+
 @pytest.mark.parametrize("split", [2, 3, 4])
 @pytest.mark.parametrize("Lq,Lk,heads", [(300, 1000, 2), (1000, 777, 3), (257, 2049, 1), (512, 512, 2)])
 def test_attention_kv_split_matches_unsplit(dev, Lq, Lk, heads, split):

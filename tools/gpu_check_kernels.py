@@ -248,6 +248,20 @@ def sec_attsplit():
         print(line, flush=True)
 
 
+def sec_att64():
+    """EXPERIMENTAL Q-in-TMEM / 64-key-tile attention against the product kernel at the 5B shape (short timeout!)."""
+    heads, L = 24, 18480
+    qkv = torch.randn(L, 3 * heads * 128, device=dev).bfloat16()
+    q = qkv[:, : heads * 128]; k = qkv[:, heads * 128: 2 * heads * 128]; v = qkv[:, 2 * heads * 128:]
+    o0, o1 = torch.empty(L, heads * 128, device=dev, dtype=torch.bfloat16), torch.empty(L, heads * 128, device=dev, dtype=torch.bfloat16)
+    fl = 4.0 * L * L * heads * 128
+    t0 = timeit(lambda: ops.attention(q, k, v, o0, heads), 5)
+    print(f"att64: product kernel {t0:.3f} ms = {fl/t0/1e9:.0f} TF/s", flush=True)
+    for emu in (0, 1, 2, 3):
+        t1 = timeit(lambda: ops.attention(q, k, v, o1, heads, variant=2, emu=emu), 5)
+        print(f"att64: q64 emu={emu} {t1:.3f} ms = {fl/t1/1e9:.0f} TF/s   rel(q64, product) {rel(o1, o0)}", flush=True)
+
+
 def sec_gemm2cta():
     """EXPERIMENTAL SM-pair GEMM against the product GEMM and cuBLAS on the DiT shapes (run with a short timeout)."""
     L, C, F = 18480, 3072, 14336
@@ -295,9 +309,9 @@ def sec_atttrace():
     print("raw rows 0..2:", (t[:3] - base).tolist())
 
 
-SECTIONS = {"gemm2cta": sec_gemm2cta, "attsplit": sec_attsplit, "atttrace": sec_atttrace, "atttune": sec_atttune, "probe": sec_probe, "gemm": sec_gemm, "attention": sec_attention, "elementwise": sec_elementwise}
+SECTIONS = {"att64": sec_att64, "gemm2cta": sec_gemm2cta, "attsplit": sec_attsplit, "atttrace": sec_atttrace, "atttune": sec_atttune, "probe": sec_probe, "gemm": sec_gemm, "attention": sec_attention, "elementwise": sec_elementwise}
 if __name__ == "__main__":
-    names = sys.argv[1:] or [n for n in SECTIONS if n != "gemm2cta"]   # experimental sections only on request
+    names = sys.argv[1:] or [n for n in SECTIONS if n not in ("gemm2cta", "att64")]   # experimental sections only on request
     print(torch.cuda.get_device_name(0))
     for n in names:
         print(f"===== {n} =====", flush=True)

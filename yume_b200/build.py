@@ -15,7 +15,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIB = CSRC / "libyume_b200.so"
-SOURCES = ["gemm.cu", "attention.cu", "elementwise.cu", "vae_elementwise.cu", "probe.cu", "gemm2cta.cu"]
+SOURCES = ["gemm.cu", "attention.cu", "elementwise.cu", "vae_elementwise.cu", "probe.cu", "gemm2cta.cu", "attention64.cu"]
 HEADERS = ["yb_ptx.cuh", "yb_host.h", "../../include/yume_b200.h"]
 
 NVCC_FLAGS = [

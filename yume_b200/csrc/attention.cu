@@ -569,6 +569,11 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, cons
 extern "C" int yb_attention_ex(const void* q, long long ldq, const void* k, long long ldk, const void* v,
                                long long ldv, void* out, long long ldo, int Lq, int Lk, int heads, float scale,
                                int flags, void* trace, void* stream_);
+namespace yb {  // attention64.cu (EXPERIMENTAL variant, reached only through the YB_ATT_Q64 flag)
+int attention64_launch(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
+                       long long ldo, int Lq, int Lk, int heads, float scale, int flags, void* const* out_peers, int world,
+                       int rank, int Lp, cudaStream_t stream);
+}
 
 extern "C" int yb_attention_plan(int Lq, int Lk, int heads, int sms, int flags, int* out4) {
   if (Lq <= 0 || Lk <= 0 || heads <= 0 || sms <= 0 || !out4) return YB_ERR_ARG;
@@ -597,6 +602,9 @@ extern "C" int yb_attention_ex(const void* q, long long ldq, const void* k, long
   if (!q || !k || !v || !out) return YB_ERR_ARG;
   if (Lq <= 0 || Lk <= 0 || heads <= 0) return YB_ERR_ARG;
   if ((ldo % 8) != 0 || (reinterpret_cast<uintptr_t>(out) & 0xF)) return YB_ERR_ALIGNMENT;
+  if (flags & YB_ATT_Q64)   // EXPERIMENTAL variant (attention64.cu): never set by the product path
+    return attention64_launch(q, ldq, k, ldk, v, ldv, out, ldo, Lq, Lk, heads, scale, flags, nullptr, 1, 0, 0,
+                              reinterpret_cast<cudaStream_t>(stream_));
   CUtensorMap tmQ, tmK, tmV;
   const uint64_t cols = static_cast<uint64_t>(heads) * 128;
   int rc = make_tmap_bf16_2d(&tmQ, q, Lq, cols, ldq, 128, 64);

@@ -156,7 +156,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
               scale: Optional[float] = None, variant: int = 0, accumulate: bool = False, emu: int = 0,
               split: int = 0) -> torch.Tensor:
     """softmax(q k^T * scale) v, non-causal. q [Lq, heads*128], k/v [Lk, heads*128] bf16 (row strides arbitrary).
-    split: KV split policy (YB_ATT_SPLIT_SHIFT): 0 automatic tail split, 1 never, 2..4 force that many KV segments."""
+    split: KV split policy (YB_ATT_SPLIT_SHIFT): 0 automatic tail split, 1 never, 2..4 force that many KV segments.
+    variant: 0 product kernel (P in TMEM), 1 debug (P through smem), 2 EXPERIMENTAL Q-in-TMEM / 64-key tiles (attention64.cu)."""
     global _launches
     for n, t in (("q", q), ("k", k), ("v", v), ("out", out)):
         _need(t, torch.bfloat16, n)
@@ -167,7 +168,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
         scale = 1.0 / math.sqrt(128.0)
     check(_lib.load().yb_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
                                    out.data_ptr(), out.stride(0), Lq, Lk, heads, scale,
-                                   (YB_ATT_P_SMEM if variant == 1 else 0) | (YB_ATT_ACCUMULATE if accumulate else 0)
+                                   (YB_ATT_P_SMEM if variant == 1 else 0) | (128 if variant == 2 else 0)  # 128 = YB_ATT_Q64 (experimental)
+                                   | (YB_ATT_ACCUMULATE if accumulate else 0)
                                    | ((emu & 3) << 2) | ((split & 7) << 4),
                                    _stream()),
           "yb_attention")
