@@ -110,7 +110,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++local) {
         const int acc = local & 1;
-        mbar_wait(&tmem_empty[acc], ((local >> 1) & 1) ^ 1);
+        mbar_wait_cluster(&tmem_empty[acc], ((local >> 1) & 1) ^ 1);   // arrivals come from both CTAs
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * G2_BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {

@@ -378,6 +378,22 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
                "h"(static_cast<uint16_t>(3))
                : "memory");
 }
+// bounded wait with cluster-scope acquire: for barriers that receive arrivals from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > YB_WAIT_LIMIT_CYCLES) __trap();
+  }
+}
 // plain arrive on the LEADER CTA's copy of a barrier, from either CTA of the pair
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
