@@ -142,6 +142,8 @@ def test_experimental_attention_q64_matches_fp32_reference(dev, Lq, Lk, heads, e
     assert rel(out, ref.transpose(0, 1).reshape(Lq, heads * 128)) < KERNEL_TOL
     acc = ops.attention(q, k, v, out.clone(), heads, variant=2, accumulate=True)     # out += result
     assert rel(acc, 2 * ref.transpose(0, 1).reshape(Lq, heads * 128)) < 2 * KERNEL_TOL
+    spl = ops.attention(q, k, v, torch.full_like(q, 3.0), heads, variant=2, emu=emu, split=2)   # forced KV split (64-key tiles)
+    assert rel(spl, ref.transpose(0, 1).reshape(Lq, heads * 128)) < KERNEL_TOL
 
 
 @pytest.mark.parametrize("split", [2, 3, 4])

@@ -13,7 +13,7 @@
 // Shared memory holds only the K/V ring (Q is read once from global memory by the thread that owns the row).
 //
 // Same contract as attention.cu (non-causal, keys >= Lk dropped, bf16 in, fp32 accumulate, [L, heads, 128] output,
-// YB_ATT_ACCUMULATE, Ulysses peer scatter); no tail split and no trace in this variant.
+// YB_ATT_ACCUMULATE, Ulysses peer scatter, automatic tail split with the same planner); no trace in this variant.
 #include "yb_host.h"
 #include "yb_ptx.cuh"
 
@@ -35,6 +35,11 @@ struct Att64Params {
   __nv_bfloat16* out_peers[8];
   int sp_world, sp_rank, sp_Lp;
   float scale_log2;
+  // tail split (same decomposition as attention.cu): unit u = head * nq + q_block; CTAs [0, full_units) run whole units,
+  // CTA full_units + r runs KV segment r % ns of unit full_units + r / ns and leaves a partial result in the workspace
+  int nq, full_units, ns;
+  float* ws_o;    // [tail CTAs, 256, 128] unnormalised O
+  float* ws_ml;   // [tail CTAs, 256, 2]   (row max in the log2 domain, row sum)
 };
 
 template <int EMU>
@@ -52,9 +57,22 @@ attention64_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int q0 = blockIdx.x * 256;
-  const int nkv = p.nkv;
+  // every role decodes the work unit INSIDE its own branch from an opaque copy of blockIdx.x (nothing stays live across
+  // the register-starved softmax loop); kv_begin is even so barrier parities can follow the global tile index
+  auto decode = [&](int& unit, int& kv_begin, int& nkv) {
+    int bx = blockIdx.x;
+    asm volatile("" : "+r"(bx));
+    unit = bx;
+    kv_begin = 0;
+    nkv = p.nkv;
+    if (bx >= p.full_units) {
+      const int r = bx - p.full_units;
+      unit = p.full_units + r / p.ns;
+      const int per = (((p.nkv + p.ns - 1) / p.ns) + 1) & ~1;
+      kv_begin = (r % p.ns) * per;
+      nkv = min(per, p.nkv - kv_begin);
+    }
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmK);
@@ -84,6 +102,9 @@ attention64_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     setmaxnreg_dec<80>();
     if (warp == 0 && lane == 0) {
       // ------------------------------- TMA producer: K_0, V_0, K_1, V_1, ... -------------------------------
+      int unit, kv_begin, nkv;
+      decode(unit, kv_begin, nkv);
+      const int head = unit / p.nq;
       for (int it = 0; it < 2 * nkv; ++it) {
         const int slot = it % A64_NS;
         const uint32_t ph = (it / A64_NS) & 1;
@@ -91,12 +112,14 @@ attention64_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
         mbar_arrive_expect_tx(&kv_full[slot], A64_TILE_BYTES);
         const CUtensorMap* tm = (it & 1) ? &tmV : &tmK;
         uint8_t* dst = smem + slot * A64_TILE_BYTES;
-        const int j = it >> 1;
+        const int j = kv_begin + (it >> 1);
         tma_load_2d(dst, tm, &kv_full[slot], head * 128, j * 64);
         tma_load_2d(dst + 8192, tm, &kv_full[slot], head * 128 + 64, j * 64);
       }
     } else if (warp == 1 && lane == 0) {
       // ------------------------------- MMA issuer -------------------------------
+      int unit, kv_begin, nkv;
+      decode(unit, kv_begin, nkv);
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);     // S[128 q, 64 keys] = Q (TMEM) x K^T (K-major smem)
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);   // O[128 q, 128 d] += P (TMEM) x V (MN-major smem)
       const uint32_t sKV = smem_u32(smem);
@@ -161,7 +184,14 @@ attention64_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     const uint32_t tQ = tmem_base + lane_off + 128 + X * 64;
     const uint32_t tO = tmem_base + lane_off + 256 + X * 128;
     const float sc = p.scale_log2;
-    const int q_row = q0 + X * 128 + row_in_tile;
+    int head, q_row, kv_begin, kv_end;
+    {
+      int unit, nkv;
+      decode(unit, kv_begin, nkv);
+      kv_end = kv_begin + nkv;
+      head = unit / p.nq;
+      q_row = (unit - head * p.nq) * 256 + X * 128 + row_in_tile;
+    }
 
     {  // Q row -> TMEM: column c of lane m holds (Q[m][2c], Q[m][2c+1]) packed lo/hi (the layout probe mode 2 verifies)
       const uint4* src = reinterpret_cast<const uint4*>(p.q + static_cast<long long>(q_row) * p.ldq + head * 128);
@@ -182,7 +212,7 @@ attention64_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 
     float m_used = -INFINITY;
     float l = 0.f;
-    for (int j = 0; j < nkv; ++j) {
+    for (int j = kv_begin; j < kv_end; ++j) {   // global key-tile index (kv_begin even: parity of j == local parity)
       mbar_wait(&s_full[X], j & 1);
       tc_fence_after();
       const int kv_rem = p.Lk - j * 64;
@@ -213,7 +243,7 @@ attention64_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
                              fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
       const float ms = mx * sc;
-      if (j == 0) {
+      if (j == kv_begin) {
         m_used = ms;
       } else {
         const bool need = ms > m_used + 8.0f;   // lazy rescale: only when a row max grew by more than 2^8
@@ -273,6 +303,21 @@ attention64_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     // epilogue: O / l -> bf16 -> global [Lq, heads*128] (or the owner rank's receive buffer)
     mbar_wait(&o_done[X], 0);
     tc_fence_after();
+    if (static_cast<int>(blockIdx.x) >= p.full_units) {
+      // KV segment of a tail unit: leave (O, m, l) for attention64_combine_kernel
+      const long long prow = static_cast<long long>(blockIdx.x - p.full_units) * 256 + X * 128 + row_in_tile;
+      float* wo = p.ws_o + prow * 128;
+      *reinterpret_cast<float2*>(p.ws_ml + prow * 2) = make_float2(m_used, l);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tO + c * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<uint4*>(wo + c * 32 + 4 * i) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+      }
+    } else {
     const float inv = 1.0f / l;
     __nv_bfloat16* orow = p.out + static_cast<long long>(q_row) * p.ldo + head * 128;
     if (p.sp_world > 1) {
@@ -312,6 +357,7 @@ attention64_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
         }
       }
     }
+    }  // whole unit
   }
 
   tc_fence_before();
@@ -322,8 +368,65 @@ attention64_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   }
 }
 
+// merge of the KV-segment partials of the tail units + the normal epilogue (same math as attention_combine_kernel)
+__global__ void __launch_bounds__(256) attention64_combine_kernel(const Att64Params p, int tail_units) {
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gw >= tail_units * 256) return;
+  const int tu = gw >> 8, r = gw & 255;
+  const int unit = p.full_units + tu;
+  const int head = unit / p.nq;
+  const int q_row = (unit - head * p.nq) * 256 + r;
+  if (q_row >= p.Lq) return;
+  float M = -INFINITY;
+  for (int sgm = 0; sgm < p.ns; ++sgm) M = fmaxf(M, p.ws_ml[((static_cast<long long>(tu) * p.ns + sgm) * 256 + r) * 2]);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float lsum = 0.f;
+  for (int sgm = 0; sgm < p.ns; ++sgm) {
+    const long long prow = (static_cast<long long>(tu) * p.ns + sgm) * 256 + r;
+    const float2 ml = *reinterpret_cast<const float2*>(p.ws_ml + prow * 2);
+    const float w = exp2f(ml.x - M);
+    const float4 o = *reinterpret_cast<const float4*>(p.ws_o + prow * 128 + lane * 4);
+    acc.x += o.x * w; acc.y += o.y * w; acc.z += o.z * w; acc.w += o.w * w;
+    lsum += ml.y * w;
+  }
+  const float inv = 1.0f / lsum;
+  __nv_bfloat16* orow = p.out + static_cast<long long>(q_row) * p.ldo + head * 128;
+  if (p.sp_world > 1) {
+    const int owner = q_row / p.sp_Lp;
+    const int t = q_row - owner * p.sp_Lp;
+    if (owner < p.sp_world)
+      orow = p.out_peers[owner] + (static_cast<long long>(p.sp_rank) * p.sp_Lp + t) * p.ldo + head * 128;
+  }
+  *reinterpret_cast<uint2*>(orow + lane * 4) = make_uint2(pack_bf16x2(acc.x * inv, acc.y * inv), pack_bf16x2(acc.z * inv, acc.w * inv));
+}
+
+static int split_workspace64(size_t ctas, float** ws_o, float** ws_ml, cudaStream_t stream) {
+  static float* buf[16] = {nullptr};
+  static size_t cap[16] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return YB_ERR_LAUNCH;
+  const size_t need = ctas * 256 * 130 * sizeof(float);
+  if (cap[dev] < need) {
+    if (buf[dev]) {
+      cudaStreamSynchronize(stream);
+      cudaFree(buf[dev]);
+      buf[dev] = nullptr;
+      cap[dev] = 0;
+    }
+    if (cudaMalloc(&buf[dev], need) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return YB_ERR_LAUNCH;
+    }
+    cap[dev] = need;
+  }
+  *ws_o = buf[dev];
+  *ws_ml = buf[dev] + ctas * 256 * 128;
+  return YB_OK;
+}
+
 template <int EMU>
-static int launch64(const CUtensorMap& tmK, const CUtensorMap& tmV, const Att64Params& p, int heads, cudaStream_t stream) {
+static int launch64(const CUtensorMap& tmK, const CUtensorMap& tmV, Att64Params p, int heads, int flags, cudaStream_t stream) {
   auto kern = attention64_kernel<EMU>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -333,9 +436,24 @@ static int launch64(const CUtensorMap& tmK, const CUtensorMap& tmV, const Att64P
     }
     attr_set = true;
   }
-  dim3 grid((p.Lq + 255) / 256, heads);
-  kern<<<grid, A64_THREADS, A64_SMEM_BYTES, stream>>>(tmK, tmV, p);
-  return check_launch("attention64");
+  // same planner as the product kernel (yb_attention_plan counts 128-key tiles: hand it an Lk with the same tile count)
+  int plan[4];
+  int prc = yb_attention_plan(p.Lq, p.nkv * 128, heads, sm_count(), flags & ~YB_ATT_Q64, plan);
+  if (prc) return prc;
+  p.nq = (p.Lq + 255) / 256;
+  p.full_units = plan[0];
+  p.ns = plan[2];
+  p.ws_o = p.ws_ml = nullptr;
+  const int tail = plan[1];
+  if (tail > 0) {
+    prc = split_workspace64(static_cast<size_t>(tail) * p.ns, &p.ws_o, &p.ws_ml, stream);
+    if (prc) return prc;
+  }
+  kern<<<p.full_units + tail * p.ns, A64_THREADS, A64_SMEM_BYTES, stream>>>(tmK, tmV, p);
+  int rc = check_launch("attention64");
+  if (rc || tail == 0) return rc;
+  attention64_combine_kernel<<<tail * 32, 256, 0, stream>>>(p, tail);
+  return check_launch("attention64_combine");
 }
 
 // Called by yb_attention_ex when YB_ATT_Q64 is set (attention.cu). out_peers / world / rank / Lp as for yb_attention_sp
@@ -365,10 +483,10 @@ int attention64_launch(const void* q, long long ldq, const void* k, long long ld
   p.sp_Lp = Lp;
   for (int i = 0; i < 8; ++i) p.out_peers[i] = (out_peers && i < world) ? static_cast<__nv_bfloat16*>(out_peers[i]) : nullptr;
   switch ((flags >> 2) & 3) {
-    case 1: return launch64<4>(tmK, tmV, p, heads, stream);
-    case 2: return launch64<3>(tmK, tmV, p, heads, stream);
-    case 3: return launch64<2>(tmK, tmV, p, heads, stream);
-    default: return launch64<0>(tmK, tmV, p, heads, stream);
+    case 1: return launch64<4>(tmK, tmV, p, heads, flags, stream);
+    case 2: return launch64<3>(tmK, tmV, p, heads, flags, stream);
+    case 3: return launch64<2>(tmK, tmV, p, heads, flags, stream);
+    default: return launch64<0>(tmK, tmV, p, heads, flags, stream);
   }
 }
 
