@@ -569,7 +569,11 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, cons
 extern "C" int yb_attention_ex(const void* q, long long ldq, const void* k, long long ldk, const void* v,
                                long long ldv, void* out, long long ldo, int Lq, int Lk, int heads, float scale,
                                int flags, void* trace, void* stream_);
-namespace yb {  // attention64.cu (EXPERIMENTAL variant, reached only through the YB_ATT_Q64 flag)
+static bool env_q64() {
+  const char* e = getenv("YB_ATT_Q64");
+  return e != nullptr && e[0] == '1';
+}
+namespace yb {  // attention64.cu (EXPERIMENTAL variant, reached only through the YB_ATT_Q64 flag / environment variable)
 int attention64_launch(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                        long long ldo, int Lq, int Lk, int heads, float scale, int flags, void* const* out_peers, int world,
                        int rank, int Lp, cudaStream_t stream);
@@ -602,7 +606,9 @@ extern "C" int yb_attention_ex(const void* q, long long ldq, const void* k, long
   if (!q || !k || !v || !out) return YB_ERR_ARG;
   if (Lq <= 0 || Lk <= 0 || heads <= 0) return YB_ERR_ARG;
   if ((ldo % 8) != 0 || (reinterpret_cast<uintptr_t>(out) & 0xF)) return YB_ERR_ALIGNMENT;
-  if (flags & YB_ATT_Q64)   // EXPERIMENTAL variant (attention64.cu): never set by the product path
+  // EXPERIMENTAL variant (attention64.cu): never selected by the product path; YB_ATT_Q64=1 in the environment routes every
+  // call through it so that the whole test-suite / bench can be pointed at it without code changes
+  if ((flags & YB_ATT_Q64) || (env_q64() && trace == nullptr && !(flags & YB_ATT_P_SMEM)))
     return attention64_launch(q, ldq, k, ldk, v, ldv, out, ldo, Lq, Lk, heads, scale, flags, nullptr, 1, 0, 0,
                               reinterpret_cast<cudaStream_t>(stream_));
   CUtensorMap tmQ, tmK, tmV;
@@ -645,6 +651,9 @@ extern "C" int yb_attention_sp(const void* q, long long ldq, const void* k, long
   using namespace yb;
   if (!q || !k || !v || !out_peers || world < 2 || world > 8 || rank < 0 || rank >= world || Lp <= 0) return YB_ERR_ARG;
   if (Lq != world * Lp || Lk <= 0 || Lk > Lq || heads <= 0 || (ldo % 8)) return YB_ERR_ARG;
+  if (env_q64())   // EXPERIMENTAL (see yb_attention_ex)
+    return attention64_launch(q, ldq, k, ldk, v, ldv, out_peers[rank], ldo, Lq, Lk, heads, scale, 0, out_peers, world, rank, Lp,
+                              reinterpret_cast<cudaStream_t>(stream_));
   CUtensorMap tmQ, tmK, tmV;
   const uint64_t cols = static_cast<uint64_t>(heads) * 128;
   int rc = make_tmap_bf16_2d(&tmQ, q, Lq, cols, ldq, 128, 64);
