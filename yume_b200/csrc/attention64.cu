@@ -42,7 +42,9 @@ struct Att64Params {
   float* ws_ml;   // [tail CTAs, 256, 2]   (row max in the log2 domain, row sum)
 };
 
-template <int EMU>
+// HALVES: P is handed to the MMA in two 32-key halves (tcgen05.st x16 + two barriers per tile) so that P.V of the first half
+// overlaps the second half of the exponentials. Off in the first validation pass (YB_ATT64_HALVES=1 turns it on).
+template <int EMU, bool HALVES>
 __global__ void __launch_bounds__(A64_THREADS, 1)
 attention64_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const Att64Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -51,8 +53,8 @@ attention64_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   uint64_t* kv_full = q_ready + 2;
   uint64_t* kv_empty = kv_full + A64_NS;
   uint64_t* s_full = kv_empty + A64_NS;
-  uint64_t* p_ready = s_full + 2;                                        // [X]: P_X of the current key tile is in TMEM
-  uint64_t* o_done = p_ready + 2;
+  uint64_t* p_ready = s_full + 2;                                        // [X][half]: P_X (or its 32-key half) is in TMEM
+  uint64_t* o_done = p_ready + 4;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -84,7 +86,8 @@ attention64_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_ready[i], 128);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 128);
+      mbar_init(&p_ready[2 * i], 128);
+      mbar_init(&p_ready[2 * i + 1], 128);
       mbar_init(&o_done[i], 1);
     }
     fence_barrier_init();
@@ -133,9 +136,9 @@ attention64_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
                   kk != 0 ? 1u : 0u);
         }
       };
-      auto issue_PV = [&](int X, uint32_t vbase, bool acc) {
+      auto issue_PV = [&](int X, uint32_t vbase, bool acc, int k0, int k1) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)     // 16 keys per MMA: 8 TMEM columns of packed P, 16 rows (2048 B) of the V tile
+        for (int kk = k0; kk < k1; ++kk)   // 16 keys per MMA: 8 TMEM columns of packed P, 16 rows (2048 B) of the V tile
           umma_ts(tmem_base + 256 + X * 128, tmem_base + X * 64 + kk * 8, vdesc0 + ((vbase + kk * 2048) >> 4), idesc_pv,
                   (acc || kk != 0) ? 1u : 0u);
       };
@@ -159,9 +162,16 @@ attention64_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
         const uint32_t kbase = sKV + slot_k * A64_TILE_BYTES;
 #pragma unroll
         for (int X = 0; X < 2; ++X) {
-          mbar_wait(&p_ready[X], j & 1);
+          mbar_wait(&p_ready[2 * X], j & 1);
           tc_fence_after();
-          issue_PV(X, vbase, j > 0);
+          if (HALVES) {
+            issue_PV(X, vbase, j > 0, 0, 2);          // keys 0..31 while the softmax warps finish 32..63
+            mbar_wait(&p_ready[2 * X + 1], j & 1);
+            tc_fence_after();
+            issue_PV(X, vbase, true, 2, 4);
+          } else {
+            issue_PV(X, vbase, j > 0, 0, 4);
+          }
           if (has_next) {
             issue_S(X, kbase);          // overwrites S_X / P_X: ordered behind PV_X(j) on the in-order tensor pipe
             umma_commit(&s_full[X]);
@@ -287,11 +297,30 @@ attention64_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
         }
         ls2[i & 1] = f2_add(ls2[i & 1], p2);
         pk[i] = pack_bf16x2(p0, p1);
+        if (HALVES && i == 15) {   // keys 0..31 are ready: 16 packed columns
+          uint32_t h0[16];
+#pragma unroll
+          for (int t = 0; t < 16; ++t) h0[t] = pk[t];
+          tmem_st16(tS, h0);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&p_ready[2 * X]);
+        }
       }
-      tmem_st32(tS, pk);     // P_X: 64 keys = 32 packed columns over the first half of S_X
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_ready[X]);
+      if (HALVES) {
+        uint32_t h1[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) h1[t] = pk[16 + t];
+        tmem_st16(tS + 16, h1);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_ready[2 * X + 1]);
+      } else {
+        tmem_st32(tS, pk);     // P_X: 64 keys = 32 packed columns over the first half of S_X
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_ready[2 * X]);
+      }
       {
         float a0, a1, b0, b1;
         f2_unpack(ls2[0], a0, a1);
@@ -425,9 +454,9 @@ static int split_workspace64(size_t ctas, float** ws_o, float** ws_ml, cudaStrea
   return YB_OK;
 }
 
-template <int EMU>
+template <int EMU, bool HALVES>
 static int launch64(const CUtensorMap& tmK, const CUtensorMap& tmV, Att64Params p, int heads, int flags, cudaStream_t stream) {
-  auto kern = attention64_kernel<EMU>;
+  auto kern = attention64_kernel<EMU, HALVES>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A64_SMEM_BYTES) != cudaSuccess) {
@@ -482,11 +511,20 @@ int attention64_launch(const void* q, long long ldq, const void* k, long long ld
   p.sp_rank = rank;
   p.sp_Lp = Lp;
   for (int i = 0; i < 8; ++i) p.out_peers[i] = (out_peers && i < world) ? static_cast<__nv_bfloat16*>(out_peers[i]) : nullptr;
+  const char* hv = getenv("YB_ATT64_HALVES");
+  if (hv != nullptr && hv[0] == '1') {
+    switch ((flags >> 2) & 3) {
+      case 1: return launch64<4, true>(tmK, tmV, p, heads, flags, stream);
+      case 2: return launch64<3, true>(tmK, tmV, p, heads, flags, stream);
+      case 3: return launch64<2, true>(tmK, tmV, p, heads, flags, stream);
+      default: return launch64<0, true>(tmK, tmV, p, heads, flags, stream);
+    }
+  }
   switch ((flags >> 2) & 3) {
-    case 1: return launch64<4>(tmK, tmV, p, heads, flags, stream);
-    case 2: return launch64<3>(tmK, tmV, p, heads, flags, stream);
-    case 3: return launch64<2>(tmK, tmV, p, heads, flags, stream);
-    default: return launch64<0>(tmK, tmV, p, heads, flags, stream);
+    case 1: return launch64<4, false>(tmK, tmV, p, heads, flags, stream);
+    case 2: return launch64<3, false>(tmK, tmV, p, heads, flags, stream);
+    case 3: return launch64<2, false>(tmK, tmV, p, heads, flags, stream);
+    default: return launch64<0, false>(tmK, tmV, p, heads, flags, stream);
   }
 }
 
