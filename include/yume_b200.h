@@ -129,6 +129,12 @@ int yb_rmsnorm_rope(void* qk, long long ld, const void* weight, const void* rope
 int yb_rmsnorm_rope_pieces(void* qk, long long ld, int piece_cols, long long piece_stride, const void* weight,
                            const void* rope, int rope_len, int L, int C, int D, float eps, void* stream);
 
+/* q AND k of the same token rows in ONE launch (WanSelfAttention runs norm_q(q), norm_k(k) and rope_apply on both with the
+ * same per-token angles, wan23/modules/model.py:190-200): q, k point at the first element of the two [L, C] row sets (same
+ * row stride ld, same piece layout as yb_rmsnorm_rope_pieces; piece_cols = C, piece_stride = 0 for plain rows). */
+int yb_qk_norm_rope(void* q, void* k, long long ld, int piece_cols, long long piece_stride, const void* wq, const void* wk,
+                    const void* rope, int rope_len, int L, int C, int D, float eps, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Non-causal softmax(Q K^T * scale) V, head_dim 128, bf16 in / bf16 out, fp32 softmax + accumulate.
  * Replaces flash_attention(q, k, v, k_lens=...) (wan23/modules/attention.py:24-130) for B == 1.

@@ -23,6 +23,11 @@ CFG_5B_TINY = dict(variant="5b", dim=256, ffn_dim=512, num_heads=2, num_layers=2
                    text_len=32, text_dim=64, freq_dim=256, clip_dim=1280)
 CFG_14B_TINY = dict(variant="14b", dim=256, ffn_dim=512, num_heads=2, num_layers=2, in_dim=36, out_dim=16,
                     text_len=32, text_dim=64, freq_dim=256, clip_dim=96)
+# 8-head geometries (dim 1024): the smallest models whose heads divide over 2, 4 AND 8 Ulysses ranks
+CFG_5B_H8 = dict(variant="5b", dim=1024, ffn_dim=2048, num_heads=8, num_layers=2, in_dim=48, out_dim=48,
+                 text_len=32, text_dim=64, freq_dim=256, clip_dim=1280)
+CFG_14B_H8 = dict(variant="14b", dim=1024, ffn_dim=2048, num_heads=8, num_layers=2, in_dim=36, out_dim=16,
+                  text_len=32, text_dim=64, freq_dim=256, clip_dim=96)
 
 
 def oracle_kwargs(cfg: dict) -> dict:

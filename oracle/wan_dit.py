@@ -90,8 +90,8 @@ def flash_attention(q: Tensor, k: Tensor, v: Tensor, k_lens: Optional[Sequence[i
     b, lq, lk = q.shape[0], q.shape[1], k.shape[1]
     qh, kh, vh = (t.to(torch.bfloat16).transpose(1, 2) for t in (q, k, v))
     mask = None
-    if k_lens is not None:
-        mask = torch.zeros(b, 1, 1, lk, dtype=torch.bool)
+    if k_lens is not None and any(int(n) < lk for n in k_lens):   # (all keys valid: no mask, like the varlen kernel)
+        mask = torch.zeros(b, 1, 1, lk, dtype=torch.bool, device=q.device)
         for i, n in enumerate(k_lens):
             mask[i, ..., :int(n)] = True
     o = F.scaled_dot_product_attention(qh, kh, vh, attn_mask=mask)
@@ -136,8 +136,10 @@ class WanOracle:
         return F.conv3d(u, w, self.sd.get(name + ".bias"), stride=w.shape[2:])
 
     # ---- attention -----------------------------------------------------------------------------------------
-    def self_attn(self, p: str, x: Tensor, freqs_tok: Tensor) -> Tensor:
-        """WanSelfAttention.forward, model.py:178-207 (k_lens == L on every Yume path, :851)."""
+    def self_attn(self, p: str, x: Tensor, freqs_tok: Tensor, k_len: Optional[int] = None) -> Tensor:
+        """WanSelfAttention.forward, model.py:178-207. k_lens: the 5B tree overrides seq_lens with x.shape[1] (:846-851)
+        so every row is a key; the 14B tree passes the ACTUAL token count (wan/modules/model.py:311-314, 916) so the
+        zero-padded rows of a regular-grid input with seq_len > F*H*W are masked (k_len)."""
         b, s, n, d = x.shape[0], x.shape[1], self.num_heads, self.d
         q = rms_norm(self._lin(p + ".q", x), self.sd[p + ".norm_q.weight"], self.eps).view(b, s, n, d)
         k = rms_norm(self._lin(p + ".k", x), self.sd[p + ".norm_k.weight"], self.eps).view(b, s, n, d)
@@ -146,7 +148,7 @@ class WanOracle:
         k = torch.stack([rope_apply(k[i], freqs_tok) for i in range(b)])
         if p.startswith("blocks.0."):
             self.trace["q_rope"], self.trace["k_rope"], self.trace["v"] = q, k, v
-        o = flash_attention(q, k, v, k_lens=[s] * b)
+        o = flash_attention(q, k, v, k_lens=[s if k_len is None else k_len] * b)
         if p.startswith("blocks.0."):
             self.trace["attn_out"] = o
         return self._lin(p + ".o", o.flatten(2))
@@ -170,7 +172,7 @@ class WanOracle:
         return self._lin(p + ".o", o)
 
     # ---- block ---------------------------------------------------------------------------------------------
-    def block(self, i: int, x: Tensor, e0: Tensor, freqs_tok: Tensor, context: Tensor) -> Tensor:
+    def block(self, i: int, x: Tensor, e0: Tensor, freqs_tok: Tensor, context: Tensor, k_len: Optional[int] = None) -> Tensor:
         """WanAttentionBlock.forward: 5B model.py:272-316 (e0 [B,L,6,C]); 14B wan/modules/model.py:444-496
         (e0 [B,6,C])."""
         p = f"blocks.{i}"
@@ -182,7 +184,7 @@ class WanOracle:
         h = layer_norm(x, self.eps).float() * (1 + e[1]) + e[0]
         if i == 0:
             self.trace["h_norm1"] = h
-        y = self.self_attn(p + ".self_attn", h, freqs_tok)
+        y = self.self_attn(p + ".self_attn", h, freqs_tok, k_len)
         x = x + y * e[2]
         xn = layer_norm(x, self.eps, self.sd[p + ".norm3.weight"], self.sd[p + ".norm3.bias"])
         x = x + self.cross_attn(p + ".cross_attn", xn, context)
@@ -310,6 +312,7 @@ class WanOracle:
         else:
             packed = bool(flag)
 
+        k_len = None
         if packed:
             tok, freqs_tok, seq_lens1, grid = self.pack(x[0].float(), latent_frame_zero)
             L = tok.shape[1]
@@ -325,6 +328,8 @@ class WanOracle:
             L = tok.shape[1]
             freqs_tok = grid_freqs(self.tables, *grid)
             seq_lens1 = 0
+            if self.variant == "14b":   # seq_lens = real token count -> k_lens (wan/modules/model.py:916, 311-314)
+                k_len = math.prod(grid)
             if self.variant == "5b":
                 t_tok = (t.expand(t.size(0), seq_len) if t.dim() == 1 else t).flatten()  # model.py:803-804
 
@@ -344,7 +349,7 @@ class WanOracle:
 
         xs = tok
         for i in range(self.num_layers):
-            xs = self.block(i, xs, e0, freqs_tok, ctx)
+            xs = self.block(i, xs, e0, freqs_tok, ctx, k_len)
         out = self.head(xs, e)
         self.trace["head_out"] = out
         return self.unpatchify(out[0, seq_lens1:], grid).float()

@@ -5,7 +5,7 @@ Tolerances (bf16 path vs fp32-weight oracle, SURVEY.md §8c / BASELINE.md §3):
   * index / gather ops (patchify, unpatchify): bit-exact
   * single kernels vs an fp32 torch reference: bf16 output rounding, rel-Frobenius <= 4e-3
   * one WanAttentionBlock (delta y - x): rel-Frobenius <= 1e-2, max-abs <= 3e-2 on unit-variance inputs
-  * whole tiny model output: rel-Frobenius <= 1.5e-2
+  * whole tiny model output: rel-Frobenius <= 5e-3 (measured ~2e-3)
 """
 import math
 import os
@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 
 KERNEL_TOL = 4e-3
 BLOCK_TOL_REL, BLOCK_TOL_ABS = 1e-2, 3e-2
-MODEL_TOL = 1.5e-2
+MODEL_TOL = 5e-3     # measured ~2e-3 on every golden case (round 1); a 2.5x regression fails
 
 
 @pytest.fixture(scope="module")
@@ -340,6 +340,26 @@ def test_14b_forward_vs_reference_golden(tiny14, case):
     assert rel(out, c["out"]) < MODEL_TOL
 
 
+@pytest.mark.parametrize("fname,case", [("wan23_h8.pt", "5b_grid"), ("wan23_h8.pt", "5b_grid_padded"), ("wan23_h8.pt", "5b_pack_h10"),
+                                        ("wan23_h8.pt", "5b_pack_h30"), ("wan21_h8.pt", "14b_grid"),
+                                        ("wan21_h8.pt", "14b_grid_padded"), ("wan21_h8.pt", "14b_pack_lfz8")])
+def test_h8_forward_vs_reference_golden(dev, golden_dir, fname, case):
+    """8-head (dim 1024) models: the goldens the Ulysses parity at world 2/4/8 uses, on one GPU. 14b_grid_padded has
+    seq_len > F*H*W: the 14B tree masks the padded rows as keys (wan/modules/model.py:311-314), the 5B tree does not."""
+    g = torch.load(golden_dir / fname, weights_only=False)
+    cfg, c = g["cfg"], g["cases"][case]
+    eng = _engine(cfg, synth.make_state_dict(cfg, g["seed_w"]), dev)
+    inp = synth.make_inputs(cfg, c["seed"], c["frames"], c["H"], c["W"], c["ctx_len"])
+    if cfg["variant"] == "5b":
+        out = eng.forward(inp["x"], torch.tensor(c["t"]), inp["context"], c["seq_len"], latent_frame_zero=c["lfz"],
+                          packed=c["flag"])
+    else:
+        out = eng.forward(inp["x"], torch.tensor(c["t"]), inp["context"], c["seq_len"], y=inp["y"], clip_fea=inp["clip_fea"],
+                          latent_frame_zero=c["lfz"], packed=c["rand_num_img"] >= 0.4)
+    assert out.shape == c["out"].shape
+    assert rel(out, c["out"]) < MODEL_TOL
+
+
 def test_mirror_module_keeps_reference_signature(tiny5, dev):
     """WanModel5B built on the meta device + install(state_dict): forward(x list, t, context list, seq_len, ...)."""
     from yume_b200.model import WanModel5B
@@ -368,6 +388,25 @@ def test_oracle_block_at_real_width(dev):
     x = torch.randn(1, L, C, generator=gen)
     e = 0.5 * torch.randn(1, L, 6, C, generator=gen)
     ctx = torch.randn(1, 64, C, generator=gen).bfloat16().float()
+    m = WanOracle(sd, **synth.oracle_kwargs(cfg))
+    want = m.block(0, x, e, grid_freqs(m.tables, 4, 8, 8), ctx)[0]
+    got = eng.block_forward(0, x[0], e[0], (4, 8, 8), ctx[0]).cpu()
+    d_ref, d = want - x[0], got - x[0]
+    assert float((d - d_ref).norm() / d_ref.norm()) < BLOCK_TOL_REL
+    assert float((got - want).abs().max()) < BLOCK_TOL_ABS * max(1.0, float(want.abs().mean()))
+
+
+def test_oracle_block_at_real_width_14b(dev):
+    """One block at the real 14B width (C=5120, 40 heads, F=13824, 257 CLIP + 64 text context rows -> the k_img/v_img
+    branch and the C=5120 template instances of the glue kernels), L=256: CUDA vs oracle. Same bar as configs[0]."""
+    cfg = dict(synth.CFG_14B, num_layers=1, text_len=64)
+    sd = synth.make_state_dict(cfg, 78, num_layers=1)
+    eng = _engine(cfg, sd, dev)
+    gen = torch.Generator().manual_seed(10)
+    L, C = 256, cfg["dim"]
+    x = torch.randn(1, L, C, generator=gen)
+    e = 0.5 * torch.randn(1, 6, C, generator=gen)                      # 14B: per-sample modulation [B, 6, C]
+    ctx = torch.randn(1, 257 + 64, C, generator=gen).bfloat16().float()
     m = WanOracle(sd, **synth.oracle_kwargs(cfg))
     want = m.block(0, x, e, grid_freqs(m.tables, 4, 8, 8), ctx)[0]
     got = eng.block_forward(0, x[0], e[0], (4, 8, 8), ctx[0]).cpu()
@@ -414,17 +453,25 @@ def test_fullsize_gemm_linearity_and_row_independence(dev):
     assert rel(o1[rows], a1[rows].float() @ w.float().t()) < 1e-4
 
 
-def test_ulysses_two_gpus_matches_golden(dev):
-    """Sequence-parallel forward on 2 GPUs (torchrun, NCCL) vs the reference-generated golden outputs."""
+@pytest.mark.parametrize("world,transport,split", [(2, "p2p", "0"), (2, "nccl", "0"), (4, "p2p", "0"), (4, "nccl", "0"),
+                                                   (8, "p2p", "0"), (8, "nccl", "0"), (2, "p2p", "2"), (8, "p2p", "2")])
+def test_ulysses_matches_golden(dev, world, transport, split):
+    """Sequence-parallel forward on `world` GPUs (torchrun) vs the reference-generated golden outputs: the 2-head tiny
+    models at world 2, the 8-head (dim 1024) models at world 2 / 4 / 8; both transports (NVLink peer-memory kernels,
+    NCCL all-to-all); split = forced KV tail split of the attention launch through the peer-scatter combine kernel.
+    Skipped on boxes with fewer GPUs — bench.py's `parity_vs_n1` carries the same check on every multi-GPU bench line."""
     import subprocess
     import sys
     from pathlib import Path
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     root = Path(__file__).resolve().parents[1]
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(root / "tools" / "sp_parity.py")],
-                       capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, YB_SP_TRANSPORT=transport)
+    if split != "0":
+        env["YB_ATT_FORCE_SPLIT"] = split
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29533 + world), str(root / "tools" / "sp_parity.py")],
+                       capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 

@@ -81,3 +81,32 @@ def test_history_beyond_last_branch_raises(g5):
     m = WanOracle(sd, **synth.oracle_kwargs(g["cfg"]))
     with pytest.raises(UnboundLocalError):
         m._segments(1400, 1400)
+
+
+# 8-head models (dim 1024): the goldens the Ulysses parity runs at world 2 / 4 / 8 use (tools/sp_parity.py)
+def _h8(golden_dir, name):
+    g = torch.load(golden_dir / name, weights_only=False)
+    return g, synth.make_state_dict(g["cfg"], g["seed_w"])
+
+
+@pytest.mark.parametrize("case", ["5b_grid", "5b_grid_padded", "5b_pack_h10", "5b_pack_h30"])
+def test_5b_h8_forward_matches_reference(golden_dir, case):
+    g, sd = _h8(golden_dir, "wan23_h8.pt")
+    c, cfg = g["cases"][case], g["cfg"]
+    inp = synth.make_inputs(cfg, c["seed"], c["frames"], c["H"], c["W"], c["ctx_len"])
+    out = WanOracle(sd, **synth.oracle_kwargs(cfg)).forward([inp["x"]], torch.tensor(c["t"]), [inp["context"]],
+                                                            seq_len=c["seq_len"], latent_frame_zero=c["lfz"], flag=c["flag"])
+    assert out.shape == c["out"].shape and _rel(out, c["out"]) < TOL
+
+
+@pytest.mark.parametrize("case", ["14b_grid", "14b_grid_padded", "14b_pack_lfz8"])
+def test_14b_h8_forward_matches_reference(golden_dir, case):
+    """14b_grid_padded: seq_len > F*H*W — the 14B tree masks the padded rows as keys (k_lens = seq_lens,
+    wan/modules/model.py:311-314, 916); the 5B tree does not (5b_grid_padded above)."""
+    g, sd = _h8(golden_dir, "wan21_h8.pt")
+    c, cfg = g["cases"][case], g["cfg"]
+    inp = synth.make_inputs(cfg, c["seed"], c["frames"], c["H"], c["W"], c["ctx_len"])
+    out = WanOracle(sd, **synth.oracle_kwargs(cfg)).forward([inp["x"]], torch.tensor(c["t"]), [inp["context"]],
+                                                            seq_len=c["seq_len"], y=[inp["y"]], clip_fea=inp["clip_fea"],
+                                                            latent_frame_zero=c["lfz"], rand_num_img=c["rand_num_img"])
+    assert out.shape == c["out"].shape and _rel(out, c["out"]) < TOL

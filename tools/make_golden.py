@@ -114,6 +114,53 @@ def cases_14b():
     ]
 
 
+def cases_h8():
+    """8-head models (dim 1024): Ulysses parity at world 2 / 4 / 8 (tools/sp_parity.py). Token counts are chosen NOT to
+    divide by 8 so the shard padding path runs; 14b_grid_padded has seq_len > F*H*W (k_lens masking,
+    wan/modules/model.py:311-314)."""
+    five = [("5b_grid", 3, 10, 14, None, False, 0, [500.0]),          # L = 105
+            ("5b_grid_padded", 2, 10, 14, None, False, 9, [250.0]),   # L = 70 + 9 padded rows (keys on the 5B tree)
+            ("5b_pack_h10", 10 + 2, 10, 14, 2, True, 0, [[0.0, 400.0]]),
+            ("5b_pack_h30", 30 + 2, 6, 10, 2, True, 0, [[0.0, 999.0]])]
+    fourteen = [("14b_grid", 3, 10, 14, 9, 0.2, 0, [300.0]),
+                ("14b_grid_padded", 3, 10, 14, 9, 0.2, 7, [300.0]),   # 105 tokens, seq_len 112: 7 masked padding rows
+                ("14b_pack_lfz8", 5 + 8, 6, 10, 8, 0.6, 0, [600.0])]
+    return five, fourteen
+
+
+@torch.no_grad()
+def main_h8(mod23, mod21, out_dir, seed_w):
+    five, fourteen = cases_h8()
+    cfg = synth.CFG_5B_H8
+    sd = synth.make_state_dict(cfg, seed_w + 10)
+    model = build_reference_model(mod23, cfg, sd)
+    gold = {"cfg": cfg, "seed_w": seed_w + 10, "cases": {}}
+    for i, (name, frames, H, W, lfz, flag, pad, t) in enumerate(five):
+        inp = synth.make_inputs(cfg, 300 + i, frames, H, W, ctx_len=20)
+        L_grid = frames * (H // 2) * (W // 2)
+        kwargs = dict(seq_len=L_grid + pad, flag=flag)
+        if lfz is not None:
+            kwargs["latent_frame_zero"] = lfz
+        out = model([inp["x"]], torch.tensor(t), [inp["context"]], **kwargs)[0]
+        gold["cases"][name] = dict(seed=300 + i, frames=frames, H=H, W=W, lfz=lfz, flag=flag, seq_len=L_grid + pad, t=t,
+                                   ctx_len=20, out=out.clone())
+        print("h8", name, tuple(out.shape), float(out.abs().mean()))
+    torch.save(gold, out_dir / "wan23_h8.pt")
+    cfg = synth.CFG_14B_H8
+    sd = synth.make_state_dict(cfg, seed_w + 11)
+    model = build_reference_model(mod21, cfg, sd)
+    gold = {"cfg": cfg, "seed_w": seed_w + 11, "cases": {}}
+    for i, (name, frames, H, W, lfz, rni, pad, t) in enumerate(fourteen):
+        inp = synth.make_inputs(cfg, 400 + i, frames, H, W, ctx_len=20)
+        L_grid = frames * (H // 2) * (W // 2)
+        out, _ = model([inp["x"]], torch.tensor(t), [inp["context"]], seq_len=L_grid + pad, clip_fea=inp["clip_fea"],
+                       y=[inp["y"]], rand_num_img=rni, latent_frame_zero=lfz)
+        gold["cases"][name] = dict(seed=400 + i, frames=frames, H=H, W=W, lfz=lfz, rand_num_img=rni, seq_len=L_grid + pad,
+                                   t=t, ctx_len=20, out=out.clone())
+        print("h8", name, tuple(out.shape), float(out.abs().mean()))
+    torch.save(gold, out_dir / "wan21_h8.pt")
+
+
 @torch.no_grad()
 def main():
     torch.manual_seed(0)
@@ -166,6 +213,7 @@ def main():
                                    ctx_len=20, out=out.clone())
         print(name, tuple(out.shape), float(out.abs().mean()))
     torch.save(gold, out_dir / "wan21_tiny.pt")
+    main_h8(mod23, mod21, out_dir, seed_w)
     for f in sorted(out_dir.glob("*.pt")):
         print(f.name, f.stat().st_size, "bytes")
 

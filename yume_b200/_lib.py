@@ -71,6 +71,7 @@ SIGNATURES = {
     "yb_ln_modulate": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp, _ll, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "yb_rmsnorm_rope": (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "yb_rmsnorm_rope_pieces": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "yb_qk_norm_rope": (_i, [_vp, _vp, _ll, _i, _ll, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "yb_attention": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _f, _i, _vp]),
     "yb_attention_ex": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _f, _i, _vp, _vp]),
     "yb_sp_scatter_qkv": (_i, [_vp, _ll, _vp, _vp, _vp, _i, _i, _i, _i, _f, C.POINTER(C.c_void_p), _i, _i, _i, _vp]),

@@ -107,14 +107,25 @@ ln_modulate_kernel(const float* __restrict__ x, long long ldx, void* __restrict_
   }
 }
 
+// Read-only 16-byte load the compiler may NOT move (volatile + memory clobber). The norm/RoPE kernels below hold a whole
+// token row in registers; left to itself the scheduler hoists the weight and angle loads of ALL chunks to the top of the
+// apply loop (4 float4 per chunk: +192 registers at C = 3072 -> 255 registers and spills). With ordered loads the loop is a
+// hand-made two-stage pipeline: the operands of chunk i+1 are in flight while chunk i is computed and stored.
+__device__ __forceinline__ float4 ldg_f4_ordered(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
 // Warp-per-row variant for C = 128*NV (3072 -> NV 24, 5120 -> NV 40): the whole row lives in one warp's registers,
 // reductions are shuffles only (no block barrier), and every lane keeps NV*16 bytes of loads in flight.
-template <int NV, bool OUT_F32>
-__global__ void __launch_bounds__(256)
+// One multiplicative and one additive per-column operand: (1 + scale[tok], shift[tok]) for adaLN (ADA = true) or the affine
+// (weight, bias) of norm3 / MLPProj (ADA = false) — the host sends the rare "both" case to the general kernel.
+template <int NV, bool OUT_F32, bool ADA>
+__global__ void __launch_bounds__(256, (NV <= 24 && !OUT_F32 && ADA) ? 2 : 1)   // C <= 3072, bf16 out: <= 128 registers, two CTAs (16 rows) per SM
 ln_modulate_warp_kernel(const float* __restrict__ x, long long ldx, void* __restrict__ out, long long ldo,
-                        const float* __restrict__ scale, const float* __restrict__ shift, long long mod_ld,
-                        const int* __restrict__ tok_idx, const float* __restrict__ weight,
-                        const float* __restrict__ lnbias, int L, float eps) {
+                        const float* __restrict__ mul, const float* __restrict__ add, long long mod_ld,
+                        const int* __restrict__ tok_idx, int L, float eps) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= L) return;
@@ -134,35 +145,27 @@ ln_modulate_warp_kernel(const float* __restrict__ x, long long ldx, void* __rest
     q += (a * a + b * b) + (c * c + d * d);
   }
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
-  const long long u = tok_idx ? tok_idx[row] : 0;
-  const float4* sc4 = scale ? reinterpret_cast<const float4*>(scale + u * mod_ld) : nullptr;
-  const float4* sh4 = shift ? reinterpret_cast<const float4*>(shift + u * mod_ld) : nullptr;
-  const float4* w4 = weight ? reinterpret_cast<const float4*>(weight) : nullptr;
-  const float4* b4 = lnbias ? reinterpret_cast<const float4*>(lnbias) : nullptr;
+  const long long u = (ADA && tok_idx) ? tok_idx[row] : 0;
+  // per-chunk operands through ORDERED loads: unordered, the scheduler hoists all 2 x NV of them above
+  // the loop (198 registers at C = 3072 -> one CTA per SM)
+  const float* mp = mul ? mul + u * mod_ld + lane * 4 : nullptr;
+  const float* ap = add ? add + u * mod_ld + lane * 4 : nullptr;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int idx = lane + i * 32;
+    float4 cm = make_float4(0.f, 0.f, 0.f, 0.f), ca = cm;
+    if (mp) cm = ldg_f4_ordered(mp + i * 128);     // (L1 hits: every warp of the SM reads the same table rows; the other
+    if (ap) ca = ldg_f4_ordered(ap + i * 128);     //  15 resident warps cover the latency)
     float4 y;
     y.x = (v[i].x - mean) * rstd;
     y.y = (v[i].y - mean) * rstd;
     y.z = (v[i].z - mean) * rstd;
     y.w = (v[i].w - mean) * rstd;
-    if (w4) {
-      const float4 w = __ldg(w4 + idx);
-      y.x *= w.x; y.y *= w.y; y.z *= w.z; y.w *= w.w;
+    if (mp) {
+      if (ADA) { y.x *= (1.f + cm.x); y.y *= (1.f + cm.y); y.z *= (1.f + cm.z); y.w *= (1.f + cm.w); }
+      else { y.x *= cm.x; y.y *= cm.y; y.z *= cm.z; y.w *= cm.w; }
     }
-    if (b4) {
-      const float4 b = __ldg(b4 + idx);
-      y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w;
-    }
-    if (sc4) {
-      const float4 c = __ldg(sc4 + idx);
-      y.x *= (1.f + c.x); y.y *= (1.f + c.y); y.z *= (1.f + c.z); y.w *= (1.f + c.w);
-    }
-    if (sh4) {
-      const float4 h = __ldg(sh4 + idx);
-      y.x += h.x; y.y += h.y; y.z += h.z; y.w += h.w;
-    }
+    if (ap) { y.x += ca.x; y.y += ca.y; y.z += ca.z; y.w += ca.w; }
     if (OUT_F32) {
       reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + static_cast<long long>(row) * ldo)[idx] = y;
     } else {
@@ -301,6 +304,74 @@ rmsnorm_rope_warp_kernel(__nv_bfloat16* __restrict__ qk, long long ld, int piece
       o[k] = pack_bf16x2(a, b);
     }
     *chunk_ptr(i) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// q AND k of a token row in one launch (WanSelfAttention: norm_q(q), norm_k(k), then rope_apply on both with the SAME
+// per-token angles — wan23/modules/model.py:190-200). One warp per token handles the q row, then the k row (the second
+// pass finds the token's (cos, sin) row in L1); the (cos, sin) quads are fetched as float4 = two pairs. Replaces two
+// rmsnorm_rope launches per block.
+template <int NCH>
+__global__ void __launch_bounds__(256, (NCH <= 12) ? 2 : 1)
+qk_norm_rope_warp_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, long long ld,
+                         const float* __restrict__ wq, const float* __restrict__ wk,
+                         const float2* __restrict__ rope, int rope_len, int L, int D, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= L) return;
+  constexpr int C = NCH * 256;
+  const long long row_off = static_cast<long long>(row) * ld + (lane << 3);
+  auto chunk_off = [&](int i) -> long long { return row_off + i * 256; };   // (plain rows: immediate offsets from one base)
+  const bool rot = (rope != nullptr) && (row < rope_len);
+  const float* rope_row = reinterpret_cast<const float*>(rope) + static_cast<long long>(row) * D;   // D/2 pairs x 2 floats
+#pragma unroll 1
+  for (int part = 0; part < 2; ++part) {
+    __nv_bfloat16* base = part == 0 ? q : k;
+    const float* weight = part == 0 ? wq : wk;
+    uint4 raw[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) raw[i] = *reinterpret_cast<const uint4*>(base + chunk_off(i));
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        ss += f.x * f.x + f.y * f.y;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) * (1.0f / C) + eps);
+    // 256 % D == 0 (checked by the host): a lane's 8 columns sit at the same offset inside a head for every chunk
+    // ((lane*8 + i*256) % D == lane*8 % D), so its 4 (cos, sin) pairs are loop invariants — two float4 loads per row.
+    // Weight chunks go through ordered loads, prefetched one chunk ahead.
+    float cs[8] = {1.f, 0.f, 1.f, 0.f, 1.f, 0.f, 1.f, 0.f};
+    if (rot) {
+      const float4 r0 = ldg_f4_ordered(rope_row + ((lane << 3) % D));
+      const float4 r1 = ldg_f4_ordered(rope_row + ((lane << 3) % D) + 4);
+      cs[0] = r0.x; cs[1] = r0.y; cs[2] = r0.z; cs[3] = r0.w; cs[4] = r1.x; cs[5] = r1.y; cs[6] = r1.z; cs[7] = r1.w;
+    }
+    float4 w0 = ldg_f4_ordered(weight + (lane << 3)), w1 = ldg_f4_ordered(weight + (lane << 3) + 4);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      float4 nw0 = w0, nw1 = w1;
+      if (i + 1 < NCH) {
+        nw0 = ldg_f4_ordered(weight + (lane << 3) + (i + 1) * 256);
+        nw1 = ldg_f4_ordered(weight + (lane << 3) + (i + 1) * 256 + 4);
+      }
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        const float a = f.x * rstd * wv[2 * j];
+        const float b2 = f.y * rstd * wv[2 * j + 1];
+        o[j] = pack_bf16x2(a * cs[2 * j] - b2 * cs[2 * j + 1], a * cs[2 * j + 1] + b2 * cs[2 * j]);
+      }
+      *reinterpret_cast<uint4*>(base + chunk_off(i)) = make_uint4(o[0], o[1], o[2], o[3]);
+      w0 = nw0; w1 = nw1;
+    }
   }
 }
 
@@ -544,24 +615,26 @@ extern "C" int yb_ln_modulate(const void* x, long long ldx, void* out, long long
   if (C % 8 != 0 || C > LN_THREADS * LN_MAX_VEC * 4) return YB_ERR_SHAPE;
   if ((ldx % 4) || (ldo % 8) || (mod_ld % 4)) return YB_ERR_ALIGNMENT;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  const bool ada = scale || shift, affine = weight || lnbias;
+#define YB_LN_LAUNCH(NV, F32, ADA, MUL, ADD)                                                                            \
+  ln_modulate_warp_kernel<NV, F32, ADA><<<(L + 7) / 8, 256, 0, s>>>(static_cast<const float*>(x), ldx, out, ldo,         \
+                                                                    static_cast<const float*>(MUL),                      \
+                                                                    static_cast<const float*>(ADD), mod_ld,              \
+                                                                    static_cast<const int*>(tok_idx), L, eps)
 #define YB_LN_WARP(NV)                                                                                                  \
-  if (C == (NV) * 128) {                                                                                                \
-    const int grid = (L + 7) / 8;                                                                                       \
-    if (out_f32)                                                                                                        \
-      ln_modulate_warp_kernel<NV, true><<<grid, 256, 0, s>>>(                                                            \
-          static_cast<const float*>(x), ldx, out, ldo, static_cast<const float*>(scale), static_cast<const float*>(shift), \
-          mod_ld, static_cast<const int*>(tok_idx), static_cast<const float*>(weight), static_cast<const float*>(lnbias), \
-          L, eps);                                                                                                      \
-    else                                                                                                                \
-      ln_modulate_warp_kernel<NV, false><<<grid, 256, 0, s>>>(                                                           \
-          static_cast<const float*>(x), ldx, out, ldo, static_cast<const float*>(scale), static_cast<const float*>(shift), \
-          mod_ld, static_cast<const int*>(tok_idx), static_cast<const float*>(weight), static_cast<const float*>(lnbias), \
-          L, eps);                                                                                                      \
+  if (C == (NV) * 128 && !(ada && affine)) {                                                                            \
+    if (affine) {                                                                                                       \
+      if (out_f32) YB_LN_LAUNCH(NV, true, false, weight, lnbias); else YB_LN_LAUNCH(NV, false, false, weight, lnbias);  \
+    } else {                                                                                                            \
+      if (out_f32) YB_LN_LAUNCH(NV, true, true, scale, shift); else YB_LN_LAUNCH(NV, false, true, scale, shift);        \
+    }                                                                                                                   \
     return check_launch("ln_modulate");                                                                                 \
   }
   YB_LN_WARP(24)
   YB_LN_WARP(40)
+  YB_LN_WARP(8)
   YB_LN_WARP(2)
+#undef YB_LN_LAUNCH
 #undef YB_LN_WARP
   if (out_f32)
     ln_modulate_kernel<true><<<L, LN_THREADS, 0, s>>>(static_cast<const float*>(x), ldx, out, ldo,
@@ -594,6 +667,7 @@ extern "C" int yb_rmsnorm_rope_pieces(void* qk, long long ld, int piece_cols, lo
   }
   YB_RR_WARP(12)
   YB_RR_WARP(20)
+  YB_RR_WARP(4)
   YB_RR_WARP(1)
 #undef YB_RR_WARP
   rmsnorm_rope_kernel<<<L, RR_THREADS, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
@@ -605,6 +679,35 @@ extern "C" int yb_rmsnorm_rope_pieces(void* qk, long long ld, int piece_cols, lo
 extern "C" int yb_rmsnorm_rope(void* qk, long long ld, const void* weight, const void* rope, int rope_len, int L,
                                int C, int D, float eps, void* stream_) {
   return yb_rmsnorm_rope_pieces(qk, ld, C, 0, weight, rope, rope_len, L, C, D, eps, stream_);
+}
+
+// RMSNorm(q) | RMSNorm(k) + RoPE on both, one launch (see qk_norm_rope_warp_kernel). q / k: first element of the two
+// [L, C] row sets (same row stride `ld`, same piece layout). Widths without a warp-per-row instance run the general
+// kernel twice.
+extern "C" int yb_qk_norm_rope(void* q, void* k, long long ld, int piece_cols, long long piece_stride, const void* wq,
+                               const void* wk, const void* rope, int rope_len, int L, int C, int D, float eps,
+                               void* stream_) {
+  if (!q || !k || !wq || !wk || L <= 0 || C <= 0 || D <= 0 || piece_cols <= 0) return YB_ERR_ARG;
+  if (C % 8 != 0 || D % 8 != 0 || C % D != 0 || piece_cols % 8 != 0 || C % piece_cols != 0) return YB_ERR_SHAPE;
+  if ((ld % 8) || (piece_stride % 8) || (reinterpret_cast<uintptr_t>(q) & 0xF) || (reinterpret_cast<uintptr_t>(k) & 0xF))
+    return YB_ERR_ALIGNMENT;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+#define YB_QK_WARP(NCH)                                                                                               \
+  if (C == (NCH) * 256 && piece_cols == C && 256 % D == 0) {                                                                                             \
+    qk_norm_rope_warp_kernel<NCH><<<(L + 7) / 8, 256, 0, s>>>(                                                         \
+        static_cast<__nv_bfloat16*>(q), static_cast<__nv_bfloat16*>(k), ld,                                            \
+        static_cast<const float*>(wq), static_cast<const float*>(wk), static_cast<const float2*>(rope), rope_len, L, D, \
+        eps);                                                                                                          \
+    return check_launch("qk_norm_rope");                                                                              \
+  }
+  YB_QK_WARP(12)
+  YB_QK_WARP(20)
+  YB_QK_WARP(4)
+  YB_QK_WARP(1)
+#undef YB_QK_WARP
+  int rc = yb_rmsnorm_rope_pieces(q, ld, piece_cols, piece_stride, wq, rope, rope_len, L, C, D, eps, stream_);
+  if (rc) return rc;
+  return yb_rmsnorm_rope_pieces(k, ld, piece_cols, piece_stride, wk, rope, rope_len, L, C, D, eps, stream_);
 }
 
 extern "C" int yb_patchify(const void* x, long long sc, long long sf, long long sh, long long sw, void* out,
@@ -678,6 +781,7 @@ extern "C" int yb_sp_scatter_qkv(const void* qkv, long long ld, const void* wq, 
   }
   YB_SC(12)
   YB_SC(20)
+  YB_SC(4)
   YB_SC(1)
 #undef YB_SC
   return YB_ERR_SHAPE;

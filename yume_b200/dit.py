@@ -14,7 +14,9 @@ regime the reference runs under torch.autocast(bf16).
 """
 from __future__ import annotations
 
+import contextlib
 import math
+from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -139,6 +141,15 @@ class WanDiT:
         self.timer = KernelTimer()          # bench.py switches it on to time individual kernels inside a live step
         self.sp_group, self.sp_world, self.sp_rank = None, 1, 0
         self.sp_transport, self._sp_p2p = "auto", None
+        # sampler-loop fusion, both behind the unchanged forward signature:
+        #  context_cache  the embedded context and every block's cross-attention K|V depend only on (context, clip_fea);
+        #                 keep them while the caller passes the SAME tensors again (every Euler step of a sampling loop,
+        #                 cond / uncond alternating under CFG) instead of recomputing 2 + layers GEMMs per forward
+        #  use_cuda_graph replay the fixed-shape step as one CUDA graph (one launch instead of ~460 ctypes calls)
+        self.context_cache = True
+        self.use_cuda_graph = False
+        self._ctx_entries: "OrderedDict[tuple, tuple]" = OrderedDict()
+        self._graphs: Dict[tuple, dict] = {}
         self._repack(state_dict)
 
     # ------------------------------------------------------------------------------------------------------
@@ -235,6 +246,17 @@ class WanDiT:
             b["w_qkv_sp"] = b["w_qkv"][idx].contiguous()
             b["b_qkv_sp"] = b["b_qkv"][idx].contiguous()
 
+    @contextlib.contextmanager
+    def sequence_parallel_disabled(self):
+        """Run forwards on this rank alone (no Ulysses, no collectives) while the block is active — bench.py uses it to
+        compare the N-GPU output with the single-GPU output of the SAME engine (`parity_vs_n1`)."""
+        saved = (self.sp_world, self.sp_rank)
+        self.sp_world, self.sp_rank = 1, 0
+        try:
+            yield self
+        finally:
+            self.sp_world, self.sp_rank = saved
+
     @classmethod
     def from_module(cls, model: torch.nn.Module, variant: str, device="cuda") -> "WanDiT":
         """Build from a live reference WanModel (or yume_b200.model.WanModel): reads its parameters, never
@@ -258,6 +280,7 @@ class WanDiT:
         if t is None:
             for old in [o for o in self._ws if o[0] == key]:   # geometry changed: drop the stale buffer
                 del self._ws[old]
+                self._graphs.clear()                           # captured graphs hold its address
             t = torch.empty(shape, device=self.device, dtype=dtype)
             self._ws[k] = t
         return t
@@ -296,6 +319,9 @@ class WanDiT:
         writing f32 token rows into out_rows [f*hp*wp, C]. Returns (f, hp, wp)."""
         w, b = self.embed[name]
         cin, f, H, W = u.shape
+        if name == "patch_embedding":          # plain Conv3d, no convpadd: odd H / W lose their last row / column
+            u = u[:, :, :H // patch * patch, :W // patch * patch]   # (model.py:453-454; convpadd only wraps the 2x..16x embedders)
+            cin, f, H, W = u.shape
         hp, wp = -(-H // patch), -(-W // patch)
         n_tok = f * hp * wp
         a = self._buf("patch_a", (n_tok, w.shape[1]), _BF16)
@@ -426,10 +452,10 @@ class WanDiT:
         T.begin("gemm_qkv")
         ops.gemm(h, b["w_qkv_sp"], b["b_qkv_sp"], send, ops.YB_EPI_BF16, n_split=W3, split_stride=Lp * W3, shape=(Lp, C))
         T.end("gemm_qkv")
-        T.begin("rmsnorm_rope")
-        ops.rmsnorm_rope(send[0], b["nq"], rope, D, self.eps, rope_len, pieces=(Lp, C, Wh, Lp * W3))
-        T.end("rmsnorm_rope")
-        ops.rmsnorm_rope(send[0][:, Wh:], b["nk"], rope, D, self.eps, rope_len, pieces=(Lp, C, Wh, Lp * W3))
+        T.begin("qk_norm_rope")
+        ops.qk_norm_rope(send[0], send[0][:, Wh:], b["nq"], b["nk"], rope, D, self.eps, rope_len,
+                         pieces=(Lp, C, Wh, Lp * W3))
+        T.end("qk_norm_rope")
         T.begin("sp_all_to_all_qkv")
         dist.all_to_all_single(recv, send, group=self.sp_group)
         T.end("sp_all_to_all_qkv")
@@ -447,17 +473,20 @@ class WanDiT:
                  a_split=Wh, a_split_stride=Lp * Wh, shape=(Lp, C))
         T.end("gemm_o")
 
-    def _cross_kv(self, ctx: Tensor):
+    def _cross_kv(self, ctx: Tensor, own_storage: bool = False):
         """K | V of the embedded context for every block in one GEMM (+ the image branch for 14B), RMSNorm on the K
-        halves. Returns per-block (kv_text, kv_img or None) views of [S, 2C]."""
+        halves. Returns per-block (kv_text, kv_img or None) views of [S, 2C]. own_storage: allocate fresh result buffers
+        (context-cache entries outlive the call) instead of the shared workspace."""
         C, D = self.dim, self.head_dim
         n_img = 257 if self.variant == "14b" else 0
         ctx_txt = ctx[n_img:]
-        kv_all = self._buf("ckv_all", (ctx_txt.shape[0], self.layers * 2 * C), _BF16)
+        alloc = (lambda key, shape: torch.empty(shape, device=self.device, dtype=_BF16)) if own_storage else \
+            (lambda key, shape: self._buf(key, shape, _BF16))
+        kv_all = alloc("ckv_all", (ctx_txt.shape[0], self.layers * 2 * C))
         ops.gemm(ctx_txt, self.cw_kv_all, self.cb_kv_all, kv_all, ops.YB_EPI_BF16)
         kvi_all = None
         if n_img:
-            kvi_all = self._buf("ckv_img_all", (n_img, self.layers * 2 * C), _BF16)
+            kvi_all = alloc("ckv_img_all", (n_img, self.layers * 2 * C))
             ops.gemm(ctx[:n_img], self.cw_kv_img_all, self.cb_kv_img_all, kvi_all, ops.YB_EPI_BF16)
         out = []
         for i, b in enumerate(self.blocks):
@@ -469,6 +498,27 @@ class WanDiT:
                 ops.rmsnorm_rope(kvi[:, :C], b["cnk_img"], None, D, self.eps)
             out.append((kv, kvi))
         return out
+
+    def _context_kv(self, context: Tensor, clip_fea: Optional[Tensor]):
+        """Per-block cross-attention K|V for (context, clip_fea). With `context_cache` the result is kept, keyed on the
+        identity AND version counter of the caller's tensors (an in-place edit bumps `_version`; the entry holds references,
+        so the addresses cannot be recycled while it lives). Four entries: cond / uncond of two prompts."""
+        if not self.context_cache:
+            return self._cross_kv(self._context(context.to(device=self.device), clip_fea))
+        key = (context.data_ptr(), context._version, tuple(context.shape), context.dtype, str(context.device),
+               None if clip_fea is None else (clip_fea.data_ptr(), clip_fea._version, tuple(clip_fea.shape)))
+        hit = self._ctx_entries.get(key)
+        if hit is not None:
+            self._ctx_entries.move_to_end(key)
+            return hit[0]
+        if torch.cuda.is_current_stream_capturing():           # (the warm-up run before a capture fills the cache)
+            return self._cross_kv(self._context(context.to(device=self.device), clip_fea))
+        kv = self._cross_kv(self._context(context.to(device=self.device), clip_fea), own_storage=True)
+        self._ctx_entries[key] = (kv, context, clip_fea)
+        while len(self._ctx_entries) > 4:
+            self._ctx_entries.popitem(last=False)
+            self._graphs.clear()                               # graphs captured against the evicted K|V buffers
+        return kv
 
     def _block(self, i: int, xs: Tensor, mod: Tensor, tok_idx: Optional[Tensor], rope: Tensor, rope_len: int,
                ctx: Tensor, L_true: Optional[int] = None) -> None:
@@ -487,20 +537,21 @@ class WanDiT:
         if self.sp_world > 1:
             self._self_attention_sp(i, b, h, xs, m, tok_idx, rope, rope_len, L_true if L_true is not None else L)
         else:
-            self._self_attention_local(b, h, qkv, att, xs, m, tok_idx, rope, rope_len)
+            self._self_attention_local(b, h, qkv, att, xs, m, tok_idx, rope, rope_len, L_true if L_true is not None else L)
         self._cross_and_ffn(b, xs, h, qkv, att, m, tok_idx, ctx[i] if isinstance(ctx, list) else self._cross_kv(ctx)[i])
 
-    def _self_attention_local(self, b, h, qkv, att, xs, m, tok_idx, rope, rope_len) -> None:
+    def _self_attention_local(self, b, h, qkv, att, xs, m, tok_idx, rope, rope_len, k_len) -> None:
+        """k_len: rows that are keys. All L on the 5B tree (wan23/modules/model.py:846-851); on the 14B regular-grid path
+        the reference passes k_lens = F*H*W, masking the zero-padded rows (wan/modules/model.py:311-314, 916)."""
         C, H, D, T = self.dim, self.heads, self.head_dim, self.timer
         T.begin("gemm_qkv")
         ops.gemm(h, b["w_qkv"], b["b_qkv"], qkv, ops.YB_EPI_BF16)
         T.end("gemm_qkv")
-        T.begin("rmsnorm_rope")
-        ops.rmsnorm_rope(qkv[:, :C], b["nq"], rope, D, self.eps, rope_len)
-        T.end("rmsnorm_rope")
-        ops.rmsnorm_rope(qkv[:, C:2 * C], b["nk"], rope, D, self.eps, rope_len)
+        T.begin("qk_norm_rope")
+        ops.qk_norm_rope(qkv[:, :C], qkv[:, C:2 * C], b["nq"], b["nk"], rope, D, self.eps, rope_len)
+        T.end("qk_norm_rope")
         T.begin("self_attention")
-        ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], att, H)
+        ops.attention(qkv[:, :C], qkv[:k_len, C:2 * C], qkv[:k_len, 2 * C:], att, H)
         T.end("self_attention")
         T.begin("gemm_o")
         ops.gemm(att, b["w_o"], b["b_o"], xs, ops.YB_EPI_GATE_RES, gate=m[:, 2], tok_idx=tok_idx)
@@ -556,6 +607,66 @@ class WanDiT:
                 clip_fea: Optional[Tensor] = None, latent_frame_zero: Optional[int] = None, packed: bool = True) -> Tensor:
         """One sample. x f32 [C_x, F, H, W] (+ y concatenated on channels), t f32 [1] or [1, L] / [2]-style
         (first = history, last = new), context [S<=text_len, text_dim]. Returns f32 [C_out, F_new, H, W]."""
+        with torch.cuda.device(self.device):               # launches take the stream of the ENGINE's device
+            if self.use_cuda_graph and self.sp_world == 1 and not self.timer.active:
+                # arbitrary per-token t goes through torch.unique (host sync): not capturable
+                if self.variant == "14b" or packed or t.numel() == 1:
+                    return self._forward_graphed(x, t, context, seq_len, y, clip_fea, latent_frame_zero, packed)
+            return self._forward_eager(x, t, context, seq_len, y, clip_fea, latent_frame_zero, packed)
+
+    def _forward_graphed(self, x, t, context, seq_len, y, clip_fea, latent_frame_zero, packed) -> Tensor:
+        """CUDA-graph replay of the step: inputs are copied into static device buffers, the graph (captured on first
+        use of a geometry, after one eager warm-up run that sizes every workspace buffer) replays all launches, the
+        result is copied out of the graph's static output. With the context cache on, the graph contains the step only
+        and reads the cached K|V of (context, clip_fea); otherwise the context embedding is part of the graph."""
+        dev = self.device
+        cached = self.context_cache
+        ckey = (context.data_ptr(), context._version, tuple(context.shape),
+                None if clip_fea is None else (clip_fea.data_ptr(), clip_fea._version)) if cached else \
+            (tuple(context.shape), None if clip_fea is None else tuple(clip_fea.shape))
+        key = (tuple(x.shape), None if y is None else tuple(y.shape), t.numel(), int(seq_len), latent_frame_zero,
+               bool(packed), cached, ckey)
+        g = self._graphs.get(key)
+        if g is None:
+            st = dict(x=torch.empty(x.shape, device=dev, dtype=_F32), t=torch.empty(t.numel(), device=dev, dtype=_F32),
+                      y=None if y is None else torch.empty(y.shape, device=dev, dtype=_F32),
+                      ctx=context if cached else torch.empty(context.shape, device=dev, dtype=context.dtype),
+                      clip=clip_fea if (cached or clip_fea is None) else torch.empty(clip_fea.shape, device=dev,
+                                                                                     dtype=clip_fea.dtype))
+            st["x"].copy_(x)
+            st["t"].copy_(t.flatten())
+            if y is not None:
+                st["y"].copy_(y)
+            if not cached:
+                st["ctx"].copy_(context)
+                if clip_fea is not None:
+                    st["clip"].copy_(clip_fea)
+            args = (st["x"], st["t"], st["ctx"], seq_len, st["y"], st["clip"], latent_frame_zero, packed)
+            self._forward_eager(*args)                          # warm-up: allocates workspaces, fills the context cache
+            torch.cuda.synchronize(dev)
+            graphs_before = self._graphs
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st["out"] = self._forward_eager(*args)
+            st["graph"] = graph
+            if self._graphs is graphs_before:                   # (a workspace change during capture would have cleared it)
+                self._graphs[key] = st
+            g = st
+        else:
+            g["x"].copy_(x, non_blocking=True)
+            g["t"].copy_(t.flatten(), non_blocking=True)
+            if y is not None:
+                g["y"].copy_(y, non_blocking=True)
+            if not cached:
+                g["ctx"].copy_(context, non_blocking=True)
+                if clip_fea is not None:
+                    g["clip"].copy_(clip_fea, non_blocking=True)
+        g["graph"].replay()
+        return g["out"].clone()
+
+    def _forward_eager(self, x: Tensor, t: Tensor, context: Tensor, seq_len: int, y: Optional[Tensor] = None,
+                       clip_fea: Optional[Tensor] = None, latent_frame_zero: Optional[int] = None,
+                       packed: bool = True) -> Tensor:
         dev, C = self.device, self.dim
         x = x.to(device=dev, dtype=_F32)
         if y is not None:
@@ -580,8 +691,11 @@ class WanDiT:
                 hh, ww = Hh, Ww
                 if seg.pre_2x_f:
                     hh, ww = -(-hh // 4), -(-ww // 4)
-                shapes.append((f, -(-hh // seg.patch), -(-ww // seg.patch)))
-            new_shape = (latent_frame_zero, -(-Hh // 2), -(-Ww // 2))
+                if seg.name == "patch_embedding":              # un-padded embedder floors (see _embed_tokens)
+                    shapes.append((f, hh // 2, ww // 2))
+                else:
+                    shapes.append((f, -(-hh // seg.patch), -(-ww // seg.patch)))
+            new_shape = (latent_frame_zero, Hh // 2, Ww // 2)
             L_hist = sum(f * a * b for f, a, b in shapes)
             L = L_hist + new_shape[0] * new_shape[1] * new_shape[2]
             xs = self._buf("xs", (L, C), _F32)
@@ -606,7 +720,7 @@ class WanDiT:
             rope_segs.append((*new_shape, f_z))
             grid_new, rope_len = new_shape, L
         else:
-            grid_new = (Ftot, -(-Hh // 2), -(-Ww // 2))
+            grid_new = (Ftot, Hh // 2, Ww // 2)
             L_grid = grid_new[0] * grid_new[1] * grid_new[2]
             if L_grid > seq_len:
                 raise AssertionError("seq_lens.max() <= seq_len")   # model.py:755
@@ -643,10 +757,12 @@ class WanDiT:
         head_tab = head_parts[0] if len(head_parts) == 1 else torch.cat(head_parts, dim=0).contiguous()
 
         # ---- context -----------------------------------------------------------------------------------
-        ctx = self._cross_kv(self._context(context.to(device=dev), clip_fea))
+        ctx = self._context_kv(context, clip_fea)
 
         # ---- Ulysses: keep only this rank's contiguous token shard --------------------------------------
-        L_true = L
+        # rows that serve as self-attention keys: every row, except on the 14B regular-grid path where the reference
+        # masks the zero padding beyond F*H*W (k_lens = seq_lens, wan/modules/model.py:311-314, 916)
+        L_true = L_grid if (self.variant == "14b" and not packed) else L
         if self.sp_world > 1:
             import torch.distributed as dist
             Lp, r0, n_valid = sp_shard(L, self.sp_world, self.sp_rank)

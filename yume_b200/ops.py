@@ -13,13 +13,20 @@ from ._lib import (YB_ATT_ACCUMULATE, YB_ATT_P_SMEM, YB_EPI_BF16, YB_EPI_F32, YB
                    YB_EPI_GELU_ERF_BF16, YB_EPI_RES_BF16, Conv3dArgs, GemmArgs, YumeB200Error, check)
 
 __all__ = [
-    "gemm", "ln_modulate", "rmsnorm_rope", "attention", "patchify", "unpatchify", "sinusoidal",
+    "gemm", "ln_modulate", "rmsnorm_rope", "qk_norm_rope", "flop_count", "attention", "patchify", "unpatchify", "sinusoidal",
     "linear_f32_small", "linear_f32", "umma_probe", "launch_count", "reset_launch_count",
     "YB_EPI_BF16", "YB_EPI_GELU_BF16", "YB_EPI_F32", "YB_EPI_GATE_RES", "YB_EPI_GELU_ERF_BF16", "bcast_add",
     "YB_ATT_P_SMEM", "YB_ATT_ACCUMULATE",
 ]
 
 _launches = 0
+_flops = 0.0        # algorithmic tensor-core FLOPs (2*M*N*K) of the GEMM / conv / attention launches since the last reset
+
+
+def flop_count() -> float:
+    """Algorithmic FLOPs of the tensor-core launches (gemm, conv3d_causal, attention*) since the last reset — bench.py
+    derives the tensor-roofline fraction of whole decodes / forwards from it."""
+    return _flops
 
 
 def launch_count() -> int:
@@ -28,8 +35,9 @@ def launch_count() -> int:
 
 
 def reset_launch_count() -> None:
-    global _launches
+    global _launches, _flops
     _launches = 0
+    _flops = 0.0
 
 
 def _stream() -> int:
@@ -54,7 +62,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
          n_split: int = 0, split_stride: int = 0, a_split: int = 0, a_split_stride: int = 0,
          shape: Optional[tuple] = None, res: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = epi(a[M,K] @ w[N,K]^T + bias). a, w bf16 (2-D, row stride arbitrary); see include/yume_b200.h."""
-    global _launches
+    global _launches, _flops
     _need(a, torch.bfloat16, "a")
     _need(w, torch.bfloat16, "w")
     N, K2 = w.shape
@@ -84,6 +92,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
         res_ld=(res.stride(-2) if res is not None else 0))
     check(_lib.load().yb_gemm_bf16(C.byref(args), _stream()), "yb_gemm_bf16")
     _launches += 1
+    _flops += 2.0 * M * N * K
     return out
 
 
@@ -132,6 +141,36 @@ def rmsnorm_rope(qk: torch.Tensor, weight: torch.Tensor, rope: Optional[torch.Te
           "yb_rmsnorm_rope")
     _launches += 1
     return qk
+
+
+def qk_norm_rope(q: torch.Tensor, k: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, rope: Optional[torch.Tensor],
+                 head_dim: int, eps: float = 1e-6, rope_len: Optional[int] = None, pieces: Optional[tuple] = None) -> None:
+    """RMSNorm(q)*wq, RMSNorm(k)*wk and RoPE on both, in place, ONE launch. q, k: bf16 [L, C] views with the same row
+    stride (e.g. two column ranges of the fused qkv buffer). pieces as for rmsnorm_rope."""
+    global _launches
+    _need(q, torch.bfloat16, "q")
+    _need(k, torch.bfloat16, "k")
+    _need(wq, torch.float32, "wq")
+    _need(wk, torch.float32, "wk")
+    if q.stride(0) != k.stride(0):
+        raise YumeB200Error("q and k must share their row stride")
+    if pieces is not None:
+        L, Cdim, piece_cols, piece_stride = pieces
+    else:
+        if q.shape != k.shape:
+            raise YumeB200Error("q and k must have the same shape")
+        L, Cdim = q.shape
+        piece_cols, piece_stride = Cdim, 0
+    if rope is not None:
+        _need(rope, torch.float32, "rope")
+        if not rope.is_contiguous() or rope.shape[-1] != 2 or rope.shape[-2] != head_dim // 2:
+            raise YumeB200Error("rope must be contiguous f32 [L, D/2, 2]")
+        if rope_len is None:
+            rope_len = rope.shape[0]
+    check(_lib.load().yb_qk_norm_rope(q.data_ptr(), k.data_ptr(), q.stride(0), piece_cols, piece_stride, wq.data_ptr(),
+                                      wk.data_ptr(), _ptr(rope), rope_len or 0, L, Cdim, head_dim, eps, _stream()),
+          "yb_qk_norm_rope")
+    _launches += 1
 
 
 def gemm_2cta(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
@@ -277,7 +316,7 @@ def conv3d_causal(xpad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tens
     """Implicit-GEMM causal conv. Default: xpad bf16 [T+2, H+2, W+2, Cp] replicate padded (hyvideo VAE). With
     oob_zero_pad the input is the unpadded [T, H, W, Cp] and the zero padding is TMA out-of-bounds fill (Wan2.2 VAE).
     w bf16 [Cout, kt*kh*kw*Cp]; out rows are output voxels (frame t -> t*out_t_mul + out_t_add)."""
-    global _launches
+    global _launches, _flops
     _need(xpad, torch.bfloat16, "xpad")
     _need(w, torch.bfloat16, "w")
     Cp = xpad.shape[-1]
@@ -294,6 +333,7 @@ def conv3d_causal(xpad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tens
                       out_t_mul=out_t_mul, out_t_add=out_t_add, fuse_w=fuse_w)
     check(_lib.load().yb_conv3d_causal(C.byref(args), _stream()), "yb_conv3d_causal")
     _launches += 1
+    _flops += 2.0 * T * H * W * kt * kh * kw * Cp * w.shape[0]
     return out
 
 
