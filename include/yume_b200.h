@@ -7,7 +7,7 @@
  * entry points below. Each entry point names the reference code it replaces.
  *
  * Conventions: every pointer is a CUDA device pointer unless stated; `stream` is a cudaStream_t passed as
- * void*; functions never allocate device memory, never synchronise, never throw; they return 0 on
+ * void*; functions never allocate device memory, never synchronise, never throw (workspaces are caller-owned); they return 0 on
  * success or a negative YB_ERR_* code. Row-major everywhere, strides in elements.
  */
 #ifndef YUME_B200_H_
@@ -44,6 +44,9 @@ int yb_abi_version(void);
 #define YB_EPI_GELU_ERF_BF16 4 /* out bf16 = gelu_erf(acc + bias)         (nn.GELU() in MLPProj, wan/modules/model.py:536) */
 
 typedef struct yb_gemm_args {
+  unsigned int struct_bytes; /* = sizeof(yb_gemm_args): the library rejects a caller built against another layout */
+  int cta_pair;    /* kernel choice: 0 = automatic (SM-pair `cta_group::2` kernel for M >= 1024 token GEMMs, 1-CTA kernel for the small
+                      context / embedding projections), 1 = force the 1-CTA kernel, 2 = force the SM-pair kernel (tests, tuning) */
   const void* A;   /* bf16 [M, K], row stride lda */
   const void* B;   /* bf16 [N, K], row stride ldb  (nn.Linear.weight layout) */
   const void* bias;/* f32 [N] or NULL */
@@ -53,7 +56,8 @@ typedef struct yb_gemm_args {
   long long lda, ldb, ldo, gate_ld;
   int M, N, K;
   int epilogue;    /* YB_EPI_* */
-  int block_n;     /* 0 = auto, or 128 / 256 */
+  int block_n;     /* N tile: 0 = auto; 1-CTA kernel 128 / 256; SM-pair kernel any multiple of 32 up to 256 (auto: the width that
+                      minimises waves x width on the SM pairs, yb_gemm_plan) */
   int n_split;     /* YB_EPI_BF16 only: > 0 => output column block j (width n_split, % 32 == 0) is written at
                       out + j*split_stride + m*ldo + (n % n_split): the peer-major layout the Ulysses all-to-all sends */
   long long split_stride;
@@ -65,6 +69,9 @@ typedef struct yb_gemm_args {
   long long res_ld;
 } yb_gemm_args;
 int yb_gemm_bf16(const yb_gemm_args* args, void* stream);
+/* Host-only: the kernel / tiling yb_gemm_bf16 picks for an [M, N] output on a GPU with `sms` SMs (no device access).
+ * out4 = {1 if the SM-pair kernel, N tile, M tiles (of 256 rows for the pair kernel, 128 otherwise), N tiles}. */
+int yb_gemm_plan(int M, int N, int sms, int* out4);
 
 /* ---------------------------------------------------------------------------------------------
  * CausalConv3d k=3 (replicate pad W 1,1 / H 1,1 / T 2,0 then Conv3d: hyvideo/vae/unet_causal_3d_blocks.py:48-74) as an
@@ -74,6 +81,8 @@ int yb_gemm_bf16(const yb_gemm_args* args, void* stream);
  *   out   [T*H*W, ldo] channels-last; epilogue YB_EPI_BF16, YB_EPI_F32 or YB_EPI_RES_BF16 (+ res bf16 [T*H*W, res_ld])
  * ------------------------------------------------------------------------------------------- */
 typedef struct yb_conv3d_args {
+  unsigned int struct_bytes; /* = sizeof(yb_conv3d_args) */
+  int reserved;              /* 0 */
   const void* xpad;
   const void* w;
   const void* bias; /* f32 [Cout] or NULL */
@@ -144,27 +153,36 @@ int yb_qk_norm_rope(void* q, void* k, long long ld, int piece_cols, long long pi
  * ------------------------------------------------------------------------------------------- */
 int yb_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                  long long ldo, int Lq, int Lk, int heads, float scale, int flags, void* stream);
-/* Same, with an optional clock64 trace buffer (int64 [32*32]) filled by CTA (1,0) for KV tiles 16..47: per tile
+/* Full form. `ws` / `ws_bytes`: caller-owned device workspace for the automatic KV tail split (size it with
+ * yb_attention_workspace_bytes; NULL or too small = the launch is not split — same result, a partly idle last wave; the
+ * library itself never allocates and never synchronises, so the call is CUDA-graph-capture safe). `trace`: optional clock64
+ * trace buffer (int64 [32*32]) filled by CTA (1,0) for KV tiles 16..47 (classic softmax schedule only): per tile
  * [X*8 + {0: before S wait, 1: S ready, 2: S in registers, 3: row max done, 4: P stored, 5: arrived}] for the softmax
- * warp of query tile X, and [16 + X*4 + {0: before P wait, 1: P ready, 2: PV+S issued}] for the MMA thread.
- * Tuning / tests only; pass NULL in production. */
+ * warp of query tile X, and [16 + X*4 + {0: before P wait, 1: P ready, 2: PV+S issued}] for the MMA thread. Tuning / tests
+ * only; pass NULL in production. */
 int yb_attention_ex(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
-                    long long ldo, int Lq, int Lk, int heads, float scale, int flags, void* trace, void* stream);
+                    long long ldo, int Lq, int Lk, int heads, float scale, int flags, void* ws, long long ws_bytes,
+                    void* trace, void* stream);
 #define YB_ATT_P_SMEM 1     /* flags bit 0: stage P through shared memory instead of TMEM (debug variant) */
 #define YB_ATT_EMU_SHIFT 2  /* flags bits 2-3: fraction of exponentials evaluated on the FMA pipe instead of the MUFU:
                                0 = none, 1 = 1/4, 2 = 1/3, 3 = 1/2 (tuning knob; results agree to < 2e-4 relative) */
 #define YB_ATT_ACCUMULATE 2 /* flags bit 1: out += result (WanI2VCrossAttention sums the text and image branches,
                                wan/modules/model.py:380-387) */
-#define YB_ATT_Q64 128      /* flags bit 7: EXPERIMENTAL kernel variant (Q resident in TMEM, 64-key tiles; attention64.cu) — not
-                               yet run on hardware, never set by the product path */
 #define YB_ATT_SPLIT_SHIFT 4 /* flags bits 4-6: KV split policy. 0 = automatic (the units of a last wave that is at most
                                half full are cut into KV segments and merged by a combine kernel), 1 = never, 2..4 = cut
                                EVERY unit into that many segments (tests). Results are identical up to fp32 rounding. */
+#define YB_ATT_SM_SHIFT 8   /* flags bits 8-9: softmax schedule. 0 = classic (tile max before the exponentials), 1 = deferred max
+                               (exponentials against the running reference, exactness guard; attention.cu), 2 = deferred max
+                               with packed bf16x2 exponentials (argument rounded to bf16: see attention.cu for the error bound) */
 /* Host-only: the work decomposition yb_attention would use on a GPU with `sms` SMs (no device access; the CPU test-suite
  * pins the scheduler with it). out4 = {CTAs running whole units, tail units that are split, KV segments per tail unit,
  * 128-key tiles per segment}. flags as for yb_attention (ACCUMULATE disables the split; bits 4-6 force it). */
 int yb_attention_plan(int Lq, int Lk, int heads, int sms, int flags, int* out4);
-
+/* Host-only: bytes of workspace yb_attention_ex / yb_attention_sp need for that decomposition (0 when nothing is split). */
+long long yb_attention_workspace_bytes(int Lq, int Lk, int heads, int sms, int flags);
+/* Test hook: force the KV split policy (0 = off, 1..4 as YB_ATT_SPLIT_SHIFT) for every later launch whose flags leave it
+ * automatic — lets the multi-GPU parity tool drive the split + peer-scatter combine path. Process-global, not thread-safe. */
+int yb_debug_force_split(int ns);
 /* ---------------------------------------------------------------------------------------------
  * Ulysses sequence parallelism fused with the NVLink exchange (design reference
  * wan23/distributed/ulysses.py:9-47, sequence_parallel.py:147-176 — three NCCL all_to_alls in, one out).
@@ -180,7 +198,7 @@ int yb_sp_scatter_qkv(const void* qkv, long long ld, const void* wq, const void*
                       int L, int C, int D, float eps, void* const* peers, int world, int rank, int Lp, void* stream);
 int yb_attention_sp(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                     void* const* out_peers, long long ldo, int Lq, int Lk, int heads, float scale, int world, int rank,
-                    int Lp, void* stream);
+                    int Lp, int flags, void* ws, long long ws_bytes, void* stream);   /* flags / ws as yb_attention_ex */
 
 /* ---------------------------------------------------------------------------------------------
  * patchify gather (bit-exact index op): x f32 [Cin, F, H, W] (element strides sc, sf, sh, sw) -> bf16 [F*(Hp)*(Wp), Cin*ph*pw] rows in
@@ -257,10 +275,6 @@ int yb_vae_unpatchify2_clamp(const void* y, long long ldy, void* out, int T, int
  *   mode 2: A in TMEM (bf16x2 packed), B MN-major D = A * Bmn
  * A, B bf16 [128,128] row-major; D f32 [128,128].
  * ------------------------------------------------------------------------------------------- */
-/* EXPERIMENTAL (not on the product path, not yet run on hardware; tests skipped unless YB_RUN_EXPERIMENTAL=1): SM-pair
- * (`tcgen05.mma.cta_group::2`) GEMM, out bf16 [M, N] = A[M, K] x B[N, K]^T + bias — yume_b200/csrc/gemm2cta.cu. */
-int yb_gemm_bf16_2cta(const void* A, long long lda, const void* B, long long ldb, const void* bias, void* out,
-                      long long ldo, int M, int N, int K, void* stream);
 int yb_umma_probe(const void* A, const void* B, void* D, int mode, void* stream);  /* modes >= 3: A rows shifted by (mode - 2) */
 
 #ifdef __cplusplus

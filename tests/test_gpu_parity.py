@@ -51,17 +51,53 @@ def test_umma_probe(dev, mode):
     assert rel(d, ref) < 1e-5
 
 
-@pytest.mark.skipif(os.environ.get("YB_RUN_EXPERIMENTAL") != "1",
-                    reason="SM-pair GEMM is experimental: written without GPU time left, never run on hardware yet")
-@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (300, 512, 192), (4097, 768, 256), (1000, 3072, 3072)])
-def test_experimental_gemm_2cta_matches_fp32_reference(dev, M, N, K):
+@pytest.mark.parametrize("M,N,K,bn", [(256, 256, 64, 0), (300, 512, 192, 0), (4097, 768, 256, 0), (1000, 3072, 3072, 0),
+                                       (2310, 3072, 512, 0), (2310, 3072, 512, 224), (1500, 704, 320, 160), (513, 96, 128, 32),
+                                       (1029, 1184, 192, 192)])
+def test_gemm_pair_kernel_matches_1cta_kernel(dev, M, N, K, bn):
+    """SM-pair (`cta_group::2`) kernel, forced, against the 1-CTA kernel (bit-identical: same products, same fp32 accumulation
+    order along K) and fp32 — ragged M / N tails, runtime N tiles (auto and forced), every fused epilogue."""
     from yume_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
     a = torch.randn(M, K, generator=g).to(dev).bfloat16()
     w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev).bfloat16()
     b = torch.randn(N, generator=g).to(dev)
-    out = ops.gemm_2cta(a, w, b, torch.empty(M, N, device=dev, dtype=torch.bfloat16))
-    assert rel(out, a.float() @ w.float().t() + b) < KERNEL_TOL
+    one = ops.gemm(a, w, b, torch.empty(M, N, device=dev, dtype=torch.bfloat16), ops.YB_EPI_BF16, cta_pair=1)
+    two = ops.gemm(a, w, b, torch.full((M, N), 7.0, device=dev, dtype=torch.bfloat16), ops.YB_EPI_BF16, cta_pair=2, block_n=bn)
+    assert torch.equal(one, two)
+    assert rel(two, a.float() @ w.float().t() + b) < KERNEL_TOL
+    acc = a.float() @ w.float().t() + b
+    o = ops.gemm(a, w, b, torch.empty(M, N, device=dev, dtype=torch.bfloat16), ops.YB_EPI_GELU_BF16, cta_pair=2, block_n=bn)
+    assert rel(o, torch.nn.functional.gelu(acc, approximate="tanh")) < KERNEL_TOL
+    U = 3
+    gate = torch.randn(U, N, generator=g).to(dev)
+    tok = torch.randint(0, U, (M,), generator=g).to(dev, torch.int32)
+    x = torch.randn(M, N, generator=g).to(dev)
+    want = x + acc * gate[tok.long()]
+    ops.gemm(a, w, b, x, ops.YB_EPI_GATE_RES, gate=gate, tok_idx=tok, cta_pair=2, block_n=bn)
+    assert rel(x, want) < 1e-5
+    res = torch.randn(M, N, generator=g).to(dev).bfloat16()
+    o = ops.gemm(a, w, b, torch.empty(M, N, device=dev, dtype=torch.bfloat16), ops.YB_EPI_RES_BF16, res=res, cta_pair=2, block_n=bn)
+    assert rel(o, acc + res.float()) < KERNEL_TOL
+    o32 = ops.gemm(a, w, None, torch.empty(M, N, device=dev), ops.YB_EPI_F32, cta_pair=2, block_n=bn)
+    assert rel(o32, acc - b) < 1e-5
+
+
+def test_gemm_pair_kernel_split_layouts(dev):
+    """The Ulysses layouts through the SM-pair kernel: K-split A operand (a_split) and N-split output (n_split)."""
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(41)
+    P, Lp, Wh, N = 4, 300, 128, 512
+    a3 = torch.randn(P, Lp, Wh, generator=g).to(dev).bfloat16()                 # [P, Lp, Wh]: column k of row t = a3[k // Wh, t, k % Wh]
+    w = (torch.randn(N, P * Wh, generator=g) / math.sqrt(P * Wh)).to(dev).bfloat16()
+    a2 = a3.permute(1, 0, 2).reshape(Lp, P * Wh).contiguous()
+    want = ops.gemm(a2, w, None, torch.empty(Lp, N, device=dev, dtype=torch.bfloat16), ops.YB_EPI_BF16, cta_pair=1)
+    got = ops.gemm(a3, w, None, torch.empty(Lp, N, device=dev, dtype=torch.bfloat16), ops.YB_EPI_BF16, a_split=Wh,
+                   a_split_stride=Lp * Wh, shape=(Lp, P * Wh), cta_pair=2)
+    assert torch.equal(got, want)
+    send = torch.zeros(P, Lp, N // P, device=dev, dtype=torch.bfloat16)         # n_split: column block j -> send[j]
+    ops.gemm(a2, w, None, send, ops.YB_EPI_BF16, n_split=N // P, split_stride=Lp * (N // P), shape=(Lp, P * Wh), cta_pair=2)
+    assert torch.equal(send.permute(1, 0, 2).reshape(Lp, N), want)
 
 
 @pytest.mark.parametrize("shift", [1, 2, 3, 7, 8])
@@ -126,26 +162,6 @@ def _sdpa(q, k, v, heads):
     return o.transpose(0, 1).reshape(Lq, heads * 128)
 
 
-@pytest.mark.skipif(os.environ.get("YB_RUN_EXPERIMENTAL") != "1",
-                    reason="Q-in-TMEM attention is experimental: written without GPU time left, never run on hardware yet")
-@pytest.mark.parametrize("emu", [0, 2])
-@pytest.mark.parametrize("Lq,Lk,heads", [(128, 64, 1), (128, 128, 1), (300, 200, 2), (1000, 512, 3), (777, 1500, 2), (257, 257, 2)])
-def test_experimental_attention_q64_matches_fp32_reference(dev, Lq, Lk, heads, emu):
-    from yume_b200 import ops
-    g = torch.Generator(device="cpu").manual_seed(Lq * 7 + Lk + emu)
-    q = torch.randn(Lq, heads * 128, generator=g).to(dev).bfloat16()
-    k = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
-    v = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
-    out = ops.attention(q, k, v, torch.full_like(q, 5.0), heads, variant=2, emu=emu)
-    qh, kh, vh = (x.float().view(-1, heads, 128).transpose(0, 1) for x in (q, k, v))
-    ref = torch.softmax(qh @ kh.transpose(1, 2) / math.sqrt(128.0), dim=-1) @ vh
-    assert rel(out, ref.transpose(0, 1).reshape(Lq, heads * 128)) < KERNEL_TOL
-    acc = ops.attention(q, k, v, out.clone(), heads, variant=2, accumulate=True)     # out += result
-    assert rel(acc, 2 * ref.transpose(0, 1).reshape(Lq, heads * 128)) < 2 * KERNEL_TOL
-    spl = ops.attention(q, k, v, torch.full_like(q, 3.0), heads, variant=2, emu=emu, split=2)   # forced KV split (64-key tiles)
-    assert rel(spl, ref.transpose(0, 1).reshape(Lq, heads * 128)) < KERNEL_TOL
-
-
 @pytest.mark.parametrize("split", [2, 3, 4])
 @pytest.mark.parametrize("Lq,Lk,heads", [(300, 1000, 2), (1000, 777, 3), (257, 2049, 1), (512, 512, 2)])
 def test_attention_kv_split_matches_unsplit(dev, Lq, Lk, heads, split):
@@ -156,7 +172,7 @@ def test_attention_kv_split_matches_unsplit(dev, Lq, Lk, heads, split):
     k = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
     v = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
     one = ops.attention(q, k, v, torch.empty_like(q), heads, split=1)
-    two = ops.attention(q, k, v, torch.full_like(q, 9.0), heads, split=split)
+    two = ops.attention(q, k, v, torch.full_like(q, 9.0), heads, split=split, softmax=split % 3)   # every schedule once
     assert rel(two, one) < 3e-3                      # both bf16-rounded; segments change the fp32 summation order only
     qh, kh, vh = (x.float().view(-1, heads, 128).transpose(0, 1) for x in (q, k, v))
     ref = torch.softmax(qh @ kh.transpose(1, 2) / math.sqrt(128.0), dim=-1) @ vh
@@ -175,21 +191,29 @@ def test_attention_auto_tail_split_full_size_properties(dev):
     assert bool(torch.isfinite(b.float()).all()) and rel(b, a) < 3e-3
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+# (variant, softmax schedule): product kernel with the classic / deferred-max / deferred-max + bf16x2-exponential schedules
+# (include/yume_b200.h YB_ATT_SM_SHIFT), and the debug variant that stages P through shared memory
+ATT_MODES = [(0, 0), (0, 1), (0, 2), (1, 0)]
+# the bf16x2 schedule rounds the exponent argument to bf16 (attention.cu): zero-mean error of the order of P's own rounding
+ATT_TOL = {0: KERNEL_TOL, 1: KERNEL_TOL, 2: 6e-3}
+
+
+@pytest.mark.parametrize("variant,softmax", ATT_MODES)
 @pytest.mark.parametrize("Lq,Lk,heads", [(128, 128, 1), (300, 200, 2), (1000, 512, 3), (777, 1500, 2), (257, 257, 2),
                                          (1, 1, 1), (130, 769, 2)])
-def test_attention_matches_sdpa(dev, variant, Lq, Lk, heads):
+def test_attention_matches_sdpa(dev, variant, softmax, Lq, Lk, heads):
     from yume_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(Lq * 7 + Lk)
     qkv = torch.randn(max(Lq, Lk), 3 * heads * 128, generator=g).to(dev).bfloat16()
     q, k, v = qkv[:Lq, :heads * 128], qkv[:Lk, heads * 128:2 * heads * 128], qkv[:Lk, 2 * heads * 128:]
     out = torch.zeros(Lq, heads * 128, device=dev, dtype=torch.bfloat16)
-    ops.attention(q, k, v, out, heads, variant=variant)
+    ops.attention(q, k, v, out, heads, variant=variant, softmax=softmax)
     assert torch.isfinite(out.float()).all()
-    assert rel(out, _sdpa(q, k, v, heads)) < KERNEL_TOL
+    assert rel(out, _sdpa(q, k, v, heads)) < ATT_TOL[softmax]
 
 
-def test_attention_large_logits_and_accumulate(dev):
+@pytest.mark.parametrize("softmax", [0, 1, 2])
+def test_attention_large_logits_and_accumulate(dev, softmax):
     from yume_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(11)
     Lq, Lk, heads = 512, 1024, 2
@@ -197,13 +221,35 @@ def test_attention_large_logits_and_accumulate(dev):
     k = (torch.randn(Lk, heads * 128, generator=g) * 4).to(dev).bfloat16()
     v = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
     out = torch.zeros(Lq, heads * 128, device=dev, dtype=torch.bfloat16)
-    ops.attention(q, k, v, out, heads)            # row maxima jump by >> 2^8: exercises the lazy O rescale
+    ops.attention(q, k, v, out, heads, softmax=softmax)   # row maxima jump by >> 2^8: lazy O rescale / exactness guard paths
     ref = _sdpa(q, k, v, heads)
-    assert rel(out, ref) < KERNEL_TOL
+    assert rel(out, ref) < ATT_TOL[softmax]
     k2 = torch.randn(257, heads * 128, generator=g).to(dev).bfloat16()
     v2 = torch.randn(257, heads * 128, generator=g).to(dev).bfloat16()
-    ops.attention(q, k2, v2, out, heads, accumulate=True)
-    assert rel(out, ref + _sdpa(q, k2, v2, heads)) < 2 * KERNEL_TOL
+    ops.attention(q, k2, v2, out, heads, accumulate=True, softmax=softmax)
+    assert rel(out, ref + _sdpa(q, k2, v2, heads)) < 2 * ATT_TOL[softmax]
+
+
+@pytest.mark.parametrize("softmax", [1, 2])
+def test_attention_deferred_max_guard_paths(dev, softmax):
+    """Adversarial rows for the deferred-max schedules: the dominant key sits in the SECOND half of a LATE tile and beats
+    everything before it by ~2^100 (guard on the second half: wait for P.V of the first half, rescale, recompute), and in the
+    first half of another tile; a third set of rows has a key far BELOW the running max (underflow side)."""
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(13)
+    Lq, Lk, heads = 256, 1024, 1
+    q = torch.randn(Lq, 128, generator=g)
+    k = torch.randn(Lk, 128, generator=g) * 0.3
+    v = torch.randn(Lk, 128, generator=g)
+    qn = q / q.norm(dim=1, keepdim=True)
+    k[700] = qn[:64].mean(0) * 900.0        # tile 5, key 60 of the tile (first half) -> huge logit for rows 0..63
+    k[888] = qn[64:128].mean(0) * 1200.0    # tile 6, key 120 of the tile (second half) for rows 64..127
+    k[5] = -qn[128:192].mean(0) * 900.0     # a key far below everything for rows 128..191
+    q[:192] = qn[:192] * 40.0
+    q, k, v = q.to(dev).bfloat16(), k.to(dev).bfloat16(), v.to(dev).bfloat16()
+    out = ops.attention(q, k, v, torch.zeros(Lq, 128, device=dev, dtype=torch.bfloat16), heads, softmax=softmax)
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, _sdpa(q, k, v, heads)) < ATT_TOL[softmax]
 
 
 def test_elementwise_kernels(dev):
@@ -237,6 +283,16 @@ def test_elementwise_kernels(dev):
     want[L - 100:] = n[L - 100:]                      # tokens past the grid are not rotated (model.py:73)
     assert rel(qkv[:, :C], want) < KERNEL_TOL
     assert torch.equal(qkv[:, 2 * C:], v0)            # neighbours untouched
+    # q and k in ONE launch (yb_qk_norm_rope) == the two single launches, bit for bit (same arithmetic, same order)
+    for Cw in (3072, 5120, 1024, 256, 384):             # warp-per-row instances and the general fallback (384)
+        qkv2 = torch.randn(333, 3 * Cw, generator=g).to(dev).bfloat16()
+        ref2 = qkv2.clone()
+        w_q, w_k = (torch.rand(Cw, generator=g) + 0.5).to(dev), (torch.rand(Cw, generator=g) + 0.5).to(dev)
+        rope2 = torch.randn(333, D // 2, 2, generator=g).to(dev)
+        ops.rmsnorm_rope(ref2[:, :Cw], w_q, rope2, D, rope_len=300)
+        ops.rmsnorm_rope(ref2[:, Cw:2 * Cw], w_k, rope2, D, rope_len=300)
+        ops.qk_norm_rope(qkv2[:, :Cw], qkv2[:, Cw:2 * Cw], w_q, w_k, rope2, D, rope_len=300)
+        assert torch.equal(qkv2, ref2), Cw
     # small fp32 pieces
     t = torch.tensor([0.0, 999.0, 500.5], device=dev)
     half = 128

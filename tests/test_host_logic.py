@@ -17,13 +17,13 @@ ROOT = Path(__file__).resolve().parents[1]
 
 def test_library_exports_every_header_symbol():
     header = (ROOT / "include" / "yume_b200.h").read_text()
-    declared = set(re.findall(r"^\s*int\s+(yb_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|long long)\s+(yb_\w+)\s*\(", header, flags=re.M))
     assert declared, "no declarations parsed"
     lib = yume_b200.load()
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/yume_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), "ctypes signature table and header disagree"
-    assert lib.yb_abi_version() == 1
+    assert lib.yb_abi_version() == 2
 
 
 def test_ops_have_no_cpu_path():

@@ -217,6 +217,11 @@ def sec_elementwise():
     qb = torch.randn(L2, 3 * Cdim, device=dev).bfloat16(); rp = torch.randn(L2, 64, 2, device=dev)
     ms = timeit(lambda: ops.rmsnorm_rope(qb[:, :Cdim], wq, rp, D))
     print(f"rmsnorm_rope L={L2}: {ms*1e3:.1f} us = {L2*Cdim*4/ms/1e6:.0f} GB/s")
+    ms = timeit(lambda: ops.qk_norm_rope(qb[:, :Cdim], qb[:, Cdim:2 * Cdim], wq, wq, rp, D))
+    print(f"qk_norm_rope (q+k, one launch) L={L2}: {ms*1e3:.1f} us = {L2*Cdim*8/ms/1e6:.0f} GB/s")
+    wln = torch.randn(Cdim, device=dev); bln = torch.randn(Cdim, device=dev)
+    ms = timeit(lambda: ops.ln_modulate(xb, ob, None, None, None, wln, bln))
+    print(f"ln affine L={L2}: {ms*1e3:.1f} us = {L2*Cdim*6/ms/1e6:.0f} GB/s")
 
 
 def sec_atttune():
@@ -248,33 +253,52 @@ def sec_attsplit():
         print(line, flush=True)
 
 
-def sec_att64():
-    """EXPERIMENTAL Q-in-TMEM / 64-key-tile attention against the product kernel at the 5B shape (short timeout!)."""
-    heads, L = 24, 18480
-    qkv = torch.randn(L, 3 * heads * 128, device=dev).bfloat16()
-    q = qkv[:, : heads * 128]; k = qkv[:, heads * 128: 2 * heads * 128]; v = qkv[:, 2 * heads * 128:]
-    o0, o1 = torch.empty(L, heads * 128, device=dev, dtype=torch.bfloat16), torch.empty(L, heads * 128, device=dev, dtype=torch.bfloat16)
-    fl = 4.0 * L * L * heads * 128
-    t0 = timeit(lambda: ops.attention(q, k, v, o0, heads), 5)
-    print(f"att64: product kernel {t0:.3f} ms = {fl/t0/1e9:.0f} TF/s", flush=True)
-    for emu in (0, 1, 2, 3):
-        t1 = timeit(lambda: ops.attention(q, k, v, o1, heads, variant=2, emu=emu), 5)
-        print(f"att64: q64 emu={emu} {t1:.3f} ms = {fl/t1/1e9:.0f} TF/s   rel(q64, product) {rel(o1, o0)}", flush=True)
+def sec_attmodes():
+    """Softmax schedules of the attention kernel at the 5B self-attention shape, the 8-GPU per-rank shape and 14B."""
+    for heads, L in ((24, 18480), (3, 18480), (40, 21930)):
+        qkv = torch.randn(L, 3 * heads * 128, device=dev).bfloat16()
+        q = qkv[:, : heads * 128]; k = qkv[:, heads * 128: 2 * heads * 128]; v = qkv[:, 2 * heads * 128:]
+        out = torch.empty(L, heads * 128, device=dev, dtype=torch.bfloat16)
+        idx = torch.randint(0, L, (256,), device=dev)
+        ref = sdpa_ref(q[idx].contiguous(), k, v, heads)
+        fl = 4.0 * L * L * heads * 128
+        for sm, emu in ((0, 0), (1, 0), (1, 1), (1, 3), (2, 0)):
+            ms = min(timeit(lambda: ops.attention(q, k, v, out, heads, emu=emu, softmax=sm), n=5) for _ in range(3))
+            print(f"attmodes heads={heads} L={L} softmax={sm} emu={emu}: {ms:.3f} ms = {fl/ms/1e9:.0f} TF/s   rel/max {rel(out[idx], ref)}", flush=True)
+    try:
+        heads, L = 24, 18480
+        qkv = torch.randn(L, 3 * heads * 128, device=dev).bfloat16()
+        q = qkv[:, : heads * 128]; k = qkv[:, heads * 128: 2 * heads * 128]; v = qkv[:, 2 * heads * 128:]
+        fl = 4.0 * L * L * heads * 128
+        qh = q.view(L, heads, 128).transpose(0, 1)[None].contiguous(); kh = k.view(L, heads, 128).transpose(0, 1)[None].contiguous(); vh = v.view(L, heads, 128).transpose(0, 1)[None].contiguous()
+        ms = min(timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qh, kh, vh), n=5) for _ in range(3))
+        print(f"attmodes comparator torch SDPA (cuDNN/flash backend) self 5B: {ms:.3f} ms = {fl/ms/1e9:.0f} TF/s", flush=True)
+    except Exception as e:
+        print("SDPA comparator failed:", e)
 
 
-def sec_gemm2cta():
-    """EXPERIMENTAL SM-pair GEMM against the product GEMM and cuBLAS on the DiT shapes (run with a short timeout)."""
-    L, C, F = 18480, 3072, 14336
-    for name, (M, N, K) in (("qkv", (L, 3 * C, C)), ("o", (L, C, C)), ("ffn1", (L, F, C)), ("ffn2", (L, C, F))):
-        a = torch.randn(M, K, device=dev).bfloat16()
-        w = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
-        o1, o2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16), torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        fl = 2.0 * M * N * K
-        t1 = timeit(lambda: ops.gemm(a, w, None, o1, ops.YB_EPI_BF16), 5)
-        t2 = timeit(lambda: ops.gemm_2cta(a, w, None, o2), 5)
-        t3 = timeit(lambda: torch.matmul(a, w.t()), 5)
-        print(f"gemm2cta {name}: 1-CTA {t1:.3f} ms ({fl/t1/1e9:.0f} TF/s)  2-CTA {t2:.3f} ms ({fl/t2/1e9:.0f} TF/s)  "
-              f"cuBLAS {t3:.3f} ms ({fl/t3/1e9:.0f} TF/s)  rel(2cta,1cta) {rel(o2, o1)}", flush=True)
+def sec_gemmpair():
+    """SM-pair (cta_group::2) GEMM against the 1-CTA kernel and cuBLAS: the DiT shapes at N = 1 and the per-rank shapes of 8-GPU
+    Ulysses (M = 2310), plain and GATE_RES epilogues, automatic and forced N tiles."""
+    C, F = 3072, 14336
+    for L in (18480, 2310):
+        for name, (M, N, K) in (("qkv", (L, 3 * C, C)), ("o", (L, C, C)), ("ffn1", (L, F, C)), ("ffn2", (L, C, F))):
+            a = torch.randn(M, K, device=dev).bfloat16()
+            w = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
+            o1, o2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16), torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            fl = 2.0 * M * N * K
+            t1 = timeit(lambda: ops.gemm(a, w, None, o1, ops.YB_EPI_BF16, cta_pair=1), 5)
+            t2 = timeit(lambda: ops.gemm(a, w, None, o2, ops.YB_EPI_BF16, cta_pair=2), 5)
+            t256 = timeit(lambda: ops.gemm(a, w, None, o2, ops.YB_EPI_BF16, cta_pair=2, block_n=256), 5)
+            t3 = timeit(lambda: torch.matmul(a, w.t()), 5)
+            line = (f"gemmpair L={L} {name}: 1-CTA {t1:.3f} ms ({fl/t1/1e9:.0f} TF/s)  pair(auto bn) {t2:.3f} ms ({fl/t2/1e9:.0f} TF/s)  "
+                    f"pair(bn=256) {t256:.3f} ms ({fl/t256/1e9:.0f})  cuBLAS {t3:.3f} ms ({fl/t3/1e9:.0f} TF/s)  equal={torch.equal(o1, o2)}")
+            if name in ("o", "ffn2"):
+                x = torch.randn(M, N, device=dev); gate = torch.randn(1, N, device=dev)
+                g1 = timeit(lambda: ops.gemm(a, w, None, x, ops.YB_EPI_GATE_RES, gate=gate, cta_pair=1), 5)
+                g2 = timeit(lambda: ops.gemm(a, w, None, x, ops.YB_EPI_GATE_RES, gate=gate, cta_pair=2), 5)
+                line += f"  GATE_RES: 1-CTA {g1:.3f} ms ({fl/g1/1e9:.0f})  pair {g2:.3f} ms ({fl/g2/1e9:.0f})"
+            print(line, flush=True)
 
 
 def sec_atttrace():
@@ -287,7 +311,7 @@ def sec_atttrace():
     lib = _lib.load()
     for _ in range(3):
         rc = lib.yb_attention_ex(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(),
-                                 out.stride(0), L, L, heads, 1.0 / math.sqrt(128.0), 0, tr.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                                 out.stride(0), L, L, heads, 1.0 / math.sqrt(128.0), 0, None, 0, tr.data_ptr(), torch.cuda.current_stream().cuda_stream)
         assert rc == 0
     torch.cuda.synchronize()
     t = tr.view(32, 32).cpu()
@@ -309,9 +333,9 @@ def sec_atttrace():
     print("raw rows 0..2:", (t[:3] - base).tolist())
 
 
-SECTIONS = {"att64": sec_att64, "gemm2cta": sec_gemm2cta, "attsplit": sec_attsplit, "atttrace": sec_atttrace, "atttune": sec_atttune, "probe": sec_probe, "gemm": sec_gemm, "attention": sec_attention, "elementwise": sec_elementwise}
+SECTIONS = {"attmodes": sec_attmodes, "gemmpair": sec_gemmpair, "attsplit": sec_attsplit, "atttrace": sec_atttrace, "atttune": sec_atttune, "probe": sec_probe, "gemm": sec_gemm, "attention": sec_attention, "elementwise": sec_elementwise}
 if __name__ == "__main__":
-    names = sys.argv[1:] or [n for n in SECTIONS if n not in ("gemm2cta", "att64")]   # experimental sections only on request
+    names = sys.argv[1:] or [n for n in SECTIONS if n not in ("gemmpair", "attmodes")]   # experimental sections only on request
     print(torch.cuda.get_device_name(0))
     for n in names:
         print(f"===== {n} =====", flush=True)

@@ -20,6 +20,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    if os.environ.get("YB_ATT_FORCE_SPLIT"):          # test hook: drive the KV split + peer-scatter combine path
+        from yume_b200 import _lib
+        _lib.load().yb_debug_force_split(int(os.environ["YB_ATT_FORCE_SPLIT"]))
     bad = ran = 0
     for fname in ("wan23_tiny.pt", "wan21_tiny.pt", "wan23_h8.pt", "wan21_h8.pt"):   # 2-head and 8-head models
         g = torch.load(ROOT / "tests" / "golden" / fname, weights_only=False)

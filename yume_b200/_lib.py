@@ -9,6 +9,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libyume_b200.so"
 
 YB_EPI_BF16, YB_EPI_GELU_BF16, YB_EPI_F32, YB_EPI_GATE_RES, YB_EPI_GELU_ERF_BF16, YB_EPI_RES_BF16 = 0, 1, 2, 3, 4, 5
 YB_ATT_P_SMEM, YB_ATT_ACCUMULATE = 1, 2
+YB_ATT_EMU_SHIFT, YB_ATT_SPLIT_SHIFT, YB_ATT_SM_SHIFT = 2, 4, 8
 
 _ERRORS = {
     -1: "YB_ERR_ARG (null pointer / bad enum / non-positive size)",
@@ -28,6 +29,7 @@ class GemmArgs(C.Structure):
     """Mirror of `struct yb_gemm_args` (include/yume_b200.h)."""
 
     _fields_ = [
+        ("struct_bytes", C.c_uint), ("cta_pair", C.c_int),
         ("A", C.c_void_p), ("B", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p),
         ("gate", C.c_void_p), ("tok_idx", C.c_void_p),
         ("lda", C.c_longlong), ("ldb", C.c_longlong), ("ldo", C.c_longlong), ("gate_ld", C.c_longlong),
@@ -41,6 +43,7 @@ class Conv3dArgs(C.Structure):
     """Mirror of `struct yb_conv3d_args`."""
 
     _fields_ = [
+        ("struct_bytes", C.c_uint), ("reserved", C.c_int),
         ("xpad", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p), ("res", C.c_void_p),
         ("ldo", C.c_longlong), ("res_ld", C.c_longlong),
         ("T", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cp", C.c_int), ("Cout", C.c_int), ("epilogue", C.c_int),
@@ -60,7 +63,7 @@ SIGNATURES = {
     "yb_masked_softmax": (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp]),
     "yb_nchw_to_nhwc_bf16": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
     "yb_nhwc_to_nchw_f32": (_i, [_vp, _ll, _vp, _ll, _i, _vp]),
-    "yb_gemm_bf16_2cta": (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _vp]),
+    "yb_gemm_plan": (_i, [_i, _i, _i, C.POINTER(C.c_int)]),
     "yb_conv3d_plan": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(C.c_int)]),
     "yb_attention_plan": (_i, [_i, _i, _i, _i, _i, C.POINTER(C.c_int)]),
     "yb_nhwc_to_nchw_f32_clamp": (_i, [_vp, _ll, _vp, _ll, _i, C.c_float, C.c_float, _vp]),
@@ -73,9 +76,12 @@ SIGNATURES = {
     "yb_rmsnorm_rope_pieces": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "yb_qk_norm_rope": (_i, [_vp, _vp, _ll, _i, _ll, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "yb_attention": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _f, _i, _vp]),
-    "yb_attention_ex": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _f, _i, _vp, _vp]),
+    "yb_attention_ex": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _f, _i, _vp, _ll, _vp, _vp]),
+    "yb_attention_workspace_bytes": (_ll, [_i, _i, _i, _i, _i]),
+    "yb_debug_force_split": (_i, [_i]),
     "yb_sp_scatter_qkv": (_i, [_vp, _ll, _vp, _vp, _vp, _i, _i, _i, _i, _f, C.POINTER(C.c_void_p), _i, _i, _i, _vp]),
-    "yb_attention_sp": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, C.POINTER(C.c_void_p), _ll, _i, _i, _i, _f, _i, _i, _i, _vp]),
+    "yb_attention_sp": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, C.POINTER(C.c_void_p), _ll, _i, _i, _i, _f, _i, _i, _i, _i, _vp, _ll,
+                             _vp]),
     "yb_patchify": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
     "yb_bcast_add": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "yb_unpatchify": (_i, [_vp, _ll, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -15,7 +15,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIB = CSRC / "libyume_b200.so"
-SOURCES = ["gemm.cu", "attention.cu", "elementwise.cu", "vae_elementwise.cu", "probe.cu", "gemm2cta.cu", "attention64.cu"]
+SOURCES = ["gemm.cu", "attention.cu", "elementwise.cu", "vae_elementwise.cu", "probe.cu"]
 HEADERS = ["yb_ptx.cuh", "yb_host.h", "../../include/yume_b200.h"]
 
 NVCC_FLAGS = [
@@ -63,11 +63,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(str(obj))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *objs]
+    tmp = LIB.with_suffix(".so.tmp")          # link beside the target, then rename: a reader never sees a half-written library
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *objs]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("nvcc link failed")
+    os.replace(tmp, LIB)
     (CSRC / "build.log").write_text("\n".join(log))
     stamp.write_text(digest)
     if verbose:

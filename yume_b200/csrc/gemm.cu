@@ -52,6 +52,7 @@ struct GemmParams {
                                 // (kt-1, kh/2, kw/2) when it is TMA out-of-bounds zero fill on the unpadded input
   int out_t_mul, out_t_add;     // output frame of input frame t = t*out_t_mul + out_t_add (time_conv interleave)
   int num_m_tiles, num_n_tiles;
+  int block_n, stages;          // SM-pair kernel (gemm_pair_kernel): runtime N tile (multiple of 32, <= 256) and ring depth
 };
 
 // CONVW = 1: kw-fused implicit-GEMM conv. The three kw taps of one (dt, dh, channel-chunk) group read the SAME TMA halo
@@ -86,6 +87,120 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m_tiles, int num_n
   const int n_in_group = min(GEMM_GROUP_N, num_n_tiles - n_first);
   m_tile = r / n_in_group;
   n_tile = n_first + (r - m_tile * n_in_group);
+}
+
+// One 32-column chunk of an output tile: r = the accumulator row of tile row `lane` (TMEM lane), my_row / my_tok = logical output
+// row and gate-table row of that tile row (-1 = none). TMEM -> registers (lane = row) -> per-warp smem transpose (row pitch 36
+// floats: conflict-free for both the row-per-lane writes and the row-segment reads) -> fused math -> global, so that every global
+// access is a full 64/128-byte row segment shared by 4/8 adjacent lanes instead of 32 different rows per instruction.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], int col0, int my_row, int my_tok,
+                                               float* stage, int lane) {
+  constexpr bool kBf16Out = (EPI == YB_EPI_BF16 || EPI == YB_EPI_GELU_BF16 || EPI == YB_EPI_GELU_ERF_BF16 ||
+                             EPI == YB_EPI_RES_BF16);
+  float4* st = reinterpret_cast<float4*>(stage + lane * 36);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    st[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                        __uint_as_float(r[4 * i + 3]));
+  __syncwarp();
+  if (col0 < p.N) {
+    if (kBf16Out) {
+      const int cq = (lane & 3) * 8;  // this lane's 8 columns of the 32-column chunk
+      float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (p.bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq + 4));
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+      }
+      // optional N-split output (Ulysses layout): column block j of width n_split goes to out + j*split_stride
+      long long col_off = col0 + cq;
+      if (p.n_split > 0) col_off = static_cast<long long>(col0 / p.n_split) * p.split_stride + (col0 % p.n_split) + cq;
+      __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + col_off;
+      uint4 resv[4];
+      if (EPI == YB_EPI_RES_BF16) {  // residual loads first (they may alias the stores for all the compiler knows)
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rowi = __shfl_sync(0xffffffffu, my_row, it * 8 + (lane >> 2));
+          resv[it] = make_uint4(0u, 0u, 0u, 0u);
+          if (rowi >= 0)
+            resv[it] = *reinterpret_cast<const uint4*>(p.res + static_cast<long long>(rowi) * p.res_ld + col0 + cq);
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + (lane >> 2);
+        const int rowi = __shfl_sync(0xffffffffu, my_row, rr);
+        const float4 a0 = *reinterpret_cast<const float4*>(stage + rr * 36 + cq);
+        const float4 a1 = *reinterpret_cast<const float4*>(stage + rr * 36 + cq + 4);
+        float v[8] = {a0.x + b[0], a0.y + b[1], a0.z + b[2], a0.w + b[3],
+                      a1.x + b[4], a1.y + b[5], a1.z + b[6], a1.w + b[7]};
+        if (EPI == YB_EPI_GELU_BF16) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = gelu_tanh(v[i]);
+        }
+        if (EPI == YB_EPI_GELU_ERF_BF16) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.7071067811865476f));
+        }
+        if (EPI == YB_EPI_RES_BF16) {
+          const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&resv[it]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(rh[i]);
+            v[2 * i] += f.x;
+            v[2 * i + 1] += f.y;
+          }
+        }
+        if (rowi >= 0) {
+          uint4 w;
+          w.x = pack_bf16x2(v[0], v[1]);
+          w.y = pack_bf16x2(v[2], v[3]);
+          w.z = pack_bf16x2(v[4], v[5]);
+          w.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(obase + static_cast<long long>(rowi) * p.ldo) = w;
+        }
+      }
+    } else {
+      const int cq = (lane & 7) * 4;  // this lane's 4 columns
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq));
+      float* obase = reinterpret_cast<float*>(p.out) + col0 + cq;
+      // all loads first, then all stores: the residual rows may alias as far as the compiler can tell, so a
+      // load placed after a store would serialise one L2 round trip per row
+      float4 xv[8], gv[8];
+      int rowv[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + (lane >> 3);
+        const int tok = __shfl_sync(0xffffffffu, my_tok, rr);
+        rowv[it] = __shfl_sync(0xffffffffu, my_row, rr);
+        xv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gv[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (EPI == YB_EPI_GATE_RES && rowv[it] >= 0) {
+          xv[it] = *reinterpret_cast<const float4*>(obase + static_cast<long long>(rowv[it]) * p.ldo);
+          if (p.gate)
+            gv[it] = __ldg(reinterpret_cast<const float4*>(p.gate + static_cast<long long>(tok) * p.gate_ld + col0 + cq));
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + (lane >> 3);
+        float4 a = *reinterpret_cast<const float4*>(stage + rr * 36 + cq);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        if (rowv[it] >= 0) {
+          float4* o4 = reinterpret_cast<float4*>(obase + static_cast<long long>(rowv[it]) * p.ldo);
+          if (EPI == YB_EPI_F32) {
+            *o4 = a;
+          } else {  // YB_EPI_GATE_RES
+            float4 x = xv[it];
+            x.x += a.x * gv[it].x; x.y += a.y * gv[it].y; x.z += a.z * gv[it].z; x.w += a.w * gv[it].w;
+            *o4 = x;
+          }
+        }
+      }
+    }
+  }
 }
 
 template <int BLOCK_N, int EPI, int CONVW = 0>
@@ -284,8 +399,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // row segment shared by 4/8 adjacent lanes instead of 32 different rows per instruction.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     float* stage = reinterpret_cast<float*>(smem + Cfg::STAGE_OFF) + quad * (32 * 36);
-    constexpr bool kBf16Out = (EPI == YB_EPI_BF16 || EPI == YB_EPI_GELU_BF16 || EPI == YB_EPI_GELU_ERF_BF16 ||
-                               EPI == YB_EPI_RES_BF16);
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       int m_tile, n_tile;
@@ -327,110 +440,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint32_t r[32];
         tmem_ld32(t_row + c * 32, r);
         tmem_ld_wait();
-        const int col0 = n_tile * BLOCK_N + c * 32;
-        float4* st = reinterpret_cast<float4*>(stage + lane * 36);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          st[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                              __uint_as_float(r[4 * i + 3]));
-        __syncwarp();
-        if (col0 < p.N) {
-          if (kBf16Out) {
-            const int cq = (lane & 3) * 8;  // this lane's 8 columns of the 32-column chunk
-            float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (p.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq + 4));
-              b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
-            }
-            // optional N-split output (Ulysses layout): column block j of width n_split goes to out + j*split_stride
-            long long col_off = col0 + cq;
-            if (p.n_split > 0) col_off = static_cast<long long>(col0 / p.n_split) * p.split_stride + (col0 % p.n_split) + cq;
-            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + col_off;
-            uint4 resv[4];
-            if (EPI == YB_EPI_RES_BF16) {  // residual loads first (they may alias the stores for all the compiler knows)
-#pragma unroll
-              for (int it = 0; it < 4; ++it) {
-                const int rowi = __shfl_sync(0xffffffffu, my_row, it * 8 + (lane >> 2));
-                resv[it] = make_uint4(0u, 0u, 0u, 0u);
-                if (rowi >= 0)
-                  resv[it] = *reinterpret_cast<const uint4*>(p.res + static_cast<long long>(rowi) * p.res_ld + col0 + cq);
-              }
-            }
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int rr = it * 8 + (lane >> 2);
-              const int rowi = __shfl_sync(0xffffffffu, my_row, rr);
-              const float4 a0 = *reinterpret_cast<const float4*>(stage + rr * 36 + cq);
-              const float4 a1 = *reinterpret_cast<const float4*>(stage + rr * 36 + cq + 4);
-              float v[8] = {a0.x + b[0], a0.y + b[1], a0.z + b[2], a0.w + b[3],
-                            a1.x + b[4], a1.y + b[5], a1.z + b[6], a1.w + b[7]};
-              if (EPI == YB_EPI_GELU_BF16) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = gelu_tanh(v[i]);
-              }
-              if (EPI == YB_EPI_GELU_ERF_BF16) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.7071067811865476f));
-              }
-              if (EPI == YB_EPI_RES_BF16) {
-                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&resv[it]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 f = __bfloat1622float2(rh[i]);
-                  v[2 * i] += f.x;
-                  v[2 * i + 1] += f.y;
-                }
-              }
-              if (rowi >= 0) {
-                uint4 w;
-                w.x = pack_bf16x2(v[0], v[1]);
-                w.y = pack_bf16x2(v[2], v[3]);
-                w.z = pack_bf16x2(v[4], v[5]);
-                w.w = pack_bf16x2(v[6], v[7]);
-                *reinterpret_cast<uint4*>(obase + static_cast<long long>(rowi) * p.ldo) = w;
-              }
-            }
-          } else {
-            const int cq = (lane & 7) * 4;  // this lane's 4 columns
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq));
-            float* obase = reinterpret_cast<float*>(p.out) + col0 + cq;
-            // all loads first, then all stores: the residual rows may alias as far as the compiler can tell, so a
-            // load placed after a store would serialise one L2 round trip per row
-            float4 xv[8], gv[8];
-            int rowv[8];
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + (lane >> 3);
-              const int tok = __shfl_sync(0xffffffffu, my_tok, rr);
-              rowv[it] = __shfl_sync(0xffffffffu, my_row, rr);
-              xv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-              gv[it] = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (EPI == YB_EPI_GATE_RES && rowv[it] >= 0) {
-                xv[it] = *reinterpret_cast<const float4*>(obase + static_cast<long long>(rowv[it]) * p.ldo);
-                if (p.gate)
-                  gv[it] = __ldg(reinterpret_cast<const float4*>(p.gate + static_cast<long long>(tok) * p.gate_ld + col0 + cq));
-              }
-            }
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + (lane >> 3);
-              float4 a = *reinterpret_cast<const float4*>(stage + rr * 36 + cq);
-              a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-              if (rowv[it] >= 0) {
-                float4* o4 = reinterpret_cast<float4*>(obase + static_cast<long long>(rowv[it]) * p.ldo);
-                if (EPI == YB_EPI_F32) {
-                  *o4 = a;
-                } else {  // YB_EPI_GATE_RES
-                  float4 x = xv[it];
-                  x.x += a.x * gv[it].x; x.y += a.y * gv[it].y; x.z += a.z * gv[it].z; x.w += a.w * gv[it].w;
-                  *o4 = x;
-                }
-              }
-            }
-          }
-        }
+        epilogue_chunk<EPI>(p, r, n_tile * BLOCK_N + c * 32, my_row, my_tok, stage, lane);
         __syncwarp();
       }
       tc_fence_before();
@@ -446,20 +456,203 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// SM-pair GEMM (`tcgen05.mma.cta_group::2`): a cluster of two CTAs owns one 256 x block_n output tile. CTA r of the pair holds rows
+// [r*128, r*128+128) of the tile (its own A rows, its own accumulator lanes) and stages HALF of the B tile; one MMA instruction
+// issued by the leader CTA multiplies 256 x block_n x 16 across both SMs, so each SM fetches 16 KB + block_n*64 B of operands per
+// 64-wide k-step instead of 16 KB + block_n*128 B — the operand fetch from shared memory is what holds 1-CTA MMAs below the math
+// rate (profiles/README.md). Measured on the DiT shapes: 1474-1505 TFLOP/s against 1381-1408 for the 1-CTA kernel (cuBLAS, which
+// pairs SMs too: 1534-1665), results bit-identical (profiles/r02_gemm_pair.md).
+//   warp 0      TMA producer (both CTAs): own 128x64 A tile + own half of the B tile per k-step; completion bytes of BOTH CTAs are
+//               credited to the LEADER's full barrier (2-SM TMA form)
+//   warp 1      MMA issuer (leader CTA only): M = 256, N = block_n, K = 16 x4 per stage; commits are multicast to both CTAs'
+//               empty / tmem_full barriers
+//   warps 2..5  epilogue (both CTAs): own 128 rows, the same fused epilogues as the 1-CTA kernel; they arrive on the LEADER's
+//               tmem_empty barrier (count 256)
+// block_n is a RUNTIME multiple of 32 (<= 256): the host picks the N tile that minimises waves x tile width on the 74 SM pairs
+// (M = 2310 x N = 3072, the 8-GPU o-projection: 120 tiles of 256x256 are 1.62 waves; 140 tiles of 256x224 fill two waves exactly
+// 12.5 % sooner). Accumulators are double buffered at TMEM columns 0 and 256.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int PAIR_EPI_STAGE_BYTES = 4 * 32 * 36 * 4;
+constexpr int PAIR_MAX_STAGES = 8;
+__host__ __device__ constexpr int pair_stage_bytes(int block_n) { return GEMM_BLOCK_M * GEMM_BLOCK_K * 2 + (block_n / 2) * GEMM_BLOCK_K * 2; }
+__host__ __device__ constexpr int pair_bar_off(int block_n, int stages) { return stages * pair_stage_bytes(block_n); }
+__host__ __device__ constexpr int pair_smem_bytes(int block_n, int stages) {
+  return pair_bar_off(block_n, stages) + 256 + PAIR_EPI_STAGE_BYTES + 1024;
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int block_n = p.block_n, stages = p.stages;
+  const int stage_bytes = pair_stage_bytes(block_n);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + pair_bar_off(block_n, stages));   // used in the leader CTA only
+  uint64_t* empty_bar = full_bar + PAIR_MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + PAIR_MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;                                                     // used in the leader CTA only
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int tile_first = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;            // tiles of 256 x block_n
+  const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 256);   // 4 epilogue warps of each CTA of the pair
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta(tmem_ptr, 512);   // same warp and same smem slot in both CTAs
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // every barrier of the pair exists before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+        int m_tile, n_tile;
+        tile_coords(tile, p.num_m_tiles, p.num_n_tiles, m_tile, n_tile);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_bytes;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
+          const int kcol = kb * GEMM_BLOCK_K;
+          const int chunk = kcol / p.a_split;      // K-split A (Ulysses receive buffer): see the 1-CTA producer
+          tma_load_3d_2cta(sa, &tmA, &full_bar[stage], kcol - chunk * p.a_split, (m_tile * 2 + rank) * GEMM_BLOCK_M, chunk);
+          tma_load_2d_2cta(sa + GEMM_BLOCK_M * GEMM_BLOCK_K * 2, &tmB, &full_bar[stage], kcol,
+                           n_tile * block_n + rank * (block_n / 2));
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(256, block_n, 0, 0);
+      int stage = 0, local = 0;
+      uint32_t phase = 0;
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++local) {
+        const int acc = local & 1;
+        mbar_wait_cluster(&tmem_empty[acc], ((local >> 1) & 1) ^ 1);   // arrivals come from both CTAs
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + GEMM_BLOCK_M * GEMM_BLOCK_K * 2, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) umma_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_2cta(&empty_bar[stage]);        // frees the slot in BOTH CTAs
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2cta(&tmem_full[acc]);            // accumulator ready in BOTH CTAs
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    float* stage = reinterpret_cast<float*>(smem + pair_bar_off(block_n, stages) + 256) + quad * (32 * 36);
+    int local = 0;
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++local) {
+      int m_tile, n_tile;
+      tile_coords(tile, p.num_m_tiles, p.num_n_tiles, m_tile, n_tile);
+      const int acc = local & 1;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
+      const int row = (m_tile * 2 + rank) * GEMM_BLOCK_M + quad * 32 + lane;
+      const int my_row = row < p.M ? row : -1;
+      const int ncols = min(block_n, p.N - n_tile * block_n);
+      if (EPI == YB_EPI_GATE_RES && my_row >= 0) {   // pull the (cold) residual rows of this tile into L2 under the main loop
+        const char* xrow = reinterpret_cast<const char*>(reinterpret_cast<const float*>(p.out) +
+                                                         static_cast<long long>(my_row) * p.ldo + n_tile * block_n);
+        for (int b = 0; b < ncols * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow + b));
+      }
+      int my_tok = 0;
+      if (EPI == YB_EPI_GATE_RES && p.gate != nullptr && p.tok_idx != nullptr && my_row >= 0) my_tok = p.tok_idx[my_row];
+      mbar_wait(&tmem_full[acc], (local >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < block_n / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c * 32, r);
+        tmem_ld_wait();
+        epilogue_chunk<EPI>(p, r, n_tile * block_n + c * 32, my_row, my_tok, stage, lane);
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive_leader(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
+// N tile of the SM-pair kernel for an [M, N] output on `clusters` SM pairs: minimise (waves x tile width); ties go to the
+// wider tile (fewer B re-reads, longer MMAs). Host arithmetic only — exported as yb_gemm_plan for the CPU test-suite.
+static int pair_block_n(int M, int N, int clusters) {
+  const int m_tiles = (M + 255) / 256;
+  int best_bn = 256;
+  long long best_cost = -1;
+  for (int bn = 256; bn >= 128; bn -= 32) {
+    if (bn > 128 && N < bn) continue;
+    const long long tiles = static_cast<long long>(m_tiles) * ((N + bn - 1) / bn);
+    const long long waves = (tiles + clusters - 1) / clusters;
+    const long long cost = waves * (bn + 8);          // + a per-tile constant: pipeline fill / accumulator hand-off
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_bn = bn;
+    }
+  }
+  return best_bn;
+}
+
+template <int EPI>
+static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_pair_kernel<EPI>;
+  static bool attr_set[kMaxDevices] = {false};
+  if (int rc = ensure_dynamic_smem(kern, 227 * 1024, attr_set, "gemm_pair")) return rc;
+  p.num_m_tiles = (p.M + 255) / 256;
+  p.num_n_tiles = (p.N + p.block_n - 1) / p.block_n;
+  int stages = (227 * 1024 - 256 - PAIR_EPI_STAGE_BYTES - 1024) / pair_stage_bytes(p.block_n);
+  p.stages = stages > PAIR_MAX_STAGES ? PAIR_MAX_STAGES : stages;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+  kern<<<2 * clusters, GEMM_THREADS, pair_smem_bytes(p.block_n, p.stages), stream>>>(tmA, tmB, p);
+  return check_launch("gemm_pair");
+}
+
 template <int BLOCK_N, int EPI, int CONVW = 0>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, CONVW>;
   auto kern = gemm_kernel<BLOCK_N, EPI, CONVW>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      fprintf(stderr, "yume_b200: gemm smem attribute failed: %s\n", cudaGetErrorString(e));
-      (void)cudaGetLastError();
-      return YB_ERR_LAUNCH;
-    }
-    attr_set = true;
-  }
+  static bool attr_set[kMaxDevices] = {false};
+  if (int rc = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_set, "gemm")) return rc;
   if (!p.conv) p.num_m_tiles = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
@@ -498,6 +691,16 @@ static void conv_plan(int T, int H, int W, int block_n, int kw, int fuse_policy,
 
 }  // namespace yb
 
+extern "C" int yb_gemm_plan(int M, int N, int sms, int* out4) {
+  if (M <= 0 || N <= 0 || sms < 2 || !out4) return YB_ERR_ARG;
+  const bool pair = M >= 1024 && N >= 128;
+  out4[0] = pair ? 1 : 0;
+  out4[1] = pair ? yb::pair_block_n(M, N, sms / 2) : ((N % 256 == 0 || N > 1024) ? 256 : 128);
+  out4[2] = pair ? (M + 255) / 256 : (M + 127) / 128;
+  out4[3] = (N + out4[1] - 1) / out4[1];
+  return YB_OK;
+}
+
 extern "C" int yb_conv3d_plan(int T, int H, int W, int Cout, int kw, int fuse_w, int* out4) {
   if (T <= 0 || H <= 0 || W <= 0 || Cout <= 0 || (kw != 1 && kw != 3) || fuse_w < 0 || fuse_w > 2 || !out4) return YB_ERR_ARG;
   bool fused = false;
@@ -515,8 +718,8 @@ extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
   if (a->epilogue == YB_EPI_RES_BF16 && (!a->res || (a->res_ld % 8))) return YB_ERR_ARG;
   if ((a->lda % 8) || (a->ldb % 8) || (a->ldo % 8) || (reinterpret_cast<uintptr_t>(a->out) & 0xF)) return YB_ERR_ALIGNMENT;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const int block_n = (a->block_n == 128 || a->block_n == 256) ? a->block_n : ((a->N % 256 == 0 || a->N > 1024) ? 256 : 128);
-  CUtensorMap tmA, tmB;
+  if (a->struct_bytes != sizeof(yb_gemm_args)) return YB_ERR_ARG;   // caller compiled against another layout of the struct
+  if (a->cta_pair < 0 || a->cta_pair > 2) return YB_ERR_ARG;
   int a_split = a->K;
   long long a_chunk_ld = 0;
   if (a->a_split > 0) {
@@ -525,11 +728,7 @@ extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
     a_chunk_ld = a->a_split_stride;
   }
   const int a_chunks = a->K / a_split;
-  int rc = make_tmap_bf16_3d(&tmA, a->A, a_chunks, a->M, a_split, a->lda, a_chunks > 1 ? a_chunk_ld : a->lda * (long long)a->M + 8,
-                             GEMM_BLOCK_M, GEMM_BLOCK_K);
-  if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmB, a->B, a->N, a->K, a->ldb, block_n, GEMM_BLOCK_K);
-  if (rc) return rc;
+  if (a->n_split < 0 || (a->n_split > 0 && (a->n_split % 32 != 0 || a->epilogue != YB_EPI_BF16))) return YB_ERR_ARG;
   GemmParams p;
   p.M = a->M;
   p.N = a->N;
@@ -546,7 +745,34 @@ extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
   p.conv = 0;
   p.n_split = a->n_split;
   p.split_stride = a->split_stride;
-  if (a->n_split < 0 || (a->n_split > 0 && (a->n_split % 32 != 0 || a->epilogue != YB_EPI_BF16))) return YB_ERR_ARG;
+  p.block_n = 0;
+  p.stages = 0;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_3d(&tmA, a->A, a_chunks, a->M, a_split, a->lda, a_chunks > 1 ? a_chunk_ld : a->lda * (long long)a->M + 8,
+                             GEMM_BLOCK_M, GEMM_BLOCK_K);
+  if (rc) return rc;
+  // SM-pair kernel for the large token GEMMs (auto: M >= 1024 rows and N >= 128); the 1-CTA kernel keeps the small ones
+  // (context / embedding projections: a 256-row tile pair would be mostly padding) and every conv mode
+  const bool pair = a->cta_pair == 2 || (a->cta_pair == 0 && a->M >= 1024 && a->N >= 128);
+  if (pair) {
+    int bn = a->block_n;
+    if (bn == 0) bn = pair_block_n(a->M, a->N, sm_count() / 2);
+    if (bn < 32 || bn > 256 || bn % 32 != 0) return YB_ERR_ARG;
+    p.block_n = bn;
+    rc = make_tmap_bf16_2d(&tmB, a->B, a->N, a->K, a->ldb, bn / 2, GEMM_BLOCK_K);
+    if (rc) return rc;
+    switch (a->epilogue) {
+      case YB_EPI_BF16: return launch_gemm_pair<YB_EPI_BF16>(tmA, tmB, p, stream);
+      case YB_EPI_GELU_BF16: return launch_gemm_pair<YB_EPI_GELU_BF16>(tmA, tmB, p, stream);
+      case YB_EPI_F32: return launch_gemm_pair<YB_EPI_F32>(tmA, tmB, p, stream);
+      case YB_EPI_GELU_ERF_BF16: return launch_gemm_pair<YB_EPI_GELU_ERF_BF16>(tmA, tmB, p, stream);
+      case YB_EPI_RES_BF16: return launch_gemm_pair<YB_EPI_RES_BF16>(tmA, tmB, p, stream);
+      default: return launch_gemm_pair<YB_EPI_GATE_RES>(tmA, tmB, p, stream);
+    }
+  }
+  const int block_n = (a->block_n == 128 || a->block_n == 256) ? a->block_n : ((a->N % 256 == 0 || a->N > 1024) ? 256 : 128);
+  rc = make_tmap_bf16_2d(&tmB, a->B, a->N, a->K, a->ldb, block_n, GEMM_BLOCK_K);
+  if (rc) return rc;
 #define YB_DISPATCH(BN)                                                                  \
   switch (a->epilogue) {                                                                 \
     case YB_EPI_BF16: return launch_gemm<BN, YB_EPI_BF16>(tmA, tmB, p, stream);           \
@@ -569,6 +795,7 @@ extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
 extern "C" int yb_conv3d_causal(const yb_conv3d_args* a, void* stream_) {
   using namespace yb;
   if (!a || !a->xpad || !a->w || !a->out) return YB_ERR_ARG;
+  if (a->struct_bytes != sizeof(yb_conv3d_args)) return YB_ERR_ARG;
   if (a->T <= 0 || a->H <= 0 || a->W <= 0 || a->Cp <= 0 || a->Cout <= 0) return YB_ERR_ARG;
   if (a->Cp % 64 != 0 || a->Cout % 32 != 0) return YB_ERR_SHAPE;
   if ((a->ldo % 8) || (reinterpret_cast<uintptr_t>(a->out) & 0xF)) return YB_ERR_ALIGNMENT;

@@ -87,15 +87,40 @@ inline int check_launch(const char* what) {
   return YB_OK;
 }
 
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
+// SM count of the CURRENT device (cached per device: a process may drive several GPUs)
 inline int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: set it once per (kernel, device).
+// `done` is the caller's static bool[kMaxDevices] for that kernel instance.
+template <class Kern>
+inline int ensure_dynamic_smem(Kern kern, int bytes, bool* done, const char* what) {
+  const int dev = current_device();
+  if (done[dev]) return YB_OK;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "yume_b200: %s: cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%d) failed: %s\n", what, bytes,
+            cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return YB_ERR_LAUNCH;
+  }
+  done[dev] = true;
+  return YB_OK;
 }
 
 }  // namespace yb

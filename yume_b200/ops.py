@@ -60,8 +60,9 @@ def _need(t: torch.Tensor, dtype, name: str) -> None:
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, epilogue: int,
          gate: Optional[torch.Tensor] = None, tok_idx: Optional[torch.Tensor] = None, block_n: int = 0,
          n_split: int = 0, split_stride: int = 0, a_split: int = 0, a_split_stride: int = 0,
-         shape: Optional[tuple] = None, res: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out = epi(a[M,K] @ w[N,K]^T + bias). a, w bf16 (2-D, row stride arbitrary); see include/yume_b200.h."""
+         shape: Optional[tuple] = None, res: Optional[torch.Tensor] = None, cta_pair: int = 0) -> torch.Tensor:
+    """out = epi(a[M,K] @ w[N,K]^T + bias). a, w bf16 (2-D, row stride arbitrary); see include/yume_b200.h.
+    cta_pair: 0 automatic, 1 force the 1-CTA kernel, 2 force the SM-pair (cta_group::2) kernel."""
     global _launches, _flops
     _need(a, torch.bfloat16, "a")
     _need(w, torch.bfloat16, "w")
@@ -85,7 +86,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
     if tok_idx is not None:
         _need(tok_idx, torch.int32, "tok_idx")
     args = GemmArgs(
-        A=a.data_ptr(), B=w.data_ptr(), bias=_ptr(bias), out=out.data_ptr(), gate=_ptr(gate), tok_idx=_ptr(tok_idx),
+        struct_bytes=C.sizeof(GemmArgs), cta_pair=cta_pair, A=a.data_ptr(), B=w.data_ptr(), bias=_ptr(bias), out=out.data_ptr(), gate=_ptr(gate), tok_idx=_ptr(tok_idx),
         lda=a.stride(-2), ldb=w.stride(0), ldo=out.stride(-2), gate_ld=(gate.stride(0) if gate is not None else 0),
         M=M, N=N, K=K, epilogue=epilogue, block_n=block_n, n_split=n_split, split_stride=split_stride,
         a_split=a_split, a_split_stride=a_split_stride, res=_ptr(res),
@@ -173,31 +174,36 @@ def qk_norm_rope(q: torch.Tensor, k: torch.Tensor, wq: torch.Tensor, wk: torch.T
     _launches += 1
 
 
-def gemm_2cta(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
-    """EXPERIMENTAL SM-pair GEMM (yb_gemm_bf16_2cta): out bf16 = a[M,K] @ w[N,K]^T + bias. Not on the product path."""
-    global _launches
-    _need(a, torch.bfloat16, "a")
-    _need(w, torch.bfloat16, "w")
-    _need(out, torch.bfloat16, "out")
-    if bias is not None:
-        _need(bias, torch.float32, "bias")
-    M, K = a.shape
-    N = w.shape[0]
-    if w.shape[1] != K or tuple(out.shape) != (M, N):
-        raise YumeB200Error("gemm_2cta: shape mismatch")
-    check(_lib.load().yb_gemm_bf16_2cta(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), out.data_ptr(),
-                                        out.stride(0), M, N, K, _stream()), "yb_gemm_bf16_2cta")
-    _launches += 1
-    return out
+# softmax schedule of the attention kernel used by the product path (include/yume_b200.h YB_ATT_SM_SHIFT; attention.cu)
+ATTENTION_SOFTMAX_MODE = 0
+_sm_counts = {}
+
+
+def _sms(device: torch.device) -> int:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    n = _sm_counts.get(idx)
+    if n is None:
+        n = _sm_counts[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return n
+
+
+def _attention_ws(Lq: int, Lk: int, heads: int, flags: int, device: torch.device):
+    """Caller-owned workspace of the automatic KV tail split (the library never allocates): a fresh stream-ordered
+    allocation from torch's caching allocator, only for launches the planner actually splits."""
+    nbytes = _lib.load().yb_attention_workspace_bytes(Lq, Lk, heads, _sms(device), flags)
+    if nbytes <= 0:
+        return None, 0
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, heads: int,
               scale: Optional[float] = None, variant: int = 0, accumulate: bool = False, emu: int = 0,
-              split: int = 0) -> torch.Tensor:
+              split: int = 0, softmax: Optional[int] = None) -> torch.Tensor:
     """softmax(q k^T * scale) v, non-causal. q [Lq, heads*128], k/v [Lk, heads*128] bf16 (row strides arbitrary).
     split: KV split policy (YB_ATT_SPLIT_SHIFT): 0 automatic tail split, 1 never, 2..4 force that many KV segments.
-    variant: 0 product kernel (P in TMEM), 1 debug (P through smem), 2 EXPERIMENTAL Q-in-TMEM / 64-key tiles (attention64.cu)."""
-    global _launches
+    softmax: schedule (YB_ATT_SM_SHIFT): 0 classic, 1 deferred max, 2 deferred max + bf16x2 exponentials; None = product default.
+    variant: 0 product kernel (P in TMEM), 1 debug (P through smem)."""
+    global _launches, _flops
     for n, t in (("q", q), ("k", k), ("v", v), ("out", out)):
         _need(t, torch.bfloat16, n)
     Lq, Lk = q.shape[0], k.shape[0]
@@ -205,14 +211,17 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
         raise YumeB200Error("attention supports head_dim 128 only")
     if scale is None:
         scale = 1.0 / math.sqrt(128.0)
-    check(_lib.load().yb_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
-                                   out.data_ptr(), out.stride(0), Lq, Lk, heads, scale,
-                                   (YB_ATT_P_SMEM if variant == 1 else 0) | (128 if variant == 2 else 0)  # 128 = YB_ATT_Q64 (experimental)
-                                   | (YB_ATT_ACCUMULATE if accumulate else 0)
-                                   | ((emu & 3) << 2) | ((split & 7) << 4),
-                                   _stream()),
-          "yb_attention")
+    sm = ATTENTION_SOFTMAX_MODE if softmax is None else softmax
+    flags = ((YB_ATT_P_SMEM if variant == 1 else 0) | (YB_ATT_ACCUMULATE if accumulate else 0) | ((emu & 3) << 2)
+             | ((split & 7) << 4) | ((sm & 3) << 8 if variant == 0 else 0))
+    if variant not in (0, 1):
+        raise YumeB200Error("attention variant must be 0 or 1")
+    ws, ws_bytes = _attention_ws(Lq, Lk, heads, flags, q.device)
+    check(_lib.load().yb_attention_ex(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                      out.data_ptr(), out.stride(0), Lq, Lk, heads, scale, flags, _ptr(ws), ws_bytes, None,
+                                      _stream()), "yb_attention")
     _launches += 1
+    _flops += 4.0 * Lq * Lk * heads * 128
     return out
 
 
@@ -327,7 +336,7 @@ def conv3d_causal(xpad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tens
     _need(out, torch.float32 if epilogue == YB_EPI_F32 else torch.bfloat16, "out")
     if res is not None:
         _need(res, torch.bfloat16, "res")
-    args = Conv3dArgs(xpad=xpad.data_ptr(), w=w.data_ptr(), bias=_ptr(bias), out=out.data_ptr(), res=_ptr(res),
+    args = Conv3dArgs(struct_bytes=C.sizeof(Conv3dArgs), reserved=0, xpad=xpad.data_ptr(), w=w.data_ptr(), bias=_ptr(bias), out=out.data_ptr(), res=_ptr(res),
                       ldo=out.stride(0), res_ld=(res.stride(0) if res is not None else 0), T=T, H=H, W=W, Cp=Cp,
                       Cout=w.shape[0], epilogue=epilogue, kt=kt, kh=kh, kw=kw, oob_zero_pad=1 if oob_zero_pad else 0,
                       out_t_mul=out_t_mul, out_t_add=out_t_add, fuse_w=fuse_w)
@@ -444,16 +453,20 @@ def sp_scatter_qkv(qkv: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, rope: 
 
 
 def attention_sp(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out_peer_ptrs, ldo: int, heads: int, rank: int,
-                 Lp: int, scale: Optional[float] = None) -> None:
-    global _launches
+                 Lp: int, scale: Optional[float] = None, softmax: Optional[int] = None) -> None:
+    global _launches, _flops
     for n, t in (("q", q), ("k", k), ("v", v)):
         _need(t, torch.bfloat16, n)
     if scale is None:
         scale = 1.0 / math.sqrt(128.0)
+    sm = ATTENTION_SOFTMAX_MODE if softmax is None else softmax
+    flags = (sm & 3) << 8
+    ws, ws_bytes = _attention_ws(q.shape[0], k.shape[0], heads, flags, q.device)
     check(_lib.load().yb_attention_sp(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
                                       _ptr_array(out_peer_ptrs), ldo, q.shape[0], k.shape[0], heads, scale,
-                                      len(out_peer_ptrs), rank, Lp, _stream()), "yb_attention_sp")
+                                      len(out_peer_ptrs), rank, Lp, flags, _ptr(ws), ws_bytes, _stream()), "yb_attention_sp")
     _launches += 1
+    _flops += 4.0 * q.shape[0] * k.shape[0] * heads * 128
 
 
 def vae_rms_act(x: torch.Tensor, dims, out: torch.Tensor, gamma: Optional[torch.Tensor], up: int = 1, silu: bool = True) -> torch.Tensor:
