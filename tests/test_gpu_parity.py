@@ -434,6 +434,105 @@ def test_mirror_module_keeps_reference_signature(tiny5, dev):
         m([inp["x"]], torch.tensor(c["t"]), [inp["context"]], seq_len=c["seq_len"], enable_mask=True)
 
 
+def _mirror5(cfg, sd, dev):
+    from yume_b200.model import WanModel5B
+    with torch.device("meta"):
+        m = WanModel5B(model_type="ti2v", text_len=cfg["text_len"], in_dim=cfg["in_dim"], dim=cfg["dim"],
+                       ffn_dim=cfg["ffn_dim"], freq_dim=cfg["freq_dim"], text_dim=cfg["text_dim"], out_dim=cfg["out_dim"],
+                       num_heads=cfg["num_heads"], num_layers=cfg["num_layers"])
+    return m.install(dev, state_dict=sd)
+
+
+def test_block_and_self_attention_seams_keep_reference_signatures(tiny5, dev):
+    """`WanAttentionBlock.forward` / `WanSelfAttention.forward` with the reference's argument lists,
+    bound by install_seams. Block seam vs the reference block output (configs[0] fixture, grid path) and vs the oracle on
+    the FramePack path (per-token complex freqs); self-attention seam vs the oracle's self_attn."""
+    import yume_b200
+    from oracle.wan_dit import grid_freqs
+    g, sd, _ = tiny5
+    cfg, b = g["cfg"], g["block"]
+    m = yume_b200.install_seams(_mirror5(cfg, sd, dev))
+    gen = torch.Generator().manual_seed(b["seed"])
+    L, C = b["L"], cfg["dim"]
+    x = torch.randn(1, L, C, generator=gen)
+    e = 0.5 * torch.randn(1, L, 6, C, generator=gen)
+    ctx = torch.randn(1, cfg["text_len"], C, generator=gen)
+    orc = WanOracle(sd, **synth.oracle_kwargs(cfg))
+    tables = torch.cat(orc.tables, dim=1)                                  # the [1024, 64] table the reference passes on the grid path
+    y = m.blocks[0](x.to(dev), e.to(dev), torch.tensor([L]), torch.tensor([[2, 8, 8]]), tables, ctx.to(dev), None, flag=False)
+    assert y.shape == (1, L, C) and y.dtype == torch.float32
+    d_ref, d = b["out"][0] - x[0], y[0].cpu() - x[0]
+    assert float((d - d_ref).norm() / d_ref.norm()) < BLOCK_TOL_REL
+    # FramePack path: per-token complex table (model.py:101-105), a temporal offset so it differs from the plain grid
+    fr = grid_freqs(orc.tables, 2, 8, 8, f0=3)
+    want = orc.block(1, x, e, fr, ctx)[0]
+    got = m.blocks[1](x.to(dev), e.to(dev), torch.tensor([L]), None, fr.to(dev), ctx.to(dev), None, flag=True)[0].cpu()
+    assert float(((got - x[0]) - (want - x[0])).norm() / (want - x[0]).norm()) < BLOCK_TOL_REL
+    # self-attention seam: o(attention(rope(norm(q)), rope(norm(k)), v))
+    h = torch.randn(1, L, C, generator=gen)
+    want_sa = orc.self_attn("blocks.0.self_attn", h, fr)[0]
+    got_sa = m.blocks[0].self_attn(h.to(dev), torch.tensor([L]), None, fr.to(dev), None, None, None, True)[0]
+    assert got_sa.dtype == torch.bfloat16 and rel(got_sa, want_sa) < 1e-2
+    with pytest.raises(NotImplementedError):
+        m.blocks[0](x.to(dev), e.to(dev), torch.tensor([L]), None, fr.to(dev), ctx.to(dev), None, ids_keep=torch.zeros(1, 4))
+
+
+def test_flash_attention_shim_keeps_reference_contract(dev):
+    """`flash_attention(q, k, v, k_lens=...)` with the reference's layout [B, L, N, D], dtype behaviour (fp32 in -> fp32
+    out, computed in bf16) and k_lens masking (wan23/modules/attention.py:24-130), B = 2."""
+    import yume_b200
+    g = torch.Generator(device="cpu").manual_seed(17)
+    B, Lq, Lk, N = 2, 200, 333, 2
+    q, k, v = (torch.randn(B, L_, N, 128, generator=g).to(dev) for L_ in (Lq, Lk, Lk))
+    k_lens = torch.tensor([333, 150])
+    out = yume_b200.flash_attention(q, k, v, k_lens=k_lens)
+    assert out.shape == (B, Lq, N, 128) and out.dtype == torch.float32
+    for i in range(B):
+        kl = int(k_lens[i])
+        ref = _sdpa(q[i].bfloat16().reshape(Lq, N * 128), k[i, :kl].bfloat16().reshape(kl, N * 128),
+                    v[i, :kl].bfloat16().reshape(kl, N * 128), N)
+        assert rel(out[i].reshape(Lq, N * 128), ref) < KERNEL_TOL
+    half = yume_b200.flash_attention(q.bfloat16(), k.bfloat16(), v.bfloat16(), softmax_scale=0.05)
+    assert half.dtype == torch.bfloat16 and bool(torch.isfinite(half.float()).all())
+    with pytest.raises(NotImplementedError):
+        yume_b200.flash_attention(q, k, v, causal=True)
+    with pytest.raises(AssertionError):
+        yume_b200.flash_attention(q.cpu(), k.cpu(), v.cpu())               # the reference asserts CUDA too (attention.py:54)
+
+
+def test_sampler_loop_cache_and_cuda_graph_match_plain_forwards(tiny5, dev):
+    """Sampler-loop fusion: the 4-step 5B loop with the context cache on, and again replayed from a
+    CUDA graph, gives the result of the same loop with every forward computed from scratch."""
+    from yume_b200 import sampler
+    g, sd, _ = tiny5
+    cfg = g["cfg"]
+    m = _mirror5(cfg, sd, dev)
+    eng = m._yb_engine
+    gen = torch.Generator().manual_seed(23)
+    hist = torch.randn(48, 5, 6, 10, generator=gen).to(dev)
+    noise = torch.randn(48, 2, 6, 10, generator=gen).to(dev)
+    ctx = torch.randn(20, cfg["text_dim"], generator=gen).to(dev).bfloat16()
+    arg_c = dict(context=[ctx], seq_len=0)
+
+    def loop():
+        return sampler.denoise_chunk_5b(m, torch.cat([hist, noise], 1), hist, 2, 4, arg_c, shift=7.0)
+    eng.context_cache, eng.use_cuda_graph = False, False
+    plain = loop()
+    eng.context_cache = True
+    cached = loop()
+    assert torch.equal(cached, plain)
+    eng.use_cuda_graph = True
+    graphed = loop()
+    graphed2 = loop()                                                      # second pass replays the captured graphs
+    assert torch.equal(graphed, plain) and torch.equal(graphed2, plain)
+    assert len(eng._graphs) >= 1
+    ctx2 = (ctx.float() * 0.5).bfloat16()                                  # a NEW context tensor must not hit the old entry
+    other = sampler.denoise_chunk_5b(m, torch.cat([hist, noise], 1), hist, 2, 4, dict(context=[ctx2], seq_len=0), shift=7.0)
+    assert not torch.equal(other, plain)
+    ctx.mul_(0.5)                                                          # in-place edit bumps _version: recomputed, same as ctx2
+    assert torch.equal(loop(), other)
+
+
 def test_oracle_block_at_real_width(dev):
     """One block at the real 5B width (C=3072, 24 heads, F=14336), L=256: CUDA vs oracle (seconds on CPU)."""
     cfg = dict(synth.CFG_5B, num_layers=1, text_len=64)

@@ -301,3 +301,89 @@ def test_conv_tile_plan():
         tiles = -(-W // tw) * -(-H // th) * -(-T // tt)
         assert tiles * 128 >= T * H * W
     assert lib.yb_conv3d_plan(1, 1, 1, 32, 2, 0, (C.c_int * 4)()) != 0
+
+
+@pytest.mark.parametrize("tree,cfg_name", [("wan23", "CFG_5B_TINY"), ("wan", "CFG_14B_TINY")])
+def test_install_on_the_reference_wanmodel_repacks_identically(tree, cfg_name):
+    """Drop-in boundary: `install()` on a live REFERENCE `WanModel` — loaded from /root/reference with the
+    recipe of tools/make_golden.py — must re-bind `forward` and build, from the module's own parameters
+    (`WanDiT.from_module`), exactly the packed tensors the state-dict path builds. Runs where the reference tree exists (the
+    authoring container); skipped on the GPU box."""
+    import sys
+    ref_root = Path("/root/reference")
+    if not (ref_root / tree / "modules" / "model.py").exists():
+        pytest.skip("reference tree not present")
+    sys.path.insert(0, str(ROOT / "tools"))
+    import make_golden
+    from yume_b200 import model as ybm
+    cfg = getattr(synth, cfg_name)
+    sd = synth.make_state_dict(cfg, 4321)
+    ref_model = make_golden.build_reference_model(make_golden.load_reference(tree), cfg, sd)
+    assert type(ref_model).__module__.startswith(tree)                 # really the reference's class
+    ref_forward = ref_model.forward
+    ybm.install(ref_model, device="cpu")                               # repack only: no kernel runs at install time
+    assert ref_model.forward is not ref_forward and ref_model.forward.__func__ in (ybm.forward_5b, ybm.forward_14b)
+    eng = ref_model._yb_engine
+    kw = synth.oracle_kwargs(cfg)
+    want = WanDiT(sd, kw.pop("variant"), device="cpu", **kw)
+    assert (eng.variant, eng.dim, eng.heads, eng.layers, eng.in_dim, eng.out_dim) == \
+        (want.variant, want.dim, want.heads, want.layers, want.in_dim, want.out_dim)
+
+    def same(a, b, path):
+        if isinstance(a, torch.Tensor):
+            assert a.dtype == b.dtype and torch.equal(a, b), path
+        elif isinstance(a, dict):
+            assert a.keys() == b.keys(), path
+            for k in a:
+                same(a[k], b[k], f"{path}.{k}")
+        elif isinstance(a, (list, tuple)):
+            assert len(a) == len(b), path
+            for i, (x, y) in enumerate(zip(a, b)):
+                same(x, y, f"{path}[{i}]")
+    for name in ("embed", "text0", "text2", "time0", "time2", "tproj", "head_w", "head_b", "head_mod", "blocks", "block_mod",
+                 "cw_kv_all", "cb_kv_all") + (("img", "cw_kv_img_all", "cb_kv_img_all") if cfg["variant"] == "14b" else ()):
+        same(getattr(eng, name), getattr(want, name), name)
+    # the re-bound forward keeps the reference's error behaviour without touching the GPU
+    if cfg["variant"] == "14b":
+        with pytest.raises(RuntimeError):
+            ref_model([torch.zeros(16, 3, 8, 8)], torch.tensor([1.0]), [torch.zeros(4, 64)], 48, clip_fea=torch.zeros(1, 257, 96),
+                      y=[torch.zeros(20, 3, 8, 8)], rand_num_img=None)
+    else:
+        with pytest.raises(NotImplementedError):
+            ref_model([torch.zeros(48, 3, 8, 8)], torch.tensor([1.0]), [torch.zeros(4, 64)], 48, enable_mask=True)
+
+
+def test_integration_doc_snippet_is_current():
+    """INTEGRATION.md §3 shows the struct layouts a foreign caller must copy: the block is generated from the live binding
+    and this test fails when either side changes without the other (round-1 ADVICE: a stale snippet over-read the struct)."""
+    import sys
+    sys.path.insert(0, str(ROOT / "tools"))
+    import gen_integration_snippet as gen
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    block = doc[doc.index(gen.BEGIN) + len(gen.BEGIN):doc.index(gen.END)].strip()
+    assert block == gen.snippet().strip(), "run: python tools/gen_integration_snippet.py --write"
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """Compile include/yume_b200.h with gcc and compare sizeof / offsetof of both argument structs with the ctypes mirrors."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    fields = {"yb_gemm_args": _lib.GemmArgs, "yb_conv3d_args": _lib.Conv3dArgs}
+    prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include" / "yume_b200.h"}"', "int main(void) {"]
+    for cname, cls in fields.items():
+        prog.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            prog.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    prog += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", str(src), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in fields.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"

@@ -9,6 +9,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libyume_b200.so"
 
 YB_EPI_BF16, YB_EPI_GELU_BF16, YB_EPI_F32, YB_EPI_GATE_RES, YB_EPI_GELU_ERF_BF16, YB_EPI_RES_BF16 = 0, 1, 2, 3, 4, 5
 YB_ATT_P_SMEM, YB_ATT_ACCUMULATE = 1, 2
+ABI_VERSION = 2   # yb_abi_version() of the library this binding was written against
 YB_ATT_EMU_SHIFT, YB_ATT_SPLIT_SHIFT, YB_ATT_SM_SHIFT = 2, 4, 8
 
 _ERRORS = {
@@ -108,6 +109,9 @@ def load():
             f"{_LIB_PATH} is missing: build it with `python -m yume_b200.build` (or __graft_entry__.build()). "
             "yume_b200 has no fallback path.")
     lib = C.CDLL(str(_LIB_PATH))
+    if lib.yb_abi_version() != ABI_VERSION:
+        raise YumeB200Error(f"{_LIB_PATH} has ABI version {lib.yb_abi_version()}, this binding expects {ABI_VERSION}: rebuild it "
+                            "(python -m yume_b200.build --force)")
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here means header and library disagree
         fn.restype = res

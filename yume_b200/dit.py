@@ -582,22 +582,84 @@ class WanDiT:
         ops.gemm(hid, b["w2"], b["b2"], xs, ops.YB_EPI_GATE_RES, gate=m[:, 5], tok_idx=tok_idx)
         T.end("gemm_ffn2")
 
-    def block_forward(self, i: int, x: Tensor, e: Tensor, grid: Tuple[int, int, int], context: Tensor) -> Tensor:
-        """Single-block entry (BASELINE.json configs[0]): the arithmetic of WanAttentionBlock.forward for one sample.
-        x f32 [L, C]; e f32 [L, 6, C] (5B, per token) or [6, C] (14B); context bf16/f32 [S, C] already embedded."""
+    def _cross_kv_one(self, i: int, ctx: Tensor):
+        """Block i's cross-attention K | V only (the block / self-attention seams run one block at a time)."""
+        C, D = self.dim, self.head_dim
+        n_img = 257 if self.variant == "14b" else 0
+        ctx_txt = ctx[n_img:]
+        kv = self._buf("ckv_one", (ctx_txt.shape[0], 2 * C), _BF16)
+        ops.gemm(ctx_txt, self.cw_kv_all[i * 2 * C:(i + 1) * 2 * C], self.cb_kv_all[i * 2 * C:(i + 1) * 2 * C], kv, ops.YB_EPI_BF16)
+        ops.rmsnorm_rope(kv[:, :C], self.blocks[i]["cnk"], None, D, self.eps)
+        kvi = None
+        if n_img:
+            kvi = self._buf("ckv_img_one", (n_img, 2 * C), _BF16)
+            ops.gemm(ctx[:n_img], self.cw_kv_img_all[i * 2 * C:(i + 1) * 2 * C], self.cb_kv_img_all[i * 2 * C:(i + 1) * 2 * C], kvi,
+                     ops.YB_EPI_BF16)
+            ops.rmsnorm_rope(kvi[:, :C], self.blocks[i]["cnk_img"], None, D, self.eps)
+        return kv, kvi
+
+    def rope_from_reference(self, freqs: Tensor, grid: Optional[Sequence[int]], packed: bool) -> Tuple[Tensor, int]:
+        """(cos, sin) table + number of rotated rows from what the reference hands its blocks: on the FramePack path `freqs`
+        is the per-token complex table [L, 1, D/2] (model.py:101-105) and is converted as is; on the grid path it is the
+        [1024, D/2] axis table and the rows follow from `grid` = (f, h, w) (model.py:54-69) — rebuilt from the same formula."""
+        if packed:
+            t = torch.view_as_real(freqs.reshape(-1, self.head_dim // 2).to(torch.complex128)).to(_F32).contiguous()
+            return t.to(self.device), t.shape[0]
+        f, h, w = (int(v) for v in grid)
+        t = self._rope_table([(f, h, w, 0)])
+        return t, t.shape[0]
+
+    @torch.no_grad()
+    def block_forward(self, i: int, x: Tensor, e: Tensor, grid: Optional[Tuple[int, int, int]], context: Tensor,
+                      freqs: Optional[Tensor] = None, packed: bool = False, k_len: Optional[int] = None) -> Tensor:
+        """Single-block entry (BASELINE.json configs[0]; the `WanAttentionBlock.forward` seam): the arithmetic of one block
+        for one sample. x f32 [L, C]; e f32 [L, 6, C] (5B, per token) or [6, C] (14B); context bf16/f32 [S, C] already
+        embedded; rope rows from `grid` (regular grid) or the reference's per-token `freqs` (packed); k_len = rows that are
+        self-attention keys (seq_lens; default all)."""
         C = self.dim
-        xs = x.to(device=self.device, dtype=_F32).clone().contiguous()
-        L = xs.shape[0]
-        e = e.to(device=self.device, dtype=_F32)
-        if e.dim() == 2:
-            e0, tok_idx = e.reshape(1, 6 * C), None
-        else:
-            e0, tok_idx = e.reshape(L, 6 * C).contiguous(), torch.arange(L, device=self.device, dtype=torch.int32)
-        mod = ops.bcast_add(self.block_mod, e0).view(self.layers, e0.shape[0], 6, C)
-        rope = self._rope_table([(grid[0], grid[1], grid[2], 0)])
-        ctx = self._cross_kv(context.to(device=self.device, dtype=_BF16).contiguous())
-        self._block(i, xs, mod, tok_idx, rope, rope.shape[0], ctx)
+        with torch.cuda.device(self.device):
+            xs = x.to(device=self.device, dtype=_F32).clone().contiguous()
+            L = xs.shape[0]
+            e = e.to(device=self.device, dtype=_F32)
+            if e.dim() == 2:
+                e0, tok_idx = e.reshape(1, 6 * C), None
+            else:
+                e0, tok_idx = e.reshape(L, 6 * C).contiguous(), torch.arange(L, device=self.device, dtype=torch.int32)
+            mod = ops.bcast_add(self.block_mod[i:i + 1], e0).view(1, e0.shape[0], 6, C)
+            rope, rope_len = self.rope_from_reference(freqs, grid, packed) if (packed or freqs is not None) else \
+                (self._rope_table([(grid[0], grid[1], grid[2], 0)]), grid[0] * grid[1] * grid[2])
+            ctx = self._cross_kv_one(i, context.to(device=self.device, dtype=_BF16).contiguous())
+            b = self.blocks[i]
+            m = mod[0]
+            h = self._buf("h", (L, C), _BF16)
+            qkv = self._buf("qkv", (L, 3 * C), _BF16)
+            att = self._buf("att", (L, C), _BF16)
+            ops.ln_modulate(xs, h, m[:, 1], m[:, 0], tok_idx, eps=self.eps)
+            self._self_attention_local(b, h, qkv, att, xs, m, tok_idx, rope, min(rope_len, L), L if k_len is None else int(k_len))
+            self._cross_and_ffn(b, xs, h, qkv, att, m, tok_idx, ctx)
         return xs
+
+    @torch.no_grad()
+    def self_attention_forward(self, i: int, x: Tensor, grid: Optional[Tuple[int, int, int]], freqs: Optional[Tensor],
+                               packed: bool, k_len: Optional[int] = None) -> Tensor:
+        """`WanSelfAttention.forward` seam for one sample: x [L, C] (the modulated, normalised input) -> o(attention(...)) as
+        bf16 [L, C] — q/k/v projection, RMSNorm(q), RMSNorm(k), RoPE, attention, output projection; no gate, no residual
+        (wan23/modules/model.py:178-207)."""
+        C, H, D = self.dim, self.heads, self.head_dim
+        with torch.cuda.device(self.device):
+            h = x.to(device=self.device, dtype=_BF16).contiguous()
+            L = h.shape[0]
+            b = self.blocks[i]
+            rope, rope_len = self.rope_from_reference(freqs, grid, packed)
+            qkv = self._buf("qkv", (L, 3 * C), _BF16)
+            att = self._buf("att", (L, C), _BF16)
+            ops.gemm(h, b["w_qkv"], b["b_qkv"], qkv, ops.YB_EPI_BF16)
+            ops.qk_norm_rope(qkv[:, :C], qkv[:, C:2 * C], b["nq"], b["nk"], rope, D, self.eps, min(rope_len, L))
+            kl = L if k_len is None else int(k_len)
+            ops.attention(qkv[:, :C], qkv[:kl, C:2 * C], qkv[:kl, 2 * C:], att, H)
+            out = torch.empty(L, C, device=self.device, dtype=_BF16)
+            ops.gemm(att, b["w_o"], b["b_o"], out, ops.YB_EPI_BF16)
+        return out
 
     # ------------------------------------------------------------------------------------------------------
     # forward
