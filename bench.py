@@ -547,7 +547,8 @@ def product_arm(args):
             "config": {"workload": WORKLOAD,
                        "model": "Yume-5B-720P (Wan2.2-TI2V-5B geometry: dim 3072, ffn 14336, 24 heads, 30 layers), random init",
                        "parallelism": "single GPU" if world == 1 else
-                       f"ulysses sp{world} ({'NVLink peer-memory exchange fused into kernels' if eng._sp_p2p else 'NCCL all-to-all'})",
+                       f"ulysses sp{world} (transport {eng.sp_transport}: "
+                       f"{'NVLink peer-memory exchange fused into kernels' if eng._sp_p2p else 'NCCL all-to-all'})",
                        "l2": "per-step working set (10 GB of bf16 weights + 1.5 GB activations) >> 126 MB L2; no flush needed",
                        "caching": "none: text embedding and all 30 cross-attention K/V projections are recomputed inside every timed step",
                        "step_tflop": step_flops / 1e12},
@@ -743,7 +744,7 @@ def main():
     ap.add_argument("--no-supplementary", action="store_true", help="headline only (no configs[2]/[3]/[4] side runs)")
     ap.add_argument("--no-14b", action="store_true", help="supplementary: skip the 14B runs")
     ap.add_argument("--no-vae", action="store_true", help="supplementary: skip the VAE decodes")
-    ap.add_argument("--sp-transport", default="auto", choices=["auto", "p2p", "nccl"])
+    ap.add_argument("--sp-transport", default="auto", choices=["auto", "p2p", "p2p_gemm", "nccl"])
     ap.add_argument("--quick", action="store_true", help="profiling runs: exact --warmup, no e2e leg, no CPU baseline")
     args = ap.parse_args()
     if args.workload == "vae":

@@ -196,6 +196,20 @@ int yb_debug_force_split(int ns);
  * ------------------------------------------------------------------------------------------- */
 int yb_sp_scatter_qkv(const void* qkv, long long ld, const void* wq, const void* wk, const void* rope, int rope_len,
                       int L, int C, int D, float eps, void* const* peers, int world, int rank, int Lp, void* stream);
+/* GEMM + collective in ONE kernel (the second Ulysses transport, "p2p_gemm"): the fused q|k|v projection of this rank's Lp_rows
+ * local tokens (A bf16 [Lp_rows, K], W bf16 [3C, K] = q|k|v weights stacked, bias f32 [3C]) on the SM-pair tcgen05 kernel whose
+ * EPILOGUE is the all-to-all: the columns of head h are stored straight into the receive buffer of the rank that owns h
+ * (`peers[r]`, layout [P(src), Lp, q|k|v of heads/P] as for yb_sp_scatter_qkv), so the NVLink transfer rides under the GEMM's
+ * main loop instead of a separate pass. WanRMSNorm spans all heads of a token, which no single receiver holds: the epilogue
+ * also accumulates the per-token sums of squares of the (bf16-rounded) q and k columns into `sums` f32 [Lp][2] (atomics; the
+ * caller zeroes it once, yb_sp_bcast_sums re-zeroes it), yb_sp_bcast_sums copies them into slot `rank` of every peer's
+ * [P, Lp, 2] table, and — after the cross-rank barrier — yb_sp_post_norm_rope finishes q, k in place on the RECEIVED rows:
+ * bf16(rope(x * rstd(token) * weight[my heads])), the arithmetic of yb_rmsnorm_rope moved behind the exchange. */
+int yb_gemm_sp_qkv(const void* A, long long lda, const void* W, const void* bias, int Lp_rows, int C, int K, void* const* peers,
+                   int world, int rank, int Lp, void* sums, void* stream);
+int yb_sp_bcast_sums(void* local_sums, void* const* peer_tables, int world, int rank, int Lp, void* stream);
+int yb_sp_post_norm_rope(void* buf, const void* sums, const void* wq, const void* wk, const void* rope, int rope_len, int L,
+                         int Wh, int C, int D, float eps, void* stream);
 int yb_attention_sp(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                     void* const* out_peers, long long ldo, int Lq, int Lk, int heads, float scale, int world, int rank,
                     int Lp, int flags, void* ws, long long ws_bytes, void* stream);   /* flags / ws as yb_attention_ex */

@@ -100,6 +100,38 @@ def test_gemm_pair_kernel_split_layouts(dev):
     assert torch.equal(send.permute(1, 0, 2).reshape(Lp, N), want)
 
 
+@pytest.mark.parametrize("P,Lp,C", [(2, 300, 1024), (4, 257, 1024), (8, 129, 3072)])
+def test_fused_qkv_gemm_all_to_all_on_one_gpu(dev, P, Lp, C):
+    """yb_gemm_sp_qkv / yb_sp_bcast_sums / yb_sp_post_norm_rope (the "p2p_gemm" Ulysses transport) with the P ranks emulated
+    on ONE device: every "rank" runs the fused projection on its token shard with peer pointers to P receive buffers; after
+    the sums exchange each receiver normalises + rotates in place. Must equal the plain path (one QKV GEMM over all tokens,
+    yb_qk_norm_rope) column block by column block; v bit-exact, q/k up to the fp32 summation order of the row statistics."""
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(P * 1000 + Lp)
+    D, K, Wh, L = 128, 256, C // P, P * Lp
+    h = torch.randn(L, K, generator=g).to(dev).bfloat16()
+    w = (torch.randn(3 * C, K, generator=g) / math.sqrt(K)).to(dev).bfloat16()
+    bias = torch.randn(3 * C, generator=g).to(dev)
+    nq, nk = (torch.rand(C, generator=g) + 0.5).to(dev), (torch.rand(C, generator=g) + 0.5).to(dev)
+    rope = torch.randn(L, D // 2, 2, generator=g).to(dev)
+    rope_len = L - 37
+    ref = ops.gemm(h, w, bias, torch.empty(L, 3 * C, device=dev, dtype=torch.bfloat16), ops.YB_EPI_BF16)
+    v_ref = ref[:, 2 * C:].clone()
+    ops.qk_norm_rope(ref[:, :C], ref[:, C:2 * C], nq, nk, rope, D, rope_len=rope_len)
+    bufs = [torch.zeros(P * Lp, 3 * Wh, device=dev, dtype=torch.bfloat16) for _ in range(P)]
+    tables = [torch.zeros(P * Lp, 2, device=dev) for _ in range(P)]
+    local = torch.zeros(Lp, 2, device=dev)
+    for r in range(P):
+        ops.gemm_sp_qkv(h[r * Lp:(r + 1) * Lp], w, bias, [b.data_ptr() for b in bufs], r, Lp, local)
+        ops.sp_bcast_sums(local, [t.data_ptr() for t in tables], r, Lp)
+        assert float(local.abs().max()) == 0.0                 # accumulator cleared for the next layer
+    for p in range(P):
+        ops.sp_post_norm_rope(bufs[p], tables[p], nq[p * Wh:(p + 1) * Wh], nk[p * Wh:(p + 1) * Wh], rope, rope_len, L, Wh, C, D, 1e-6)
+        assert torch.equal(bufs[p][:, 2 * Wh:], v_ref[:, p * Wh:(p + 1) * Wh])
+        assert rel(bufs[p][:, :Wh], ref[:, p * Wh:(p + 1) * Wh]) < 2e-3
+        assert rel(bufs[p][:, Wh:2 * Wh], ref[:, C + p * Wh:C + (p + 1) * Wh]) < 2e-3
+
+
 @pytest.mark.parametrize("shift", [1, 2, 3, 7, 8])
 def test_umma_probe_row_shifted_a(dev, shift):
     """The conv kernel reuses one TMA halo box for the three kw taps by moving the A descriptor's start address by whole
@@ -608,12 +640,13 @@ def test_fullsize_gemm_linearity_and_row_independence(dev):
     assert rel(o1[rows], a1[rows].float() @ w.float().t()) < 1e-4
 
 
-@pytest.mark.parametrize("world,transport,split", [(2, "p2p", "0"), (2, "nccl", "0"), (4, "p2p", "0"), (4, "nccl", "0"),
-                                                   (8, "p2p", "0"), (8, "nccl", "0"), (2, "p2p", "2"), (8, "p2p", "2")])
+@pytest.mark.parametrize("world,transport,split", [(2, "p2p", "0"), (2, "p2p_gemm", "0"), (2, "nccl", "0"), (4, "p2p", "0"),
+                                                   (4, "p2p_gemm", "0"), (4, "nccl", "0"), (8, "p2p", "0"), (8, "p2p_gemm", "0"),
+                                                   (8, "nccl", "0"), (2, "p2p", "2"), (8, "p2p_gemm", "2")])
 def test_ulysses_matches_golden(dev, world, transport, split):
     """Sequence-parallel forward on `world` GPUs (torchrun) vs the reference-generated golden outputs: the 2-head tiny
-    models at world 2, the 8-head (dim 1024) models at world 2 / 4 / 8; both transports (NVLink peer-memory kernels,
-    NCCL all-to-all); split = forced KV tail split of the attention launch through the peer-scatter combine kernel.
+    models at world 2, the 8-head (dim 1024) models at world 2 / 4 / 8; every transport (NVLink peer-memory kernels with the
+    q|k|v exchange in the norm/RoPE pass or in the QKV GEMM's epilogue, NCCL all-to-all); split = forced KV tail split of the attention launch through the peer-scatter combine kernel.
     Skipped on boxes with fewer GPUs — bench.py's `parity_vs_n1` carries the same check on every multi-GPU bench line."""
     import subprocess
     import sys

@@ -81,6 +81,9 @@ SIGNATURES = {
     "yb_attention_workspace_bytes": (_ll, [_i, _i, _i, _i, _i]),
     "yb_debug_force_split": (_i, [_i]),
     "yb_sp_scatter_qkv": (_i, [_vp, _ll, _vp, _vp, _vp, _i, _i, _i, _i, _f, C.POINTER(C.c_void_p), _i, _i, _i, _vp]),
+    "yb_gemm_sp_qkv": (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, C.POINTER(C.c_void_p), _i, _i, _i, _vp, _vp]),
+    "yb_sp_bcast_sums": (_i, [_vp, C.POINTER(C.c_void_p), _i, _i, _i, _vp]),
+    "yb_sp_post_norm_rope": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "yb_attention_sp": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, C.POINTER(C.c_void_p), _ll, _i, _i, _i, _f, _i, _i, _i, _i, _vp, _ll,
                              _vp]),
     "yb_patchify": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),

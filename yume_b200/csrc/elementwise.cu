@@ -382,6 +382,9 @@ qk_norm_rope_warp_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restric
 struct PeerPtrs {
   __nv_bfloat16* p[8];
 };
+struct PeerPtrsF {
+  float* p[8];
+};
 template <int NCH>
 __global__ void __launch_bounds__(256)
 sp_scatter_qkv_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, const float* __restrict__ wq,
@@ -446,6 +449,64 @@ sp_scatter_qkv_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, const
       const int peer = col / Wh;
       *reinterpret_cast<uint4*>(peers.p[peer] + dst_row + part * Wh + (col - peer * Wh)) = o;
     }
+  }
+}
+
+// Receiver side of the fused projection + all-to-all (yb_gemm_sp_qkv): the q | k columns this rank received are still
+// un-normalised (WanRMSNorm needs the sum of squares over ALL heads of a token, which no single rank holds).
+//   sp_bcast_sums_kernel   every rank copies its [Lp][2] sums of squares (q, k) into slot `rank` of every peer's table and
+//                          clears its accumulator for the next layer
+//   sp_post_norm_rope_kernel  after the barrier: q, k <- bf16(rope(x * rstd(token) * weight[my heads])) in place on the
+//                          received [L, 3*Wh] rows (one warp per token; v untouched) — the arithmetic of rmsnorm_rope, moved
+//                          behind the exchange so that the NVLink traffic rides under the GEMM instead of a separate pass.
+__global__ void sp_bcast_sums_kernel(float* __restrict__ local, const PeerPtrsF peers, int rank, int Lp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Lp) return;
+  const float2 v = reinterpret_cast<const float2*>(local)[i];
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+    if (peers.p[p]) reinterpret_cast<float2*>(peers.p[p])[static_cast<long long>(rank) * Lp + i] = v;
+  reinterpret_cast<float2*>(local)[i] = make_float2(0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(256)
+sp_post_norm_rope_kernel(__nv_bfloat16* __restrict__ buf, const float* __restrict__ sums, const float* __restrict__ wq,
+                         const float* __restrict__ wk, const float2* __restrict__ rope, int rope_len, int L, int Wh, int C,
+                         int D, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= L) return;
+  const float2 ss = reinterpret_cast<const float2*>(sums)[row];
+  const float rstd_q = rsqrtf(ss.x / static_cast<float>(C) + eps), rstd_k = rsqrtf(ss.y / static_cast<float>(C) + eps);
+  const bool rot = (rope != nullptr) && (row < rope_len);
+  const float* rope_row = reinterpret_cast<const float*>(rope) + static_cast<long long>(row) * D;
+  __nv_bfloat16* base = buf + static_cast<long long>(row) * (3 * Wh);
+  const int nch = Wh >> 3;
+  for (int c = lane; c < 2 * nch; c += 32) {       // chunks [0, nch) = q, [nch, 2 nch) = k
+    const int part = c >= nch ? 1 : 0;
+    const int col = (c - part * nch) << 3;
+    const float* weight = part ? wk : wq;
+    const float rstd = part ? rstd_k : rstd_q;
+    uint4 raw = *reinterpret_cast<const uint4*>(base + part * Wh + col);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(weight + col));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(weight + col + 4));
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    float cs[8] = {1.f, 0.f, 1.f, 0.f, 1.f, 0.f, 1.f, 0.f};
+    if (rot) {
+      const float4 r0 = __ldg(reinterpret_cast<const float4*>(rope_row + (col % D)));
+      const float4 r1 = __ldg(reinterpret_cast<const float4*>(rope_row + (col % D) + 4));
+      cs[0] = r0.x; cs[1] = r0.y; cs[2] = r0.z; cs[3] = r0.w; cs[4] = r1.x; cs[5] = r1.y; cs[6] = r1.z; cs[7] = r1.w;
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h[j]);
+      const float a = f.x * rstd * wv[2 * j];
+      const float b2 = f.y * rstd * wv[2 * j + 1];
+      o[j] = pack_bf16x2(a * cs[2 * j] - b2 * cs[2 * j + 1], a * cs[2 * j + 1] + b2 * cs[2 * j]);
+    }
+    *reinterpret_cast<uint4*>(base + part * Wh + col) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -761,6 +822,24 @@ extern "C" int yb_linear_f32(const void* in, long long ldi, const void* W, const
   return check_launch("linear_f32");
 }
 
+
+extern "C" int yb_sp_bcast_sums(void* local, void* const* peers, int world, int rank, int Lp, void* stream_) {
+  if (!local || !peers || world < 2 || world > 8 || rank < 0 || rank >= world || Lp <= 0) return YB_ERR_ARG;
+  PeerPtrsF pp;
+  for (int i = 0; i < 8; ++i) pp.p[i] = i < world ? static_cast<float*>(peers[i]) : nullptr;
+  sp_bcast_sums_kernel<<<(Lp + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(static_cast<float*>(local), pp, rank, Lp);
+  return check_launch("sp_bcast_sums");
+}
+
+extern "C" int yb_sp_post_norm_rope(void* buf, const void* sums, const void* wq, const void* wk, const void* rope, int rope_len,
+                                    int L, int Wh, int C, int D, float eps, void* stream_) {
+  if (!buf || !sums || !wq || !wk || L <= 0 || Wh <= 0 || C <= 0 || D <= 0) return YB_ERR_ARG;
+  if (Wh % D != 0 || D % 8 != 0 || (reinterpret_cast<uintptr_t>(buf) & 0xF)) return YB_ERR_SHAPE;
+  sp_post_norm_rope_kernel<<<(L + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<__nv_bfloat16*>(buf), static_cast<const float*>(sums), static_cast<const float*>(wq),
+      static_cast<const float*>(wk), static_cast<const float2*>(rope), rope_len, L, Wh, C, D, eps);
+  return check_launch("sp_post_norm_rope");
+}
 
 extern "C" int yb_sp_scatter_qkv(const void* qkv, long long ld, const void* wq, const void* wk, const void* rope,
                                  int rope_len, int L, int C, int D, float eps, void* const* peers, int world, int rank,

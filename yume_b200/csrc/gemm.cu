@@ -53,7 +53,15 @@ struct GemmParams {
   int out_t_mul, out_t_add;     // output frame of input frame t = t*out_t_mul + out_t_add (time_conv interleave)
   int num_m_tiles, num_n_tiles;
   int block_n, stages;          // SM-pair kernel (gemm_pair_kernel): runtime N tile (multiple of 32, <= 256) and ring depth
+  // YB_EPI_SP_QKV (internal): the fused q|k|v projection of a Ulysses rank whose epilogue IS the all-to-all — column
+  // (part, head h, d) of local token t is stored into the receive buffer of the rank that owns head h (NVLink peer pointer),
+  // layout [P(src), Lp, q|k|v of heads/P]; and the per-row sums of squares of the q and k parts (WanRMSNorm spans all heads)
+  // are accumulated into sp_sums [Lp][2] for the receiver-side normalisation
+  __nv_bfloat16* sp_peers[8];
+  float* sp_sums;
+  int sp_rank, sp_Lp, sp_Wh, sp_C;
 };
+constexpr int YB_EPI_SP_QKV = 6;   // not part of the public enum: reached through yb_gemm_sp_qkv only
 
 // CONVW = 1: kw-fused implicit-GEMM conv. The three kw taps of one (dt, dh, channel-chunk) group read the SAME TMA halo
 // box of 130 voxels along W; tap dw is fed to the MMA by moving the A descriptor's start address by dw 128-byte rows
@@ -95,9 +103,9 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m_tiles, int num_n
 // access is a full 64/128-byte row segment shared by 4/8 adjacent lanes instead of 32 different rows per instruction.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], int col0, int my_row, int my_tok,
-                                               float* stage, int lane) {
+                                               float* stage, int lane, float* sq = nullptr) {
   constexpr bool kBf16Out = (EPI == YB_EPI_BF16 || EPI == YB_EPI_GELU_BF16 || EPI == YB_EPI_GELU_ERF_BF16 ||
-                             EPI == YB_EPI_RES_BF16);
+                             EPI == YB_EPI_RES_BF16 || EPI == YB_EPI_SP_QKV);
   float4* st = reinterpret_cast<float4*>(stage + lane * 36);
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -117,6 +125,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
       long long col_off = col0 + cq;
       if (p.n_split > 0) col_off = static_cast<long long>(col0 / p.n_split) * p.split_stride + (col0 % p.n_split) + cq;
       __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + col_off;
+      long long sp_ld = p.ldo;
+      if (EPI == YB_EPI_SP_QKV) {   // destination = the owner rank's receive buffer; rows are (this rank, local token)
+        const int part = col0 / p.sp_C, cin = col0 - part * p.sp_C;
+        const int peer = cin / p.sp_Wh;
+        sp_ld = 3LL * p.sp_Wh;
+        obase = p.sp_peers[peer] + static_cast<long long>(p.sp_rank) * p.sp_Lp * sp_ld + part * p.sp_Wh + (cin - peer * p.sp_Wh) + cq;
+      }
       uint4 resv[4];
       if (EPI == YB_EPI_RES_BF16) {  // residual loads first (they may alias the stores for all the compiler knows)
 #pragma unroll
@@ -158,7 +173,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
           w.y = pack_bf16x2(v[2], v[3]);
           w.z = pack_bf16x2(v[4], v[5]);
           w.w = pack_bf16x2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(obase + static_cast<long long>(rowi) * p.ldo) = w;
+          *reinterpret_cast<uint4*>(obase + static_cast<long long>(rowi) * (EPI == YB_EPI_SP_QKV ? sp_ld : p.ldo)) = w;
+          if (EPI == YB_EPI_SP_QKV) {   // sum of squares of the ROUNDED values (what the receiver normalises)
+            const __nv_bfloat162* wh = reinterpret_cast<const __nv_bfloat162*>(&w);
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __bfloat1622float2(wh[i]);
+              acc += f.x * f.x + f.y * f.y;
+            }
+            sq[it] += acc;
+          }
         }
       }
     } else {
@@ -591,14 +616,36 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (EPI == YB_EPI_GATE_RES && p.gate != nullptr && p.tok_idx != nullptr && my_row >= 0) my_tok = p.tok_idx[my_row];
       mbar_wait(&tmem_full[acc], (local >> 1) & 1);
       tc_fence_after();
+      float sq[4] = {0.f, 0.f, 0.f, 0.f};   // SP_QKV: running sum of squares of tile rows it*8 + lane/4 over the current part
+      auto flush_sq = [&](int part) {       // 4 lanes share a row: reduce, one atomic per row and (tile, part)
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          float v = sq[it];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          const int rowi = __shfl_sync(0xffffffffu, my_row, it * 8 + (lane >> 2));
+          if ((lane & 3) == 0 && rowi >= 0 && part < 2) atomicAdd(p.sp_sums + rowi * 2 + part, v);
+          sq[it] = 0.f;
+        }
+      };
+      int cur_part = (EPI == YB_EPI_SP_QKV) ? (n_tile * block_n) / p.sp_C : 0;
 #pragma unroll 1
       for (int c = 0; c < block_n / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(t_row + c * 32, r);
         tmem_ld_wait();
-        epilogue_chunk<EPI>(p, r, n_tile * block_n + c * 32, my_row, my_tok, stage, lane);
+        const int col0 = n_tile * block_n + c * 32;
+        if (EPI == YB_EPI_SP_QKV && col0 < p.N) {
+          const int part = col0 / p.sp_C;
+          if (part != cur_part) {
+            flush_sq(cur_part);
+            cur_part = part;
+          }
+        }
+        epilogue_chunk<EPI>(p, r, col0, my_row, my_tok, stage, lane, sq);
         __syncwarp();
       }
+      if (EPI == YB_EPI_SP_QKV) flush_sq(cur_part);
       tc_fence_before();
       mbar_arrive_leader(&tmem_empty[acc]);
     }
@@ -642,7 +689,30 @@ static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, Gemm
   int stages = (227 * 1024 - 256 - PAIR_EPI_STAGE_BYTES - 1024) / pair_stage_bytes(p.block_n);
   p.stages = stages > PAIR_MAX_STAGES ? PAIR_MAX_STAGES : stages;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+  // persistent grid = the number of CTA pairs the device can hold at once (GPCs with an odd SM count leave an SM unpaired;
+  // asked of the driver once per device, the SM count / 2 if the query is unavailable)
+  static int max_clusters[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (max_clusters[dev] == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (sm_count() / 2));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = 227 * 1024;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      (void)cudaGetLastError();
+      n = sm_count() / 2;
+    }
+    max_clusters[dev] = n;
+  }
+  const int clusters = tiles < max_clusters[dev] ? tiles : max_clusters[dev];
   kern<<<2 * clusters, GEMM_THREADS, pair_smem_bytes(p.block_n, p.stages), stream>>>(tmA, tmB, p);
   return check_launch("gemm_pair");
 }
@@ -690,6 +760,36 @@ static void conv_plan(int T, int H, int W, int block_n, int kw, int fuse_policy,
 }
 
 }  // namespace yb
+
+// Fused q|k|v projection + Ulysses all-to-all (see GemmParams): out rows go straight into the owner ranks' receive buffers.
+extern "C" int yb_gemm_sp_qkv(const void* A, long long lda, const void* W, const void* bias, int Lp_rows, int C, int K,
+                              void* const* peers, int world, int rank, int Lp, void* sums, void* stream_) {
+  using namespace yb;
+  if (!A || !W || !peers || !sums || Lp_rows <= 0 || C <= 0 || K <= 0) return YB_ERR_ARG;
+  if (world < 2 || world > 8 || rank < 0 || rank >= world || Lp < Lp_rows) return YB_ERR_ARG;
+  if (C % (world * 128) != 0 || K % 8 != 0 || (lda % 8)) return YB_ERR_SHAPE;
+  GemmParams p = {};
+  p.M = Lp_rows;
+  p.N = 3 * C;
+  p.K = K;
+  p.bias = static_cast<const float*>(bias);
+  p.out = peers[rank];
+  p.ldo = 3LL * (C / world);
+  p.a_split = K;
+  p.sp_rank = rank;
+  p.sp_Lp = Lp;
+  p.sp_Wh = C / world;
+  p.sp_C = C;
+  p.sp_sums = static_cast<float*>(sums);
+  for (int i = 0; i < 8; ++i) p.sp_peers[i] = i < world ? static_cast<__nv_bfloat16*>(peers[i]) : nullptr;
+  p.block_n = pair_block_n(p.M, p.N, sm_count() / 2);
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_3d(&tmA, A, 1, p.M, K, lda, lda * (long long)p.M + 8, GEMM_BLOCK_M, GEMM_BLOCK_K);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, W, p.N, K, K, p.block_n / 2, GEMM_BLOCK_K);
+  if (rc) return rc;
+  return launch_gemm_pair<YB_EPI_SP_QKV>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream_));
+}
 
 extern "C" int yb_gemm_plan(int M, int N, int sms, int* out4) {
   if (M <= 0 || N <= 0 || sms < 2 || !out4) return YB_ERR_ARG;

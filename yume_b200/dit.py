@@ -227,12 +227,14 @@ class WanDiT:
 
     def enable_sequence_parallel(self, group, transport: str = "auto") -> None:
         """Shard the token sequence Ulysses-style over `group` (one process per GPU). transport: "p2p" = exchanges
-        fused into the kernels over NVLink peer memory (torch symmetric memory), "nccl" = NCCL all_to_all_single,
-        "auto" = p2p when symmetric memory is available. For the NCCL path builds the peer-major fused q|k|v weight:
+        fused into the kernels over NVLink peer memory (torch symmetric memory) — the q|k|v exchange rides in the RMSNorm+RoPE
+        pass, the output exchange in the attention epilogue; "p2p_gemm" = as p2p, but the q|k|v exchange is the EPILOGUE OF THE
+        QKV GEMM itself (yb_gemm_sp_qkv: peer stores under the main loop, normalisation finished on the receiver);
+        "nccl" = NCCL all_to_all_single; "auto" = p2p when symmetric memory is available. For the NCCL path builds the peer-major fused q|k|v weight:
         rows ordered [peer p][q, k, v][heads p*H/P .. (p+1)*H/P) so that the QKV GEMM's `n_split` epilogue emits
         exactly the chunks the all-to-all sends."""
-        if transport not in ("auto", "p2p", "nccl"):
-            raise YumeB200Error("transport must be auto, p2p or nccl")
+        if transport not in ("auto", "p2p", "p2p_gemm", "nccl"):
+            raise YumeB200Error("transport must be auto, p2p, p2p_gemm or nccl")
         self.sp_transport, self._sp_p2p = transport, None
         import torch.distributed as dist
         P = dist.get_world_size(group)
@@ -241,7 +243,15 @@ class WanDiT:
         self.sp_group, self.sp_world, self.sp_rank = group, P, dist.get_rank(group)
         if P == 1:
             return
-        idx = sp_qkv_row_order(self.dim, self.heads, P).to(self.device)
+        if transport == "nccl":
+            self._build_nccl_weights()
+
+    def _build_nccl_weights(self) -> None:
+        """Peer-major copies of the fused q|k|v weights: only the NCCL transport reads them (+6.3 GB at 14B), so they are
+        built when that transport is chosen — up front, or when symmetric memory turns out to be unavailable."""
+        if "w_qkv_sp" in self.blocks[0]:
+            return
+        idx = sp_qkv_row_order(self.dim, self.heads, self.sp_world).to(self.device)
         for b in self.blocks:
             b["w_qkv_sp"] = b["w_qkv"][idx].contiguous()
             b["b_qkv_sp"] = b["b_qkv"][idx].contiguous()
@@ -314,9 +324,11 @@ class WanDiT:
     # ------------------------------------------------------------------------------------------------------
     # pieces of the forward
     # ------------------------------------------------------------------------------------------------------
-    def _embed_tokens(self, u: Tensor, name: str, patch: int, out_rows: Tensor) -> Tuple[int, int, int]:
-        """Patch-embed u [Cin, f, H, W] (f32, any strides) with Conv3d `name` (kernel == stride == (1,patch,patch)),
-        writing f32 token rows into out_rows [f*hp*wp, C]. Returns (f, hp, wp)."""
+    def _embed_tokens(self, u: Tensor, name: str, patch: int, xs: Tensor, row0: int, window: Tuple[int, int]) -> None:
+        """Patch-embed u [Cin, f, H, W] (f32, any strides) with Conv3d `name` (kernel == stride == (1,patch,patch)). The
+        segment's tokens are global rows [row0, row0 + n); `xs` holds the global rows `window` = [w0, w1) (the whole sequence,
+        or this rank's Ulysses shard): only the rows of the segment that fall inside the window are projected — under
+        sequence parallelism every rank embeds just its own tokens (the patch gather itself is a cheap index pass)."""
         w, b = self.embed[name]
         cin, f, H, W = u.shape
         if name == "patch_embedding":          # plain Conv3d, no convpadd: odd H / W lose their last row / column
@@ -324,12 +336,30 @@ class WanDiT:
             cin, f, H, W = u.shape
         hp, wp = -(-H // patch), -(-W // patch)
         n_tok = f * hp * wp
+        lo, hi = max(row0, window[0]), min(row0 + n_tok, window[1])
+        if lo >= hi:
+            return
         a = self._buf("patch_a", (n_tok, w.shape[1]), _BF16)
         if w.shape[1] != cin * patch * patch:
             a.zero_()                                           # K padding columns must be zero
         ops.patchify(u, a, patch, patch)
-        ops.gemm(a, w, b, out_rows, ops.YB_EPI_F32)
-        return f, hp, wp
+        ops.gemm(a[lo - row0:hi - row0], w, b, xs[lo - window[0]:hi - window[0]], ops.YB_EPI_F32)
+
+    def _token_stream(self, L: int, n_real: int) -> Tuple[Tensor, Tuple[int, int]]:
+        """The fp32 residual stream and the window of global token rows it holds: all L rows on one GPU, this rank's
+        contiguous shard of ceil(L / P) rows under Ulysses. Rows that no embedder writes (zero padding tokens of a padded
+        grid, rows >= n_real; shard rows past L) are zeroed here."""
+        if self.sp_world > 1:
+            Lp, r0, n_valid = sp_shard(L, self.sp_world, self.sp_rank)
+            xs = self._buf("xs_shard", (Lp, self.dim), _F32)
+            filled = max(0, min(n_real, r0 + n_valid) - r0)
+            if filled < Lp:
+                xs[filled:].zero_()
+            return xs, (r0, r0 + n_valid)
+        xs = self._buf("xs", (L, self.dim), _F32)
+        if n_real < L:
+            xs[n_real:].zero_()
+        return xs, (0, L)
 
     def _time_tables(self, t_unique: Tensor):
         """e [U, C], per-block modulation tables [layers, U, 6, C], head table [U, 2, C] (model.py:805-812, 296, 344)."""
@@ -382,18 +412,34 @@ class WanDiT:
             bases = [int(x) for x in hdl.buffer_ptrs]
             off_q = [0, n_qkv]
             off_a = [2 * n_qkv, 2 * n_qkv + n_att]
+            sbuf = symm.empty(2 * P * Lp * 2, dtype=_F32, device=self.device)    # [parity][P(src)][Lp][q, k] sums of squares
+            shdl = symm.rendezvous(sbuf, self.sp_group)
+            sbases = [int(x) for x in shdl.buffer_ptrs]
             self._sp_p2p = dict(
+                sums_buf=sbuf, sums_hdl=shdl, sums=[sbuf[o:o + P * Lp * 2].view(P * Lp, 2) for o in (0, P * Lp * 2)],
+                sums_ptrs=[[bp + 4 * o for bp in sbases] for o in (0, P * Lp * 2)],
+                sums_local=torch.zeros(Lp, 2, device=self.device, dtype=_F32),
                 Lp=Lp, buf=buf, hdl=hdl,
                 qkv=[buf[o:o + n_qkv].view(P, Lp, 3 * Wh) for o in off_q],
                 att=[buf[o:o + n_att].view(P, Lp, Wh) for o in off_a],
                 qkv_ptrs=[[bp + 2 * o for bp in bases] for o in off_q],
                 att_ptrs=[[bp + 2 * o for bp in bases] for o in off_a])
+            ok = True
         except Exception as e:  # transport choice only: the NCCL path below runs the same kernels
-            if self.sp_transport == "p2p":
-                raise
+            ok, err = False, e
+        # the ranks must take the SAME transport: agree on the outcome (a rank that failed alone would otherwise sit in an
+        # NCCL all-to-all while its peers wait on a symmetric-memory barrier)
+        import torch.distributed as dist
+        flag = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.sp_group)
+        if int(flag.item()) == 0:
+            self._sp_p2p = None
+            if self.sp_transport in ("p2p", "p2p_gemm"):
+                raise YumeB200Error("symmetric memory unavailable on at least one rank" + ("" if ok else f": {err}"))
             import warnings
-            warnings.warn(f"yume_b200: symmetric memory unavailable ({type(e).__name__}: {e}); Ulysses uses NCCL all-to-all")
+            warnings.warn("yume_b200: symmetric memory unavailable; Ulysses uses NCCL all-to-all")
             self.sp_transport = "nccl"
+            self._build_nccl_weights()
             return None
         return self._sp_p2p
 
@@ -410,15 +456,30 @@ class WanDiT:
         Lp = xs.shape[0]
         par = i & 1
         T = self.timer
-        qkv = self._buf("qkv", (Lp, 3 * C), _BF16)
-        T.begin("gemm_qkv")
-        ops.gemm(h, b["w_qkv"], b["b_qkv"], qkv, ops.YB_EPI_BF16)
-        T.end("gemm_qkv")
-        T.begin("sp_scatter_qkv")
-        ops.sp_scatter_qkv(qkv, b["nq"], b["nk"], rope, rope_len, D, self.eps, st["qkv_ptrs"][par], self.sp_rank, Lp)
-        st["hdl"].barrier(channel=0)
-        T.end("sp_scatter_qkv")
         full = st["qkv"][par].view(P * Lp, 3 * Wh)
+        if self.sp_transport == "p2p_gemm":
+            # GEMM + all-to-all in one kernel: the projection's epilogue stores every head's columns into its owner's receive
+            # buffer and accumulates the per-token sums of squares; the receiver finishes RMSNorm + RoPE after the barrier
+            T.begin("gemm_qkv")
+            ops.gemm_sp_qkv(h, b["w_qkv"], b["b_qkv"], st["qkv_ptrs"][par], self.sp_rank, Lp, st["sums_local"])
+            T.end("gemm_qkv")
+            T.begin("sp_scatter_qkv")
+            ops.sp_bcast_sums(st["sums_local"], st["sums_ptrs"][par], self.sp_rank, Lp)
+            st["hdl"].barrier(channel=0)
+            r0w = self.sp_rank * Wh
+            rope_g, rope_len_g = self._sp_rope_global
+            ops.sp_post_norm_rope(full, st["sums"][par], b["nq"][r0w:r0w + Wh], b["nk"][r0w:r0w + Wh], rope_g, rope_len_g,
+                                  P * Lp, Wh, C, D, self.eps)
+            T.end("sp_scatter_qkv")
+        else:
+            qkv = self._buf("qkv", (Lp, 3 * C), _BF16)
+            T.begin("gemm_qkv")
+            ops.gemm(h, b["w_qkv"], b["b_qkv"], qkv, ops.YB_EPI_BF16)
+            T.end("gemm_qkv")
+            T.begin("sp_scatter_qkv")
+            ops.sp_scatter_qkv(qkv, b["nq"], b["nk"], rope, rope_len, D, self.eps, st["qkv_ptrs"][par], self.sp_rank, Lp)
+            st["hdl"].barrier(channel=0)
+            T.end("sp_scatter_qkv")
         T.begin("self_attention")
         ops.attention_sp(full[:, :Wh], full[:L_true, Wh:2 * Wh], full[:L_true, 2 * Wh:], st["att_ptrs"][par], Wh, Hp,
                          self.sp_rank, Lp)
@@ -760,7 +821,7 @@ class WanDiT:
             new_shape = (latent_frame_zero, Hh // 2, Ww // 2)
             L_hist = sum(f * a * b for f, a, b in shapes)
             L = L_hist + new_shape[0] * new_shape[1] * new_shape[2]
-            xs = self._buf("xs", (L, C), _F32)
+            xs, window = self._token_stream(L, L)
             row, f_z, rope_segs = 0, 0, []
             for seg, (f, hp, wp) in zip(plan, shapes):
                 src = u1[:, seg.frames]
@@ -774,11 +835,11 @@ class WanDiT:
                     ld = tmp.stride(0)                         # view the token-major result as [Cin, f, h, w]
                     src = torch.as_strided(tmp, (cin, f2, h2, w2), (1, h2 * w2 * ld, w2 * ld, ld))
                 n = f * hp * wp
-                self._embed_tokens(src, seg.name, seg.patch, xs[row:row + n])
+                self._embed_tokens(src, seg.name, seg.patch, xs, row, window)
                 rope_segs.append((f, hp, wp, f_z))
                 row += n
                 f_z += f
-            self._embed_tokens(u2, "patch_embedding", 2, xs[row:])
+            self._embed_tokens(u2, "patch_embedding", 2, xs, row, window)
             rope_segs.append((*new_shape, f_z))
             grid_new, rope_len = new_shape, L
         else:
@@ -787,10 +848,8 @@ class WanDiT:
             if L_grid > seq_len:
                 raise AssertionError("seq_lens.max() <= seq_len")   # model.py:755
             L, L_hist = seq_len, 0
-            xs = self._buf("xs", (L, C), _F32)
-            self._embed_tokens(x, "patch_embedding", 2, xs[:L_grid])
-            if L > L_grid:
-                xs[L_grid:].zero_()                            # padded tokens are zeros (model.py:756-759)
+            xs, window = self._token_stream(L, L_grid)         # rows >= L_grid: zero padding tokens (model.py:756-759)
+            self._embed_tokens(x, "patch_embedding", 2, xs, 0, window)
             rope_segs, rope_len = [(*grid_new, 0)], L_grid
         rope = self._rope_table(rope_segs)
 
@@ -827,17 +886,13 @@ class WanDiT:
         L_true = L_grid if (self.variant == "14b" and not packed) else L
         if self.sp_world > 1:
             import torch.distributed as dist
-            Lp, r0, n_valid = sp_shard(L, self.sp_world, self.sp_rank)
-            xs_full = xs
-            xs = self._buf("xs_shard", (Lp, C), _F32)
-            xs[:n_valid].copy_(xs_full[r0:r0 + n_valid])
-            if n_valid < Lp:
-                xs[n_valid:].zero_()                           # padding tokens (never used as keys: Lk = L_true)
+            Lp, r0, n_valid = sp_shard(L, self.sp_world, self.sp_rank)   # xs already IS this rank's shard (_token_stream)
             if tok_idx is not None:
                 ti = self._buf("tok_idx_shard", (Lp,), torch.int32)
                 ti.zero_()
                 ti[:n_valid].copy_(tok_idx[r0:r0 + n_valid])
                 tok_idx = ti
+            self._sp_rope_global = (rope, rope_len)              # the p2p_gemm transport rotates on the receiver: global rows
             rope = rope[min(r0, rope.shape[0]):]
             if rope.shape[0] == 0:
                 rope = self._rope_table(rope_segs)[:1]

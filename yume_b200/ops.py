@@ -452,6 +452,43 @@ def sp_scatter_qkv(qkv: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, rope: 
     _launches += 1
 
 
+def gemm_sp_qkv(h: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, peer_ptrs, rank: int, Lp: int,
+                sums: torch.Tensor) -> None:
+    """Fused q|k|v projection whose epilogue is the Ulysses all-to-all (yb_gemm_sp_qkv). h bf16 [Lp, K]; w_qkv bf16 [3C, K]."""
+    global _launches, _flops
+    _need(h, torch.bfloat16, "h")
+    _need(w_qkv, torch.bfloat16, "w_qkv")
+    _need(b_qkv, torch.float32, "b_qkv")
+    _need(sums, torch.float32, "sums")
+    if not w_qkv.is_contiguous():
+        raise YumeB200Error("gemm_sp_qkv weight must be contiguous")
+    M, K = h.shape
+    C3 = w_qkv.shape[0]
+    check(_lib.load().yb_gemm_sp_qkv(h.data_ptr(), h.stride(0), w_qkv.data_ptr(), b_qkv.data_ptr(), M, C3 // 3, K,
+                                     _ptr_array(peer_ptrs), len(peer_ptrs), rank, Lp, sums.data_ptr(), _stream()),
+          "yb_gemm_sp_qkv")
+    _launches += 1
+    _flops += 2.0 * M * C3 * K
+
+
+def sp_bcast_sums(local: torch.Tensor, peer_table_ptrs, rank: int, Lp: int) -> None:
+    global _launches
+    check(_lib.load().yb_sp_bcast_sums(local.data_ptr(), _ptr_array(peer_table_ptrs), len(peer_table_ptrs), rank, Lp, _stream()),
+          "yb_sp_bcast_sums")
+    _launches += 1
+
+
+def sp_post_norm_rope(buf: torch.Tensor, sums: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, rope: Optional[torch.Tensor],
+                      rope_len: int, L: int, Wh: int, Cdim: int, head_dim: int, eps: float) -> None:
+    """buf bf16 [>= L rows, 3*Wh] received q|k|v rows in global token order; sums f32 [>= L, 2]; wq / wk f32 [Wh] = this rank's
+    slice of the norm weights; rope f32 [>= L, D/2, 2] rows of the GLOBAL tokens."""
+    global _launches
+    _need(buf, torch.bfloat16, "buf")
+    check(_lib.load().yb_sp_post_norm_rope(buf.data_ptr(), sums.data_ptr(), wq.data_ptr(), wk.data_ptr(), _ptr(rope), rope_len, L,
+                                           Wh, Cdim, head_dim, eps, _stream()), "yb_sp_post_norm_rope")
+    _launches += 1
+
+
 def attention_sp(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out_peer_ptrs, ldo: int, heads: int, rank: int,
                  Lp: int, scale: Optional[float] = None, softmax: Optional[int] = None) -> None:
     global _launches, _flops
