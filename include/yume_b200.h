@@ -82,7 +82,8 @@ int yb_gemm_plan(int M, int N, int sms, int* out4);
  * ------------------------------------------------------------------------------------------- */
 typedef struct yb_conv3d_args {
   unsigned int struct_bytes; /* = sizeof(yb_conv3d_args) */
-  int reserved;              /* 0 */
+  int cta_pair;              /* 0 = 1-CTA kernel (kw-fused where the planner chooses it); 1 = SM-pair kernel: each CTA of a
+                                cluster owns one 128-voxel box, the weight tile is split between the two (un-fused taps) */
   const void* xpad;
   const void* w;
   const void* bias; /* f32 [Cout] or NULL */

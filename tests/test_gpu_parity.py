@@ -692,6 +692,13 @@ def test_conv3d_causal_matches_torch(dev, T, H, W, ci, co, fuse_w):
     o32 = torch.empty(T * H * W, co, device=dev)
     ops.conv3d_causal(xpad, wk, None, o32, T, H, W, ops.YB_EPI_F32, fuse_w=fuse_w)
     assert rel(o32, ref - res.float() - b) < 1e-4
+    if fuse_w == 1:   # SM-pair conv kernel: same taps, same K order -> the 1-CTA un-fused result bit for bit
+        pair = torch.full_like(out, 3.0)
+        ops.conv3d_causal(xpad, wk, b, pair, T, H, W, ops.YB_EPI_RES_BF16, res, cta_pair=1)
+        assert torch.equal(pair, out)
+        p32 = torch.empty_like(o32)
+        ops.conv3d_causal(xpad, wk, None, p32, T, H, W, ops.YB_EPI_F32, cta_pair=1)
+        assert torch.equal(p32, o32)
 
 
 def test_vae_glue_kernels(dev):

@@ -301,6 +301,25 @@ def sec_gemmpair():
             print(line, flush=True)
 
 
+def sec_convpair():
+    """Causal conv as implicit GEMM: 1-CTA un-fused / 1-CTA kw-fused / SM-pair kernel on the widths of the three VAE decoders."""
+    shapes = [("hy 128->128 @17x256x256", 17, 256, 256, 128, 128), ("hy 256->256 @17x128x128", 17, 128, 128, 256, 256),
+              ("hy 512->512 @9x64x64", 9, 64, 64, 512, 512), ("w21 96->96 @21x272x480", 21, 272, 480, 128, 96),
+              ("w21 192->192 @21x136x240", 21, 136, 240, 192, 192), ("w22 256->256 @21x176x320", 21, 176, 320, 256, 256),
+              ("w21 384->384 @11x68x120", 11, 68, 120, 384, 384)]
+    for name, T, H, W, ci, co in shapes:
+        x = torch.randn(T + 2, H + 2, W + 2, ci, device=dev).bfloat16()
+        wk = (torch.randn(co, 27 * ci, device=dev) / math.sqrt(27 * ci)).bfloat16()
+        outs, line = [], f"convpair {name}:"
+        fl = 2.0 * T * H * W * 27 * ci * co
+        for label, kw in (("1cta", dict(fuse_w=1)), ("1cta-kwfused", dict(fuse_w=2)), ("pair", dict(cta_pair=1))):
+            o = torch.empty(T * H * W, co, device=dev, dtype=torch.bfloat16)
+            ms = timeit(lambda: ops.conv3d_causal(x, wk, None, o, T, H, W, ops.YB_EPI_BF16, **kw), 3)
+            outs.append(o)
+            line += f"  {label} {ms:.3f} ms ({fl/ms/1e9:.0f} TF/s)"
+        print(line + f"  equal={torch.equal(outs[0], outs[2])} fused_rel={rel(outs[1], outs[0])[0]:.1e}", flush=True)
+
+
 def sec_atttrace():
     from yume_b200 import _lib
     heads, L = 24, 18480
@@ -333,9 +352,9 @@ def sec_atttrace():
     print("raw rows 0..2:", (t[:3] - base).tolist())
 
 
-SECTIONS = {"attmodes": sec_attmodes, "gemmpair": sec_gemmpair, "attsplit": sec_attsplit, "atttrace": sec_atttrace, "atttune": sec_atttune, "probe": sec_probe, "gemm": sec_gemm, "attention": sec_attention, "elementwise": sec_elementwise}
+SECTIONS = {"attmodes": sec_attmodes, "gemmpair": sec_gemmpair, "convpair": sec_convpair, "attsplit": sec_attsplit, "atttrace": sec_atttrace, "atttune": sec_atttune, "probe": sec_probe, "gemm": sec_gemm, "attention": sec_attention, "elementwise": sec_elementwise}
 if __name__ == "__main__":
-    names = sys.argv[1:] or [n for n in SECTIONS if n not in ("gemmpair", "attmodes")]   # experimental sections only on request
+    names = sys.argv[1:] or [n for n in SECTIONS if n not in ("gemmpair", "attmodes", "convpair")]   # experimental sections only on request
     print(torch.cuda.get_device_name(0))
     for n in names:
         print(f"===== {n} =====", flush=True)

@@ -44,7 +44,7 @@ class Conv3dArgs(C.Structure):
     """Mirror of `struct yb_conv3d_args`."""
 
     _fields_ = [
-        ("struct_bytes", C.c_uint), ("reserved", C.c_int),
+        ("struct_bytes", C.c_uint), ("cta_pair", C.c_int),
         ("xpad", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p), ("res", C.c_void_p),
         ("ldo", C.c_longlong), ("res_ld", C.c_longlong),
         ("T", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cp", C.c_int), ("Cout", C.c_int), ("epilogue", C.c_int),

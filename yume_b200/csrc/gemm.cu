@@ -557,8 +557,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sa = smem + stage * stage_bytes;
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
           const int kcol = kb * GEMM_BLOCK_K;
-          const int chunk = kcol / p.a_split;      // K-split A (Ulysses receive buffer): see the 1-CTA producer
-          tma_load_3d_2cta(sa, &tmA, &full_bar[stage], kcol - chunk * p.a_split, (m_tile * 2 + rank) * GEMM_BLOCK_M, chunk);
+          if (p.conv) {   // implicit-GEMM conv: this CTA's 128-voxel box of tap (dt, dh, dw), channel chunk cc (see gemm_kernel)
+            const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
+            const int dt = tap / (p.kh * p.kw), dh = (tap / p.kw) % p.kh, dw = tap % p.kw;
+            const int mt = m_tile * 2 + rank, per_t = p.tiles_h * p.tiles_w;
+            const int it = mt / per_t, rem = mt - it * per_t;
+            const int ih = rem / p.tiles_w, iw = rem - ih * p.tiles_w;
+            tma_load_4d_2cta(sa, &tmA, &full_bar[stage], cc * GEMM_BLOCK_K, iw * p.TW + dw - p.off_w, ih * p.TH + dh - p.off_h,
+                             it * p.TT + dt - p.off_t);   // (a pair's second box past the last tile is all out of bounds: zeros)
+          } else {
+            const int chunk = kcol / p.a_split;      // K-split A (Ulysses receive buffer): see the 1-CTA producer
+            tma_load_3d_2cta(sa, &tmA, &full_bar[stage], kcol - chunk * p.a_split, (m_tile * 2 + rank) * GEMM_BLOCK_M, chunk);
+          }
           tma_load_2d_2cta(sa + GEMM_BLOCK_M * GEMM_BLOCK_K * 2, &tmB, &full_bar[stage], kcol,
                            n_tile * block_n + rank * (block_n / 2));
           if (++stage == stages) {
@@ -604,8 +614,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tile_coords(tile, p.num_m_tiles, p.num_n_tiles, m_tile, n_tile);
       const int acc = local & 1;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
-      const int row = (m_tile * 2 + rank) * GEMM_BLOCK_M + quad * 32 + lane;
-      const int my_row = row < p.M ? row : -1;
+      int my_row;
+      if (p.conv) {   // tile row -> voxel of this CTA's TT x TH x TW box -> output row (see gemm_kernel)
+        const int r = quad * 32 + lane, mt = m_tile * 2 + rank, per_t = p.tiles_h * p.tiles_w;
+        const int it = mt / per_t, rem = mt - it * per_t;
+        const int ih = rem / p.tiles_w, iw = rem - ih * p.tiles_w;
+        const int tw = r % p.TW, th = (r / p.TW) % p.TH, tt = r / (p.TW * p.TH);
+        const int t = it * p.TT + tt, hh = ih * p.TH + th, ww = iw * p.TW + tw;
+        my_row = (t < p.cT && hh < p.cH && ww < p.cW) ? ((t * p.out_t_mul + p.out_t_add) * p.cH + hh) * p.cW + ww : -1;
+      } else {
+        const int row = (m_tile * 2 + rank) * GEMM_BLOCK_M + quad * 32 + lane;
+        my_row = row < p.M ? row : -1;
+      }
       const int ncols = min(block_n, p.N - n_tile * block_n);
       if (EPI == YB_EPI_GATE_RES && my_row >= 0) {   // pull the (cold) residual rows of this tile into L2 under the main loop
         const char* xrow = reinterpret_cast<const char*>(reinterpret_cast<const float*>(p.out) +
@@ -684,7 +704,7 @@ static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, Gemm
   auto kern = gemm_pair_kernel<EPI>;
   static bool attr_set[kMaxDevices] = {false};
   if (int rc = ensure_dynamic_smem(kern, 227 * 1024, attr_set, "gemm_pair")) return rc;
-  p.num_m_tiles = (p.M + 255) / 256;
+  p.num_m_tiles = p.conv ? (p.num_m_tiles + 1) / 2 : (p.M + 255) / 256;   // conv: pairs of 128-voxel boxes
   p.num_n_tiles = (p.N + p.block_n - 1) / p.block_n;
   int stages = (227 * 1024 - 256 - PAIR_EPI_STAGE_BYTES - 1024) / pair_stage_bytes(p.block_n);
   p.stages = stages > PAIR_MAX_STAGES ? PAIR_MAX_STAGES : stages;
@@ -907,7 +927,8 @@ extern "C" int yb_conv3d_causal(const yb_conv3d_args* a, void* stream_) {
   if ((kt != 1 && kt != 3) || (kh != 1 && kh != 3) || (kw != 1 && kw != 3)) return YB_ERR_SHAPE;
   const int block_n = (a->Cout % 256 == 0) ? 256 : 128;
   bool fuse_w = false;
-  conv_plan(a->T, a->H, a->W, block_n, kw, a->fuse_w, &p.TW, &p.TH, &p.TT, &fuse_w);
+  if (a->cta_pair < 0 || a->cta_pair > 1) return YB_ERR_ARG;
+  conv_plan(a->T, a->H, a->W, block_n, kw, a->cta_pair == 1 ? 1 : a->fuse_w, &p.TW, &p.TH, &p.TT, &fuse_w);
   p.tiles_w = (a->W + p.TW - 1) / p.TW;
   p.tiles_h = (a->H + p.TH - 1) / p.TH;
   const int tiles_t = (a->T + p.TT - 1) / p.TT;
@@ -940,6 +961,21 @@ extern "C" int yb_conv3d_causal(const yb_conv3d_args* a, void* stream_) {
   rc = make_tmap_bf16_2d(&tmB, a->w, a->Cout, static_cast<uint64_t>(taps) * a->Cp, static_cast<uint64_t>(taps) * a->Cp,
                          block_n, GEMM_BLOCK_K);
   if (rc) return rc;
+  // SM-pair kernel (un-fused taps; each CTA of the pair owns one 128-voxel box, the weight tile is split between them):
+  // selected by a->cta_pair (1 = always, 0 = never until the per-width crossover is measured)
+  if (a->cta_pair == 1 && !fuse_w) {
+    p.conv = 1;
+    p.block_n = a->Cout <= 256 ? a->Cout : pair_block_n(2 * p.num_m_tiles * 128, a->Cout, sm_count() / 2);
+    CUtensorMap tmBp;
+    rc = make_tmap_bf16_2d(&tmBp, a->w, a->Cout, static_cast<uint64_t>(taps) * a->Cp, static_cast<uint64_t>(taps) * a->Cp,
+                           p.block_n / 2, GEMM_BLOCK_K);
+    if (rc) return rc;
+    switch (a->epilogue) {
+      case YB_EPI_BF16: return launch_gemm_pair<YB_EPI_BF16>(tmA, tmBp, p, stream);
+      case YB_EPI_F32: return launch_gemm_pair<YB_EPI_F32>(tmA, tmBp, p, stream);
+      default: return launch_gemm_pair<YB_EPI_RES_BF16>(tmA, tmBp, p, stream);
+    }
+  }
 #define YB_CONV_DISPATCH(BN, CW)                                                              \
   switch (a->epilogue) {                                                                     \
     case YB_EPI_BF16: return launch_gemm<BN, YB_EPI_BF16, CW>(tmA, tmB, p, stream);           \

@@ -319,9 +319,15 @@ def umma_probe(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
 YB_EPI_RES_BF16 = YB_EPI_RES_BF16
 
 
+# kernel choice of conv3d_causal when the caller does not say (0 = 1-CTA kernel, 1 = SM-pair kernel); set per engine after the
+# per-width crossover measurement (profiles/README.md)
+CONV_CTA_PAIR = 0
+
+
 def conv3d_causal(xpad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, T: int, H: int,
                   W: int, epilogue: int = YB_EPI_BF16, res: Optional[torch.Tensor] = None, taps=(3, 3, 3),
-                  oob_zero_pad: bool = False, out_t_mul: int = 1, out_t_add: int = 0, fuse_w: int = 0) -> torch.Tensor:
+                  oob_zero_pad: bool = False, out_t_mul: int = 1, out_t_add: int = 0, fuse_w: int = 0,
+                  cta_pair: Optional[int] = None) -> torch.Tensor:
     """Implicit-GEMM causal conv. Default: xpad bf16 [T+2, H+2, W+2, Cp] replicate padded (hyvideo VAE). With
     oob_zero_pad the input is the unpadded [T, H, W, Cp] and the zero padding is TMA out-of-bounds fill (Wan2.2 VAE).
     w bf16 [Cout, kt*kh*kw*Cp]; out rows are output voxels (frame t -> t*out_t_mul + out_t_add)."""
@@ -336,7 +342,8 @@ def conv3d_causal(xpad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tens
     _need(out, torch.float32 if epilogue == YB_EPI_F32 else torch.bfloat16, "out")
     if res is not None:
         _need(res, torch.bfloat16, "res")
-    args = Conv3dArgs(struct_bytes=C.sizeof(Conv3dArgs), reserved=0, xpad=xpad.data_ptr(), w=w.data_ptr(), bias=_ptr(bias), out=out.data_ptr(), res=_ptr(res),
+    args = Conv3dArgs(struct_bytes=C.sizeof(Conv3dArgs), cta_pair=CONV_CTA_PAIR if cta_pair is None else cta_pair,
+                      xpad=xpad.data_ptr(), w=w.data_ptr(), bias=_ptr(bias), out=out.data_ptr(), res=_ptr(res),
                       ldo=out.stride(0), res_ld=(res.stride(0) if res is not None else 0), T=T, H=H, W=W, Cp=Cp,
                       Cout=w.shape[0], epilogue=epilogue, kt=kt, kh=kh, kw=kw, oob_zero_pad=1 if oob_zero_pad else 0,
                       out_t_mul=out_t_mul, out_t_add=out_t_add, fuse_w=fuse_w)
