@@ -157,7 +157,7 @@ int yb_attention(const void* q, long long ldq, const void* k, long long ldk, con
 /* Full form. `ws` / `ws_bytes`: caller-owned device workspace for the automatic KV tail split (size it with
  * yb_attention_workspace_bytes; NULL or too small = the launch is not split — same result, a partly idle last wave; the
  * library itself never allocates and never synchronises, so the call is CUDA-graph-capture safe). `trace`: optional clock64
- * trace buffer (int64 [32*32]) filled by CTA (1,0) for KV tiles 16..47 (classic softmax schedule only): per tile
+ * trace buffer (int64 [32*32]) filled by CTA (1,0) for KV tiles 16..47: per tile
  * [X*8 + {0: before S wait, 1: S ready, 2: S in registers, 3: row max done, 4: P stored, 5: arrived}] for the softmax
  * warp of query tile X, and [16 + X*4 + {0: before P wait, 1: P ready, 2: PV+S issued}] for the MMA thread. Tuning / tests
  * only; pass NULL in production. */
@@ -172,9 +172,8 @@ int yb_attention_ex(const void* q, long long ldq, const void* k, long long ldk, 
 #define YB_ATT_SPLIT_SHIFT 4 /* flags bits 4-6: KV split policy. 0 = automatic (the units of a last wave that is at most
                                half full are cut into KV segments and merged by a combine kernel), 1 = never, 2..4 = cut
                                EVERY unit into that many segments (tests). Results are identical up to fp32 rounding. */
-#define YB_ATT_SM_SHIFT 8   /* flags bits 8-9: softmax schedule. 0 = classic (tile max before the exponentials), 1 = deferred max
-                               (exponentials against the running reference, exactness guard; attention.cu), 2 = deferred max
-                               with packed bf16x2 exponentials (argument rounded to bf16: see attention.cu for the error bound) */
+#define YB_ATT_SM_SHIFT 8   /* flags bits 8-9: softmax schedule. 0 = classic, 1 = pipelined (S halves loaded under the FMNMX3 max pass,
+                               one TMEM-store wait for both P halves); bit-identical results — attention.cu */
 /* Host-only: the work decomposition yb_attention would use on a GPU with `sms` SMs (no device access; the CPU test-suite
  * pins the scheduler with it). out4 = {CTAs running whole units, tail units that are split, KV segments per tail unit,
  * 128-key tiles per segment}. flags as for yb_attention (ACCUMULATE disables the split; bits 4-6 force it). */

@@ -204,7 +204,7 @@ def test_attention_kv_split_matches_unsplit(dev, Lq, Lk, heads, split):
     k = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
     v = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
     one = ops.attention(q, k, v, torch.empty_like(q), heads, split=1)
-    two = ops.attention(q, k, v, torch.full_like(q, 9.0), heads, split=split, softmax=split % 3)   # every schedule once
+    two = ops.attention(q, k, v, torch.full_like(q, 9.0), heads, split=split, softmax=split % 2)   # both schedules
     assert rel(two, one) < 3e-3                      # both bf16-rounded; segments change the fp32 summation order only
     qh, kh, vh = (x.float().view(-1, heads, 128).transpose(0, 1) for x in (q, k, v))
     ref = torch.softmax(qh @ kh.transpose(1, 2) / math.sqrt(128.0), dim=-1) @ vh
@@ -223,11 +223,9 @@ def test_attention_auto_tail_split_full_size_properties(dev):
     assert bool(torch.isfinite(b.float()).all()) and rel(b, a) < 3e-3
 
 
-# (variant, softmax schedule): product kernel with the classic / deferred-max / deferred-max + bf16x2-exponential schedules
-# (include/yume_b200.h YB_ATT_SM_SHIFT), and the debug variant that stages P through shared memory
-ATT_MODES = [(0, 0), (0, 1), (0, 2), (1, 0)]
-# the bf16x2 schedule rounds the exponent argument to bf16 (attention.cu): zero-mean error of the order of P's own rounding
-ATT_TOL = {0: KERNEL_TOL, 1: KERNEL_TOL, 2: 6e-3}
+# (variant, softmax schedule): product kernel with the classic / pipelined schedules (include/yume_b200.h YB_ATT_SM_SHIFT),
+# and the debug variant that stages P through shared memory
+ATT_MODES = [(0, 0), (0, 1), (1, 0)]
 
 
 @pytest.mark.parametrize("variant,softmax", ATT_MODES)
@@ -241,10 +239,12 @@ def test_attention_matches_sdpa(dev, variant, softmax, Lq, Lk, heads):
     out = torch.zeros(Lq, heads * 128, device=dev, dtype=torch.bfloat16)
     ops.attention(q, k, v, out, heads, variant=variant, softmax=softmax)
     assert torch.isfinite(out.float()).all()
-    assert rel(out, _sdpa(q, k, v, heads)) < ATT_TOL[softmax]
+    assert rel(out, _sdpa(q, k, v, heads)) < KERNEL_TOL
+    if (variant, softmax) == (0, 1):   # the pipelined schedule reorders instructions, not arithmetic: bit-identical
+        assert torch.equal(out, ops.attention(q, k, v, torch.zeros_like(out), heads, softmax=0))
 
 
-@pytest.mark.parametrize("softmax", [0, 1, 2])
+@pytest.mark.parametrize("softmax", [0, 1])
 def test_attention_large_logits_and_accumulate(dev, softmax):
     from yume_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(11)
@@ -253,35 +253,13 @@ def test_attention_large_logits_and_accumulate(dev, softmax):
     k = (torch.randn(Lk, heads * 128, generator=g) * 4).to(dev).bfloat16()
     v = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
     out = torch.zeros(Lq, heads * 128, device=dev, dtype=torch.bfloat16)
-    ops.attention(q, k, v, out, heads, softmax=softmax)   # row maxima jump by >> 2^8: lazy O rescale / exactness guard paths
+    ops.attention(q, k, v, out, heads, softmax=softmax)   # row maxima jump by >> 2^8: exercises the lazy O rescale
     ref = _sdpa(q, k, v, heads)
-    assert rel(out, ref) < ATT_TOL[softmax]
+    assert rel(out, ref) < KERNEL_TOL
     k2 = torch.randn(257, heads * 128, generator=g).to(dev).bfloat16()
     v2 = torch.randn(257, heads * 128, generator=g).to(dev).bfloat16()
     ops.attention(q, k2, v2, out, heads, accumulate=True, softmax=softmax)
-    assert rel(out, ref + _sdpa(q, k2, v2, heads)) < 2 * ATT_TOL[softmax]
-
-
-@pytest.mark.parametrize("softmax", [1, 2])
-def test_attention_deferred_max_guard_paths(dev, softmax):
-    """Adversarial rows for the deferred-max schedules: the dominant key sits in the SECOND half of a LATE tile and beats
-    everything before it by ~2^100 (guard on the second half: wait for P.V of the first half, rescale, recompute), and in the
-    first half of another tile; a third set of rows has a key far BELOW the running max (underflow side)."""
-    from yume_b200 import ops
-    g = torch.Generator(device="cpu").manual_seed(13)
-    Lq, Lk, heads = 256, 1024, 1
-    q = torch.randn(Lq, 128, generator=g)
-    k = torch.randn(Lk, 128, generator=g) * 0.3
-    v = torch.randn(Lk, 128, generator=g)
-    qn = q / q.norm(dim=1, keepdim=True)
-    k[700] = qn[:64].mean(0) * 900.0        # tile 5, key 60 of the tile (first half) -> huge logit for rows 0..63
-    k[888] = qn[64:128].mean(0) * 1200.0    # tile 6, key 120 of the tile (second half) for rows 64..127
-    k[5] = -qn[128:192].mean(0) * 900.0     # a key far below everything for rows 128..191
-    q[:192] = qn[:192] * 40.0
-    q, k, v = q.to(dev).bfloat16(), k.to(dev).bfloat16(), v.to(dev).bfloat16()
-    out = ops.attention(q, k, v, torch.zeros(Lq, 128, device=dev, dtype=torch.bfloat16), heads, softmax=softmax)
-    assert torch.isfinite(out.float()).all()
-    assert rel(out, _sdpa(q, k, v, heads)) < ATT_TOL[softmax]
+    assert rel(out, ref + _sdpa(q, k2, v2, heads)) < 2 * KERNEL_TOL
 
 
 def test_elementwise_kernels(dev):
@@ -667,6 +645,17 @@ def test_ulysses_matches_golden(dev, world, transport, split):
 # hyvideo causal 3D VAE decode
 # ------------------------------------------------------------------------------------------------------------
 VAE_TOL = 3e-2   # ~35 bf16 conv/norm layers deep; fp32 oracle / reference fixtures
+VAE_PSNR_DB = 40.0   # the same bar as an image metric: decoded video lives in [-1, 1] (peak-to-peak 2); rel-Fro 3e-2 on an output
+                     # of RMS ~0.5 is ~42 dB. The Wan VAEs run in fp32 in the reference (vae2_2.py:918): this is the error budget
+                     # of multiplying in bf16 (fp32 accumulation, fp32 norms / softmax) instead.
+
+
+def psnr(got, want):
+    """PSNR in dB against the reference's own dynamic range (2 for a clamped [-1, 1] video; random-init fixtures can be wider)."""
+    want = want.float().cpu()
+    mse = float((got.float().cpu() - want).pow(2).mean())
+    peak = max(2.0, float(want.max() - want.min()))
+    return 10.0 * math.log10(peak * peak / max(mse, 1e-20))
 
 
 @pytest.mark.parametrize("T,H,W,ci,co", [(3, 8, 8, 64, 64), (2, 6, 10, 128, 128), (5, 32, 32, 64, 256), (1, 18, 32, 128, 96),
@@ -760,6 +749,7 @@ def test_vae_decode_vs_reference_golden(dev, vae_gold, case):
     assert tuple(out.shape) == c["shape"]
     for name, got in (("sample", out[..., ::3, ::3]), ("rowsum", out.sum(-1)), ("colsum", out.sum(-2))):
         assert float((got - c[name]).norm() / c[name].norm()) < VAE_TOL, name
+        assert psnr(got, c[name]) > VAE_PSNR_DB, name
 
 
 def test_vae_decode_real_width_tile_vs_oracle(dev):
@@ -771,7 +761,7 @@ def test_vae_decode_real_width_tile_vs_oracle(dev):
     z = torch.randn(1, 16, 2, 4, 4, generator=torch.Generator().manual_seed(5))
     want = hyvae.HyVaeOracle(sd, **cfg).decode(z)
     got = HyVaeDecoder(sd, device=dev, **cfg).decode(z).cpu()
-    assert got.shape == want.shape and rel(got, want) < VAE_TOL
+    assert got.shape == want.shape and rel(got, want) < VAE_TOL and psnr(got, want) > VAE_PSNR_DB
 
 
 # ---- Wan2.2 VAE (wan23/modules/vae2_2.py) -------------------------------------------------------------------------
@@ -855,6 +845,7 @@ def test_wan22_vae_decode_vs_reference_golden(dev, vae22_gold, case):
     assert tuple(out.shape) == c["shape"]
     for name, got in (("sample", out[..., ::3, ::3]), ("rowsum", out.sum(-1)), ("colsum", out.sum(-2))):
         assert float((got - c[name]).norm() / c[name].norm()) < VAE_TOL, name
+        assert psnr(got, c[name]) > VAE_PSNR_DB, name
 
 
 def test_wan22_vae_decode_real_width_vs_oracle(dev):
@@ -868,7 +859,7 @@ def test_wan22_vae_decode_real_width_vs_oracle(dev):
     z = torch.randn(48, 2, 2, 4, generator=gen)
     want = wan22vae.Wan22VaeOracle(sd, mean=mean, std=std, **cfg).decode(z)
     got = Wan22VaeDecoder(sd, mean=mean, std=std, device=dev, **cfg).decode(z).cpu()
-    assert got.shape == want.shape and rel(got, want) < VAE_TOL
+    assert got.shape == want.shape and rel(got, want) < VAE_TOL and psnr(got, want) > VAE_PSNR_DB
 
 
 # ---- Wan2.1 VAE (wan/modules/vae.py) ------------------------------------------------------------------------------
@@ -890,6 +881,7 @@ def test_wan21_vae_decode_vs_reference_golden(dev, vae21_gold, case):
     assert tuple(out.shape) == c["shape"]
     for name, got in (("sample", out[..., ::3, ::3]), ("rowsum", out.sum(-1)), ("colsum", out.sum(-2))):
         assert float((got - c[name]).norm() / c[name].norm()) < VAE_TOL, name
+        assert psnr(got, c[name]) > VAE_PSNR_DB, name
 
 
 def test_wan21_vae_decode_real_width_vs_oracle(dev):
@@ -903,5 +895,5 @@ def test_wan21_vae_decode_real_width_vs_oracle(dev):
     z = torch.randn(16, 3, 4, 6, generator=gen)
     want = wan21vae.Wan21VaeOracle(sd, mean=mean, std=std, **cfg).decode(z)
     got = Wan21VaeDecoder(sd, mean=mean, std=std, device=dev, **cfg).decode(z).cpu()
-    assert got.shape == want.shape and rel(got, want) < VAE_TOL
+    assert got.shape == want.shape and rel(got, want) < VAE_TOL and psnr(got, want) > VAE_PSNR_DB
     assert float(got.min()) >= -1.0 and float(got.max()) <= 1.0

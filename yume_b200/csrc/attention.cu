@@ -61,18 +61,14 @@ struct AttCfg {
 // EMU: 0 = every exp2 on the MUFU; n > 0 = one of every n probability PAIRS is computed by exp2_poly2 on the FMA pipe
 // (the MUFU's 16 ex2/clk/SM is exactly co-saturated with the tensor pipe at head_dim 128, so part of the
 // exponentials has to move off it for the MMA to stay fed).
-// SM (softmax schedule): 0 = classic: the exact row max of the tile is found before any exponential (LDTM x4 -> 128 max ops ->
-// exps: ~450 cycles of load + max sit in front of the 1024-cycle MUFU phase on the per-tile critical path).
-// 1 / 2 = DEFERRED MAX: the exponentials of tile j use the reference m_used left by the tiles before it, so they start as soon as
-// the first half of S is in registers; the tile's own max is computed beside them on the ALU pipe (FMNMX3) and only steers
-//   * the lazy rescale, applied at the START of the next iteration (P.V of this tile has retired by then), and
-//   * an exactness guard: if a half-tile's max exceeds m_used by more than kGuard (2^kGuard headroom before fp32/bf16 overflow is
-//     ~2^127) the warp raises m_used first — for the second half after waiting for the first half's P.V (pv0_done) — rescales O and
-//     recomputes that half. Results are those of the classic schedule up to the usual fp32 reassociation; nothing is approximated.
-// 2 additionally evaluates the exponentials as ex2.approx.ftz.bf16x2: ONE MUFU op yields two probabilities already in the bf16x2
-// format of P (halves the MUFU work that co-limits the kernel at head_dim 128, drops the separate F2FP pack). The argument is
-// rounded to bf16 (|x| <= kGuard = 8 -> relative error of p <= 1.1 %, typically ~0.1 %: zero-mean, same order as the bf16
-// rounding of P itself); the lazy-rescale window is tightened to 2^1 so the dominant keys have |x| <= 1.
+// SM (softmax schedule): 0 = classic (all of S loaded, 128 FMNMX, exponentials, each P half stored + waited + published).
+// 1 = pipelined: S halves loaded back to back with the max pass (FMNMX3: 64 ALU instructions instead of 128) running under the
+// second load; the TMEM store of P's first half is not waited for — one wait after the second half covers both, then both halves
+// are published. Removes ~100 cycles of max and one store round trip from the per-tile critical path
+// (profiles/r02_experimental_runbook.md has the cycle trace that motivated it). Results are bit-identical to schedule 0.
+// Tried and dropped in round 2 (profiles/r02_attention_schedules.md): exponentials against a stale reference with a deferred
+// max + exactness guard (3.30 vs 3.18 ms), and packed `ex2.approx.ftz.bf16x2` exponentials (4.24 ms: MUFU.EX2.BF16 is not
+// double rate, and unpacking for the row sum costs more than the F2FP it saves).
 template <bool P_TMEM, int EMU, int SM>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -87,8 +83,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* s_full = kv_empty + NS;
   uint64_t* p_half = s_full + 2;  // [X][half]: P columns [64*half, 64*half+64) of query tile X are in place
   uint64_t* o_done = p_half + 4;
-  uint64_t* pv0_done = o_done + 2;   // [X]: P.V of the first key half of the current tile has retired (SM >= 1 guard path only)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv0_done + 2);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -123,7 +118,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&p_half[2 * i], 128);
       mbar_init(&p_half[2 * i + 1], 128);
       mbar_init(&o_done[i], 1);
-      mbar_init(&pv0_done[i], 1);
     }
     fence_barrier_init();
   }
@@ -233,7 +227,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (tr) tr[1] = clock64();
           tc_fence_after();
           issue_PV(X, vbase, j > 0, 0);             // keys 0..63 of the tile, while the softmax warps finish 64..127
-          if (SM >= 1) umma_commit(&pv0_done[X]);
           mbar_wait(&p_half[2 * X + 1], j & 1);
           tc_fence_after();
           issue_PV(X, vbase, true, 1);
@@ -268,163 +261,56 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       decode(unit, kv_begin, nkv);
       kv_end = kv_begin + nkv;
     }
-    if constexpr (SM >= 1) {
-      // ------------------------ deferred-max schedule (see the comment above the kernel) ------------------------
-      constexpr float kLazy = (SM == 2) ? 1.0f : 8.0f;     // rescale O when the running max grew by more than 2^kLazy
-      constexpr float kGuard = (SM == 2) ? 8.0f : 64.0f;   // exactness guard: never evaluate 2^x for x > kGuard
-      float ms_prev = -INFINITY;                           // scaled max of the previous tile's scores
-      auto rescale_to = [&](float m_new) {                 // O *= 2^(m_used - m_new), l likewise (alpha == 1 where nothing grew)
-        const float alpha = fast_exp2(m_used - m_new);
-        l *= alpha;
+    for (int j = kv_begin; j < kv_end; ++j) {   // global KV tile index (kv_begin is even: parity of j == local parity)
+      long long* tr = (p.trace != nullptr && blockIdx.x == 1 && (warp & 3) == 0 && lane == 0 && j >= 16 && j < 48)
+                          ? p.trace + (j - 16) * 32 + X * 8 : nullptr;
+      if (tr) tr[0] = clock64();
+      mbar_wait(&s_full[X], j & 1);
+      if (tr) tr[1] = clock64();
+      tc_fence_after();
+      const int kv_rem = p.Lk - j * 128;
+      if (kv_rem < 128) {
+        // last, partial KV tile (k_lens contract): overwrite the out-of-range columns of S with -inf in TMEM.
+        // Kept as a cold side-effecting loop so the per-element selects are not if-converted into every tile.
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tO + c * 32, o);
+        for (int c = kv_rem >> 5; c < 4; ++c) {
+          uint32_t t[32];
+          tmem_ld32(tS + c * 32, t);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st32(tO + c * 32, o);
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= kv_rem) t[i] = 0xff800000u;  // -inf
+          tmem_st32(tS + c * 32, t);
         }
         tmem_st_wait();
-        m_used = m_new;
-      };
-      for (int j = kv_begin; j < kv_end; ++j) {   // global KV tile index (kv_begin is even: parity of j == local parity)
-        mbar_wait(&s_full[X], j & 1);
-        tc_fence_after();
-        const int kv_rem = p.Lk - j * 128;
-        if (kv_rem < 128) {   // last, partial KV tile: out-of-range columns of S become -inf in TMEM (cold path)
-#pragma unroll 1
-          for (int c = kv_rem >> 5; c < 4; ++c) {
-            uint32_t t[32];
-            tmem_ld32(tS + c * 32, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= kv_rem) t[i] = 0xff800000u;  // -inf
-            tmem_st32(tS + c * 32, t);
-          }
-          tmem_st_wait();
-        }
-        const bool first = (j == kv_begin);
-        if (!first && __any_sync(0xffffffffu, ms_prev > m_used + kLazy)) rescale_to(fmaxf(m_used, ms_prev));
-        uint32_t s[4][32];
+      }
+      uint32_t s[4][32];
+      float mx;
+      if constexpr (SM == 1) {
+        // pipelined: the second half of S is still in flight while the first half's maxima are taken; 3-input FMNMX3 halves
+        // the max pass (64 instead of 128 ALU instructions per row)
         tmem_ld32(tS + 0, s[0]);
         tmem_ld32(tS + 32, s[1]);
-        if (first) {   // no reference yet: the first tile takes its exact max before the exponentials
-          tmem_ld32(tS + 64, s[2]);
-          tmem_ld32(tS + 96, s[3]);
-          tmem_ld_wait();
-          reg_fence32(s[0]); reg_fence32(s[1]); reg_fence32(s[2]); reg_fence32(s[3]);
-          float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        tmem_ld_wait();
+        reg_fence32(s[0]); reg_fence32(s[1]);
+        tmem_ld32(tS + 64, s[2]);
+        tmem_ld32(tS + 96, s[3]);
+        float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
-            for (int i = 0; i < 32; i += 2)
-              mxa[(i >> 1) & 3] = fmax3(mxa[(i >> 1) & 3], __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
-          m_used = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * sc;
-        } else {
-          tmem_ld_wait();
-          reg_fence32(s[0]); reg_fence32(s[1]);
-          tmem_ld32(tS + 64, s[2]);   // second half of S stays in flight under the first half's exponentials
-          tmem_ld32(tS + 96, s[3]);
-        }
-        const uint64_t sc2 = f2_pack(sc, sc);
-        float ms_tile = -INFINITY;
+          for (int i = 0; i < 32; i += 2)
+            mxa[(i >> 1) & 3] = fmax3(mxa[(i >> 1) & 3], __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
+        tmem_ld_wait();
+        reg_fence32(s[2]); reg_fence32(s[3]);
+        if (tr) tr[2] = clock64();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (h == 1 && !first) {
-            tmem_ld_wait();
-            reg_fence32(s[2]); reg_fence32(s[3]);
-          }
-          // this half's max of the raw scores: 32 FMNMX3 on the ALU pipe, independent of the exponentials below
-          float hm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        for (int c = 2; c < 4; ++c)
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; i += 2)
-              hm[(i >> 1) & 3] = fmax3(hm[(i >> 1) & 3], __uint_as_float(s[2 * h + c][i]), __uint_as_float(s[2 * h + c][i + 1]));
-          const float msh = fmaxf(fmaxf(hm[0], hm[1]), fmaxf(hm[2], hm[3])) * sc;
-          ms_tile = fmaxf(ms_tile, msh);
-          uint32_t pk[32];
-          float lsum;
-          auto exps = [&]() {   // pk = bf16x2(2^(s*sc - m_used)) for the 64 keys of this half, lsum = their sum
-            const uint64_t negm2 = f2_pack(-m_used, -m_used);
-            uint64_t ls2[2] = {0ull, 0ull};
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int c0 = h * 64 + 2 * i;
-              const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[c0 >> 5][c0 & 31]),
-                                                 __uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31])), sc2, negm2);
-              uint64_t p2;
-              if (SM == 2) {
-                float x0, x1;
-                f2_unpack(x2, x0, x1);
-                const uint32_t pb = ex2_bf16x2(pack_bf16x2(x0, x1));
-                pk[i] = pb;
-                p2 = f2_pack(__uint_as_float(pb << 16), __uint_as_float(pb & 0xffff0000u));
-              } else {
-                float p0, p1;
-                if ((EMU > 0) && (i % (EMU > 0 ? EMU : 1) == EMU - 1)) {
-                  p2 = exp2_poly2(x2);
-                  f2_unpack(p2, p0, p1);
-                } else {
-                  float x0, x1;
-                  f2_unpack(x2, x0, x1);
-                  p0 = fast_exp2(x0);
-                  p1 = fast_exp2(x1);
-                  p2 = f2_pack(p0, p1);
-                }
-                pk[i] = pack_bf16x2(p0, p1);
-              }
-              ls2[i & 1] = f2_add(ls2[i & 1], p2);
-            }
-            float a0, a1, b0, b1;
-            f2_unpack(ls2[0], a0, a1);
-            f2_unpack(ls2[1], b0, b1);
-            lsum = (a0 + a1) + (b0 + b1);
-          };
-          exps();
-          if (__any_sync(0xffffffffu, msh > m_used + kGuard)) {   // guard (rare): raise the reference first, then redo this half
-            if (h == 1) {                                         // O_X is being updated by P.V of the first half: wait for it
-              mbar_wait(&pv0_done[X], j & 1);
-              tc_fence_after();
-            }
-            rescale_to(fmaxf(m_used, msh));
-            exps();
-          }
-          l += lsum;
-          tmem_st32(tS + h * 32, pk);
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&p_half[2 * X + h]);
-        }
-        ms_prev = ms_tile;
-      }
-    } else {
-      for (int j = kv_begin; j < kv_end; ++j) {   // global KV tile index (kv_begin is even: parity of j == local parity)
-        long long* tr = (p.trace != nullptr && blockIdx.x == 1 && (warp & 3) == 0 && lane == 0 && j >= 16 && j < 48)
-                            ? p.trace + (j - 16) * 32 + X * 8 : nullptr;
-        if (tr) tr[0] = clock64();
-        mbar_wait(&s_full[X], j & 1);
-        if (tr) tr[1] = clock64();
-        tc_fence_after();
-        const int kv_rem = p.Lk - j * 128;
-        if (kv_rem < 128) {
-          // last, partial KV tile (k_lens contract): overwrite the out-of-range columns of S with -inf in TMEM.
-          // Kept as a cold side-effecting loop so the per-element selects are not if-converted into every tile.
-  #pragma unroll 1
-          for (int c = kv_rem >> 5; c < 4; ++c) {
-            uint32_t t[32];
-            tmem_ld32(tS + c * 32, t);
-            tmem_ld_wait();
-  #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= kv_rem) t[i] = 0xff800000u;  // -inf
-            tmem_st32(tS + c * 32, t);
-          }
-          tmem_st_wait();
-        }
-        uint32_t s[4][32];
+          for (int i = 0; i < 32; i += 2)
+            mxa[(i >> 1) & 3] = fmax3(mxa[(i >> 1) & 3], __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
+        mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+      } else {
         tmem_ld32(tS + 0, s[0]);
         tmem_ld32(tS + 32, s[1]);
         tmem_ld32(tS + 64, s[2]);
@@ -433,93 +319,104 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (tr) tr[2] = clock64();
         // 8 independent running maxima (a single fmaxf chain is 128 dependent ops of 4-cycle latency each)
         float mxa[8];
-  #pragma unroll
+#pragma unroll
         for (int a = 0; a < 8; ++a) mxa[a] = -INFINITY;
-  #pragma unroll
+#pragma unroll
         for (int c = 0; c < 4; ++c)
-  #pragma unroll
+#pragma unroll
           for (int i = 0; i < 32; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(s[c][i]));
-        const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
-                               fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
-        const float ms = mx * sc;
-        if (tr) {
-          asm volatile("" ::"f"(ms));
-          tr[3] = clock64();
-        }
-        if (j == kv_begin) {
-          m_used = ms;
-        } else {
-          const bool need = ms > m_used + 8.0f;
-          if (__any_sync(0xffffffffu, need)) {
-            const float m_new = fmaxf(m_used, ms);
-            const float alpha = fast_exp2(m_used - m_new);
-            l *= alpha;
-  #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              uint32_t o[32];
-              tmem_ld32(tO + c * 32, o);
-              tmem_ld_wait();
-  #pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st32(tO + c * 32, o);
-            }
-            tmem_st_wait();
-            m_used = m_new;
+        mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+      }
+      const float ms = mx * sc;
+      if (tr) {
+        asm volatile("" ::"f"(ms));
+        tr[3] = clock64();
+      }
+      if (j == kv_begin) {
+        m_used = ms;
+      } else {
+        const bool need = ms > m_used + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = fmaxf(m_used, ms);
+          const float alpha = fast_exp2(m_used - m_new);
+          l *= alpha;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tO + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tO + c * 32, o);
           }
+          tmem_st_wait();
+          m_used = m_new;
         }
-        // probabilities on packed fp32 pairs: one FFMA2 scales+shifts two scores, one FADD2 accumulates two sums;
-        // every EMU-th pair takes the FMA-pipe polynomial instead of two MUFU.EX2
-        const uint64_t sc2 = f2_pack(sc, sc);
-        const uint64_t negm2 = f2_pack(-m_used, -m_used);
-        uint64_t ls2[2] = {0ull, 0ull};  // two independent packed partial row sums (0ull == (+0.f, +0.f))
-  #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t pk[32];
-  #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int c0 = h * 64 + 2 * i;
-            const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[c0 >> 5][c0 & 31]),
-                                               __uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31])), sc2, negm2);
-            uint64_t p2;
-            float p0, p1;
-            if ((EMU > 0) && (i % (EMU > 0 ? EMU : 1) == EMU - 1)) {
-              p2 = exp2_poly2(x2);
-              f2_unpack(p2, p0, p1);
-            } else {
-              float x0, x1;
-              f2_unpack(x2, x0, x1);
-              p0 = fast_exp2(x0);
-              p1 = fast_exp2(x1);
-              p2 = f2_pack(p0, p1);
-            }
-            ls2[i & 1] = f2_add(ls2[i & 1], p2);
-            pk[i] = pack_bf16x2(p0, p1);
-          }
-          if (P_TMEM) {
-            tmem_st32(tS + h * 32, pk);
-            tmem_st_wait();
+      }
+      // probabilities on packed fp32 pairs: one FFMA2 scales+shifts two scores, one FADD2 accumulates two sums;
+      // every EMU-th pair takes the FMA-pipe polynomial instead of two MUFU.EX2
+      const uint64_t sc2 = f2_pack(sc, sc);
+      const uint64_t negm2 = f2_pack(-m_used, -m_used);
+      uint64_t ls2[2] = {0ull, 0ull};  // two independent packed partial row sums (0ull == (+0.f, +0.f))
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c0 = h * 64 + 2 * i;
+          const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[c0 >> 5][c0 & 31]),
+                                             __uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31])), sc2, negm2);
+          uint64_t p2;
+          float p0, p1;
+          if ((EMU > 0) && (i % (EMU > 0 ? EMU : 1) == EMU - 1)) {
+            p2 = exp2_poly2(x2);
+            f2_unpack(p2, p0, p1);
           } else {
-            // K-major 128B-swizzled slab h of the P tile: row r, 16-byte chunk c -> r*128 + ((c ^ (r & 7)) << 4)
-            uint8_t* slab = smem + Cfg::P_OFF + X * ATT_TILE_BYTES + h * 16384 + row_in_tile * 128;
-  #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              uint4 w = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-              *reinterpret_cast<uint4*>(slab + ((c ^ (row_in_tile & 7)) << 4)) = w;
-            }
-            fence_proxy_async_smem();
+            float x0, x1;
+            f2_unpack(x2, x0, x1);
+            p0 = fast_exp2(x0);
+            p1 = fast_exp2(x1);
+            p2 = f2_pack(p0, p1);
           }
-          if (tr) tr[4 + h] = clock64();
+          ls2[i & 1] = f2_add(ls2[i & 1], p2);
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        if (P_TMEM && SM == 1) {
+          // pipelined hand-off: the store of this half is issued and NOT waited for here — half 0's completion is collected
+          // after the first quarter of half 1's exponentials (see below), only the last store's latency is exposed
+          tmem_st32(tS + h * 32, pk);
+          if (h == 1) tmem_st_wait();
+        } else if (P_TMEM) {
+          tmem_st32(tS + h * 32, pk);
+          tmem_st_wait();
+        } else {
+          // K-major 128B-swizzled slab h of the P tile: row r, 16-byte chunk c -> r*128 + ((c ^ (r & 7)) << 4)
+          uint8_t* slab = smem + Cfg::P_OFF + X * ATT_TILE_BYTES + h * 16384 + row_in_tile * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 w = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            *reinterpret_cast<uint4*>(slab + ((c ^ (row_in_tile & 7)) << 4)) = w;
+          }
+          fence_proxy_async_smem();
+        }
+        if (tr) tr[4 + h] = clock64();
+        if (P_TMEM && SM == 1) {
+          if (h == 1) {   // both stores have completed (single wait above): publish both halves
+            tc_fence_before();
+            mbar_arrive(&p_half[2 * X]);
+            mbar_arrive(&p_half[2 * X + 1]);
+          }
+        } else {
           tc_fence_before();
           mbar_arrive(&p_half[2 * X + h]);
         }
-        {
-          float a0, a1, b0, b1;
-          f2_unpack(ls2[0], a0, a1);
-          f2_unpack(ls2[1], b0, b1);
-          l += (a0 + a1) + (b0 + b1);
-        }
       }
-
+      {
+        float a0, a1, b0, b1;
+        f2_unpack(ls2[0], a0, a1);
+        f2_unpack(ls2[1], b0, b1);
+        l += (a0 + a1) + (b0 + b1);
+      }
     }
 
     // epilogue: O / l -> bf16 -> global [Lq, heads*128]
@@ -701,8 +598,7 @@ static int dispatch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, co
 #define YB_ATT_CASE(E, EMUV, S)                                                                                     \
   if (emu == (E) && sm == (S)) return launch_attention<true, EMUV, S>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
   YB_ATT_CASE(0, 0, 0) YB_ATT_CASE(1, 4, 0) YB_ATT_CASE(2, 3, 0) YB_ATT_CASE(3, 2, 0)
-  YB_ATT_CASE(0, 0, 1) YB_ATT_CASE(1, 4, 1) YB_ATT_CASE(2, 3, 1) YB_ATT_CASE(3, 2, 1)
-  YB_ATT_CASE(0, 0, 2)
+  YB_ATT_CASE(0, 0, 1) YB_ATT_CASE(1, 4, 1)
 #undef YB_ATT_CASE
   return YB_ERR_ARG;
 }
@@ -754,7 +650,6 @@ extern "C" int yb_attention_ex(const void* q, long long ldq, const void* k, long
   if (!q || !k || !v || !out) return YB_ERR_ARG;
   if (Lq <= 0 || Lk <= 0 || heads <= 0) return YB_ERR_ARG;
   if ((ldo % 8) != 0 || (reinterpret_cast<uintptr_t>(out) & 0xF)) return YB_ERR_ALIGNMENT;
-  if (trace != nullptr && ((flags >> YB_ATT_SM_SHIFT) & 3)) return YB_ERR_ARG;   // the clock trace exists in the classic schedule only
   CUtensorMap tmQ, tmK, tmV;
   if (int rc = att_common(q, ldq, k, ldk, v, ldv, Lq, Lk, heads, &tmQ, &tmK, &tmV)) return rc;
   AttParams p;
