@@ -172,8 +172,9 @@ int yb_attention_ex(const void* q, long long ldq, const void* k, long long ldk, 
 #define YB_ATT_SPLIT_SHIFT 4 /* flags bits 4-6: KV split policy. 0 = automatic (the units of a last wave that is at most
                                half full are cut into KV segments and merged by a combine kernel), 1 = never, 2..4 = cut
                                EVERY unit into that many segments (tests). Results are identical up to fp32 rounding. */
-#define YB_ATT_SM_SHIFT 8   /* flags bits 8-9: softmax schedule. 0 = classic, 1 = pipelined (S halves loaded under the FMNMX3 max pass,
-                               one TMEM-store wait for both P halves); bit-identical results — attention.cu */
+#define YB_ATT_SM_SHIFT 8   /* flags bits 8-9: schedule. 0 = classic, 1 = pipelined (S halves loaded under the FMNMX3 max pass, one TMEM-store
+                               wait for both P halves; bit-identical to 0), 2 = lookahead (64-key tiles, S double-buffered in TMEM and
+                               computed one tile ahead of the softmax: attention_la_kernel) — attention.cu */
 /* Host-only: the work decomposition yb_attention would use on a GPU with `sms` SMs (no device access; the CPU test-suite
  * pins the scheduler with it). out4 = {CTAs running whole units, tail units that are split, KV segments per tail unit,
  * 128-key tiles per segment}. flags as for yb_attention (ACCUMULATE disables the split; bits 4-6 force it). */
