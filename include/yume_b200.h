@@ -82,8 +82,8 @@ int yb_gemm_plan(int M, int N, int sms, int* out4);
  * ------------------------------------------------------------------------------------------- */
 typedef struct yb_conv3d_args {
   unsigned int struct_bytes; /* = sizeof(yb_conv3d_args) */
-  int cta_pair;              /* 0 = 1-CTA kernel (kw-fused where the planner chooses it); 1 = SM-pair kernel: each CTA of a
-                                cluster owns one 128-voxel box, the weight tile is split between the two (un-fused taps) */
+  int cta_pair;              /* SM-pair kernel (each CTA of a cluster owns one 128-voxel box, the weight tile is split between the two,
+                                un-fused taps): 0 = automatic (output widths 192 / 384), 1 = always, 2 = never */
   const void* xpad;
   const void* w;
   const void* bias; /* f32 [Cout] or NULL */
@@ -172,9 +172,9 @@ int yb_attention_ex(const void* q, long long ldq, const void* k, long long ldk, 
 #define YB_ATT_SPLIT_SHIFT 4 /* flags bits 4-6: KV split policy. 0 = automatic (the units of a last wave that is at most
                                half full are cut into KV segments and merged by a combine kernel), 1 = never, 2..4 = cut
                                EVERY unit into that many segments (tests). Results are identical up to fp32 rounding. */
-#define YB_ATT_SM_SHIFT 8   /* flags bits 8-9: schedule. 0 = classic, 1 = pipelined (S halves loaded under the FMNMX3 max pass, one TMEM-store
-                               wait for both P halves; bit-identical to 0), 2 = lookahead (64-key tiles, S double-buffered in TMEM and
-                               computed one tile ahead of the softmax: attention_la_kernel) — attention.cu */
+#define YB_ATT_SM_SHIFT 8   /* flags bits 8-9: kernel schedule. bit 0: pack P to bf16 on the ALU pipe (IADD + PRMT, round-half-up) instead of
+                               F2FP; bit 1: LOOKAHEAD schedule (64-key tiles, S double-buffered in TMEM and computed one tile ahead of
+                               the softmax: attention_la_kernel). 0 = the round-1 kernel. attention.cu has the measurements. */
 /* Host-only: the work decomposition yb_attention would use on a GPU with `sms` SMs (no device access; the CPU test-suite
  * pins the scheduler with it). out4 = {CTAs running whole units, tail units that are split, KV segments per tail unit,
  * 128-key tiles per segment}. flags as for yb_attention (ACCUMULATE disables the split; bits 4-6 force it). */

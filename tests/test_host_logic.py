@@ -387,3 +387,22 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         assert int(got[cname]) == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
+def test_gemm_plan_kernel_choice():
+    """Host-side kernel / tile choice of yb_gemm_bf16 (yb_gemm_plan): the SM-pair kernel with 256-wide tiles for the token GEMMs,
+    the 1-CTA kernel for the small context / embedding projections."""
+    import ctypes as C
+    lib = yume_b200.load()
+    out = (C.c_int * 4)()
+
+    def plan(M, N):
+        assert lib.yb_gemm_plan(M, N, 148, out) == 0
+        return tuple(out)
+    assert plan(18480, 3072) == (1, 256, 73, 12)
+    assert plan(18480, 14336) == (1, 256, 73, 56)
+    assert plan(2310, 9216) == (1, 256, 10, 36)
+    assert plan(1024, 128) == (1, 128, 4, 1)
+    assert plan(512, 3072) == (0, 256, 4, 12)            # context rows: 1-CTA kernel
+    assert plan(257, 96) == (0, 128, 3, 1)
+    assert lib.yb_gemm_plan(0, 128, 148, out) != 0

@@ -262,7 +262,7 @@ def sec_attmodes():
         idx = torch.randint(0, L, (256,), device=dev)
         ref = sdpa_ref(q[idx].contiguous(), k, v, heads)
         fl = 4.0 * L * L * heads * 128
-        for sm, emu in ((0, 0), (1, 0), (2, 0), (2, 1), (0, 1)):
+        for sm, emu in ((0, 0), (1, 0), (2, 0), (3, 0), (3, 1)):
             ms = min(timeit(lambda: ops.attention(q, k, v, out, heads, emu=emu, softmax=sm), n=5) for _ in range(3))
             print(f"attmodes heads={heads} L={L} softmax={sm} emu={emu}: {ms:.3f} ms = {fl/ms/1e9:.0f} TF/s   rel/max {rel(out[idx], ref)}", flush=True)
     try:
@@ -312,7 +312,7 @@ def sec_convpair():
         wk = (torch.randn(co, 27 * ci, device=dev) / math.sqrt(27 * ci)).bfloat16()
         outs, line = [], f"convpair {name}:"
         fl = 2.0 * T * H * W * 27 * ci * co
-        for label, kw in (("1cta", dict(fuse_w=1)), ("1cta-kwfused", dict(fuse_w=2)), ("pair", dict(cta_pair=1))):
+        for label, kw in (("1cta", dict(fuse_w=1, cta_pair=2)), ("1cta-kwfused", dict(fuse_w=2, cta_pair=2)), ("pair", dict(cta_pair=1))):
             o = torch.empty(T * H * W, co, device=dev, dtype=torch.bfloat16)
             ms = timeit(lambda: ops.conv3d_causal(x, wk, None, o, T, H, W, ops.YB_EPI_BF16, **kw), 3)
             outs.append(o)
@@ -322,7 +322,7 @@ def sec_convpair():
 
 def sec_atttrace():
     for sm in (0, 1):
-        print(f'--- softmax schedule {sm}')
+        print(f'--- schedule {sm} (0 = F2FP pack, 1 = ALU pack)')
         _atttrace(sm)
 
 

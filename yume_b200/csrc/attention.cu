@@ -125,14 +125,13 @@ struct AttCfg {
 // EMU: 0 = every exp2 on the MUFU; n > 0 = one of every n probability PAIRS is computed by exp2_poly2 on the FMA pipe
 // (the MUFU's 16 ex2/clk/SM is exactly co-saturated with the tensor pipe at head_dim 128, so part of the
 // exponentials has to move off it for the MMA to stay fed).
-// SM (softmax schedule): 0 = classic (all of S loaded, 128 FMNMX, exponentials, each P half stored + waited + published).
-// 1 = pipelined: S halves loaded back to back with the max pass (FMNMX3: 64 ALU instructions instead of 128) running under the
-// second load; the TMEM store of P's first half is not waited for — one wait after the second half covers both, then both halves
-// are published. Removes ~100 cycles of max and one store round trip from the per-tile critical path
-// (profiles/r02_experimental_runbook.md has the cycle trace that motivated it). Results are bit-identical to schedule 0.
-// Tried and dropped in round 2 (profiles/r02_attention_schedules.md): exponentials against a stale reference with a deferred
-// max + exactness guard (3.30 vs 3.18 ms), and packed `ex2.approx.ftz.bf16x2` exponentials (4.24 ms: MUFU.EX2.BF16 is not
-// double rate, and unpacking for the row sum costs more than the F2FP it saves).
+// SM: 0 = probabilities packed to bf16x2 with F2FP (cvt.rn.bf16x2.f32), 1 = packed on the ALU pipe (IADD + PRMT,
+// round-half-up: differs from round-to-nearest-even only on exact ties). The exponential phase of a tile takes ~1400 cycles for
+// 128 MUFU.EX2 per thread (1024 cycles at 16 ex2/clk/SM): the trace is consistent with F2FP sharing the MUFU's issue port.
+// Tried and dropped in round 2 (profiles/r02_attention_schedules.md): exponentials against a stale reference with a deferred max
+// (3.30 vs 3.18 ms), packed `ex2.approx.ftz.bf16x2` exponentials (4.24 ms), and a pipelined variant of this schedule (FMNMX3 max
+// under a split S load, one TMEM-store wait for both P halves: 3.29 vs 3.10 ms — the later hand-off of the first P half delays the
+// MMA thread by more than the max pass saves).
 template <bool P_TMEM, int EMU, int SM>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -349,48 +348,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_st_wait();
       }
       uint32_t s[4][32];
-      float mx;
-      if constexpr (SM == 1) {
-        // pipelined: the second half of S is still in flight while the first half's maxima are taken; 3-input FMNMX3 halves
-        // the max pass (64 instead of 128 ALU instructions per row)
-        tmem_ld32(tS + 0, s[0]);
-        tmem_ld32(tS + 32, s[1]);
-        tmem_ld_wait();
-        reg_fence32(s[0]); reg_fence32(s[1]);
-        tmem_ld32(tS + 64, s[2]);
-        tmem_ld32(tS + 96, s[3]);
-        float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      tmem_ld32(tS + 0, s[0]);
+      tmem_ld32(tS + 32, s[1]);
+      tmem_ld32(tS + 64, s[2]);
+      tmem_ld32(tS + 96, s[3]);
+      tmem_ld_wait();
+      if (tr) tr[2] = clock64();
+      // 8 independent running maxima (a single fmaxf chain is 128 dependent ops of 4-cycle latency each)
+      float mxa[8];
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+      for (int a = 0; a < 8; ++a) mxa[a] = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            mxa[(i >> 1) & 3] = fmax3(mxa[(i >> 1) & 3], __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
-        tmem_ld_wait();
-        reg_fence32(s[2]); reg_fence32(s[3]);
-        if (tr) tr[2] = clock64();
+      for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int c = 2; c < 4; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            mxa[(i >> 1) & 3] = fmax3(mxa[(i >> 1) & 3], __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
-        mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-      } else {
-        tmem_ld32(tS + 0, s[0]);
-        tmem_ld32(tS + 32, s[1]);
-        tmem_ld32(tS + 64, s[2]);
-        tmem_ld32(tS + 96, s[3]);
-        tmem_ld_wait();
-        if (tr) tr[2] = clock64();
-        // 8 independent running maxima (a single fmaxf chain is 128 dependent ops of 4-cycle latency each)
-        float mxa[8];
-#pragma unroll
-        for (int a = 0; a < 8; ++a) mxa[a] = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(s[c][i]));
-        mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
-      }
+        for (int i = 0; i < 32; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(s[c][i]));
+      const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
+                             fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
       const float ms = mx * sc;
       if (tr) {
         asm volatile("" ::"f"(ms));
@@ -443,14 +416,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             p2 = f2_pack(p0, p1);
           }
           ls2[i & 1] = f2_add(ls2[i & 1], p2);
-          pk[i] = pack_bf16x2(p0, p1);
+          pk[i] = (SM == 1) ? pack_bf16x2_alu(p0, p1) : pack_bf16x2(p0, p1);
         }
-        if (P_TMEM && SM == 1) {
-          // pipelined hand-off: the store of this half is issued and NOT waited for here — half 0's completion is collected
-          // after the first quarter of half 1's exponentials (see below), only the last store's latency is exposed
-          tmem_st32(tS + h * 32, pk);
-          if (h == 1) tmem_st_wait();
-        } else if (P_TMEM) {
+        if (P_TMEM) {
           tmem_st32(tS + h * 32, pk);
           tmem_st_wait();
         } else {
@@ -464,16 +432,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           fence_proxy_async_smem();
         }
         if (tr) tr[4 + h] = clock64();
-        if (P_TMEM && SM == 1) {
-          if (h == 1) {   // both stores have completed (single wait above): publish both halves
-            tc_fence_before();
-            mbar_arrive(&p_half[2 * X]);
-            mbar_arrive(&p_half[2 * X + 1]);
-          }
-        } else {
-          tc_fence_before();
-          mbar_arrive(&p_half[2 * X + h]);
-        }
+        tc_fence_before();
+        mbar_arrive(&p_half[2 * X + h]);
       }
       {
         float a0, a1, b0, b1;
@@ -526,7 +486,7 @@ constexpr int LA_BAR_OFF = LA_KV_OFF + LA_NS * LA_TILE_BYTES;
 constexpr int LA_SMEM_BYTES = LA_BAR_OFF + 512 + 1024;
 static_assert(LA_SMEM_BYTES <= 227 * 1024, "attention_la shared memory budget");
 
-template <int EMU>
+template <int EMU, bool ALU_PACK>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_la_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttParams p) {
@@ -771,7 +731,7 @@ attention_la_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           p2 = f2_pack(p0, p1);
         }
         ls2[i & 1] = f2_add(ls2[i & 1], p2);
-        pk[i] = pack_bf16x2(p0, p1);
+        pk[i] = ALU_PACK ? pack_bf16x2_alu(p0, p1) : pack_bf16x2(p0, p1);
       }
       tmem_st32(tS, pk);     // P(j): 64 keys = 32 packed columns over the first half of this S buffer
       tmem_st_wait();
@@ -893,10 +853,10 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, cons
   return check_launch("attention_combine");
 }
 
-template <int EMU>
+template <int EMU, bool ALU_PACK>
 static int launch_attention_la(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, AttParams p,
                                int heads, cudaStream_t stream, int force_ns, void* ws, long long ws_bytes) {
-  auto kern = attention_la_kernel<EMU>;
+  auto kern = attention_la_kernel<EMU, ALU_PACK>;
   static bool attr_set[kMaxDevices] = {false};
   if (int rc = ensure_dynamic_smem(kern, LA_SMEM_BYTES, attr_set, "attention_la")) return rc;
   CUtensorMap tmQ, tmK, tmV;
@@ -937,10 +897,11 @@ static int dispatch_attention(const void* q, long long ldq, const void* k, long 
   const int force_ns = (flags >> YB_ATT_SPLIT_SHIFT) & 7;
   if (force_ns > 4) return YB_ERR_ARG;
   const int emu = (flags >> YB_ATT_EMU_SHIFT) & 3, sm = (flags >> YB_ATT_SM_SHIFT) & 3;
-  if (sm == 2 && !(flags & YB_ATT_P_SMEM)) {            // lookahead schedule (64-key tiles: its own tensor maps)
+  if (sm >= 2 && !(flags & YB_ATT_P_SMEM)) {            // lookahead schedule (64-key tiles: its own tensor maps)
     if (p.trace != nullptr) return YB_ERR_ARG;
-    if (emu == 0) return launch_attention_la<0>(q, ldq, k, ldk, v, ldv, p, heads, stream, force_ns, ws, ws_bytes);
-    if (emu == 1) return launch_attention_la<4>(q, ldq, k, ldk, v, ldv, p, heads, stream, force_ns, ws, ws_bytes);
+    if (emu == 0 && sm == 2) return launch_attention_la<0, false>(q, ldq, k, ldk, v, ldv, p, heads, stream, force_ns, ws, ws_bytes);
+    if (emu == 0 && sm == 3) return launch_attention_la<0, true>(q, ldq, k, ldk, v, ldv, p, heads, stream, force_ns, ws, ws_bytes);
+    if (emu == 1 && sm == 3) return launch_attention_la<4, true>(q, ldq, k, ldk, v, ldv, p, heads, stream, force_ns, ws, ws_bytes);
     return YB_ERR_ARG;
   }
   CUtensorMap tmQ, tmK, tmV;

@@ -680,23 +680,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-// N tile of the SM-pair kernel for an [M, N] output on `clusters` SM pairs: minimise (waves x tile width); ties go to the
-// wider tile (fewer B re-reads, longer MMAs). Host arithmetic only — exported as yb_gemm_plan for the CPU test-suite.
+// N tile of the SM-pair kernel: 256 (N itself, rounded up to 32, for narrower outputs). The kernel takes any multiple of 32 and
+// a waves-x-width cost model was tried: on the 8-GPU o-projection (M = 2310, N = 3072) 224-wide tiles fill two waves exactly
+// where 256-wide ones need 1.62, but measured 0.045 ms vs 0.043 ms (ffn1: 0.196 vs 0.176): narrower MMAs and more B re-reads cost
+// more than the idle tail (profiles/r02_gemm_pair.md). Host arithmetic only — exported through yb_gemm_plan.
 static int pair_block_n(int M, int N, int clusters) {
-  const int m_tiles = (M + 255) / 256;
-  int best_bn = 256;
-  long long best_cost = -1;
-  for (int bn = 256; bn >= 128; bn -= 32) {
-    if (bn > 128 && N < bn) continue;
-    const long long tiles = static_cast<long long>(m_tiles) * ((N + bn - 1) / bn);
-    const long long waves = (tiles + clusters - 1) / clusters;
-    const long long cost = waves * (bn + 8);          // + a per-tile constant: pipeline fill / accumulator hand-off
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best_bn = bn;
-    }
-  }
-  return best_bn;
+  (void)M;
+  (void)clusters;
+  return N >= 256 ? 256 : ((N + 31) / 32) * 32;
 }
 
 template <int EPI>
@@ -927,8 +918,12 @@ extern "C" int yb_conv3d_causal(const yb_conv3d_args* a, void* stream_) {
   if ((kt != 1 && kt != 3) || (kh != 1 && kh != 3) || (kw != 1 && kw != 3)) return YB_ERR_SHAPE;
   const int block_n = (a->Cout % 256 == 0) ? 256 : 128;
   bool fuse_w = false;
-  if (a->cta_pair < 0 || a->cta_pair > 1) return YB_ERR_ARG;
-  conv_plan(a->T, a->H, a->W, block_n, kw, a->cta_pair == 1 ? 1 : a->fuse_w, &p.TW, &p.TH, &p.TT, &fuse_w);
+  if (a->cta_pair < 0 || a->cta_pair > 2) return YB_ERR_ARG;
+  // SM-pair kernel: 1 = forced, 2 = forced off, 0 = automatic — taken for output widths the 1-CTA kernel has to cut into a 128-wide
+  // tile plus a padded remainder (192, 384 channels of the Wan2.1 decoder: 1006 vs 678 and 832 vs 787 TFLOP/s measured); the other
+  // widths keep the 1-CTA kernel, whose kw-fused mode (3x less A traffic) wins there (profiles/r02_gemm_pair.md)
+  const bool conv_pair = a->cta_pair == 1 || (a->cta_pair == 0 && a->fuse_w != 2 && a->Cout > 128 && a->Cout % 256 != 0 && a->Cout <= 512);
+  conv_plan(a->T, a->H, a->W, block_n, kw, conv_pair ? 1 : a->fuse_w, &p.TW, &p.TH, &p.TT, &fuse_w);
   p.tiles_w = (a->W + p.TW - 1) / p.TW;
   p.tiles_h = (a->H + p.TH - 1) / p.TH;
   const int tiles_t = (a->T + p.TT - 1) / p.TT;
@@ -963,9 +958,9 @@ extern "C" int yb_conv3d_causal(const yb_conv3d_args* a, void* stream_) {
   if (rc) return rc;
   // SM-pair kernel (un-fused taps; each CTA of the pair owns one 128-voxel box, the weight tile is split between them):
   // selected by a->cta_pair (1 = always, 0 = never until the per-width crossover is measured)
-  if (a->cta_pair == 1 && !fuse_w) {
+  if (conv_pair && !fuse_w) {
     p.conv = 1;
-    p.block_n = a->Cout <= 256 ? a->Cout : pair_block_n(2 * p.num_m_tiles * 128, a->Cout, sm_count() / 2);
+    p.block_n = a->Cout <= 256 ? a->Cout : (a->Cout % 192 == 0 ? 192 : 256);
     CUtensorMap tmBp;
     rc = make_tmap_bf16_2d(&tmBp, a->w, a->Cout, static_cast<uint64_t>(taps) * a->Cp, static_cast<uint64_t>(taps) * a->Cp,
                            p.block_n / 2, GEMM_BLOCK_K);
