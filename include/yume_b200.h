@@ -271,6 +271,19 @@ int yb_nhwc_to_nchw_f32_clamp(const void* x, long long ldx, void* out, long long
  * b[o, y, i] = a[o, ea-ext+y, i] * (1 - y/ext) + b[o, y, i] * (y/ext) for y < ext; a is [outer, ea, inner], b [outer, eb, inner]. */
 int yb_blend(const void* a, void* b, long long outer, int ea, int eb, int ext, long long inner, void* stream);
 
+/* One-pass assembly of a tiled decode (temporal_tiled_decode / spatial_tiled_decode + blend_v / blend_h / blend_t,
+ * autoencoder_kl_causal_3d.py:343-359, 417-463, 500-531): the final f32 [C, F, H, W] video straight from the RAW decoded tiles — each
+ * output voxel is the reference's in-place cross-fade sequence written out as one expression of <= 2 x 4 raw tile values (same
+ * operations, same order), so tiles may be decoded in any order / on any GPU and no torch.cat or per-row blend launch remains.
+ *   tile_ptrs  DEVICE array [nt*ni*nj] of device pointers: tile (ti, i, j) = f32 [C, tlen[ti] + tskip(ti), th[i], tw[j]] contiguous,
+ *              tskip(ti) = 1 for ti > 0 (the first decoded frame of later temporal tiles is dropped, :519-520), else 0
+ *   th, tw, tlen, tf0   DEVICE int arrays: tile heights [ni] / widths [nj] in pixels, kept-length source frames [nt] (after the
+ *              drop), first output frame [nt]
+ *   row_limit / blend_extent (space), t_limit / t_blend_extent (time): the reference's crop and cross-fade lengths */
+int yb_vae_assemble_tiles(const void* const* tile_ptrs, const int* th, const int* tw, const int* tlen, const int* tf0, int nt,
+                          int ni, int nj, int C, int F, int H, int W, int row_limit, int blend_extent, int t_limit,
+                          int t_blend_extent, void* out, void* stream);
+
 /* Wan2.2 VAE decoder glue (wan23/modules/vae2_2.py), channels-last bf16:
  *   yb_vae_rms_act: out[T, Hs*up, Ws*up, Cp] = [SiLU]([RMS_norm over channels * gamma](x)) nearest-exact upsampled by
  *     `up` in {1,2} (RMS_norm :47-61 = F.normalize * sqrt(C) * gamma; Upsample :64-70). gamma NULL = no norm.

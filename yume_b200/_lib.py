@@ -69,6 +69,7 @@ SIGNATURES = {
     "yb_attention_plan": (_i, [_i, _i, _i, _i, _i, C.POINTER(C.c_int)]),
     "yb_nhwc_to_nchw_f32_clamp": (_i, [_vp, _ll, _vp, _ll, _i, C.c_float, C.c_float, _vp]),
     "yb_blend": (_i, [_vp, _vp, _ll, _i, _i, _i, _ll, _vp]),
+    "yb_vae_assemble_tiles": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "yb_vae_rms_act": (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "yb_vae_dupup_add": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "yb_vae_unpatchify2_clamp": (_i, [_vp, _ll, _vp, _i, _i, _i, _vp]),

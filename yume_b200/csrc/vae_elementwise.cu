@@ -215,6 +215,96 @@ __global__ void blend_kernel(const float* __restrict__ a, float* __restrict__ b,
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// One-pass assembly of a tiled decode (AutoencoderKLCausal3D.temporal_tiled_decode / spatial_tiled_decode,
+// hyvideo/vae/autoencoder_kl_causal_3d.py:417-463, 500-531). The reference decodes tile after tile, cross-fades each tile IN PLACE
+// with its upper / left / previous neighbour (blend_v, blend_h, blend_t, :343-359), crops and torch.cat's rows, then columns, then
+// time. Every output voxel is therefore a fixed expression of at most 2 (time) x 4 (space) RAW tile values; this kernel evaluates
+// that expression directly from the raw tiles into the final [C, F, H, W] video — same operations, same order, same fp32
+// roundings as the in-place sequence (a*(1-w) + b*w per blend) — so tiles can be decoded in any order, on any GPU.
+//   tiles   table of raw decoded tiles: tile (ti, i, j) is f32 [C, ft, h_i, w_j] contiguous at ptr[(ti*ni + i)*nj + j]
+//   space   tile (i, j) covers output rows [i*rl, i*rl + min(rl, h_i)), blended over its first ev rows with tile (i-1, j):
+//           ev = min(h_{i-1}, h_i, E) (blend_v clamps the extent to both tiles); columns likewise
+//   time    temporal tile ti (its first decoded frame already dropped for ti > 0) covers frames [f0(ti), f0(ti) + keep(ti)),
+//           blended over its first min(len_{ti-1}, len_ti, Et) frames with the last frames of tile ti-1
+// ---------------------------------------------------------------------------------------------------------
+struct TileAsm {
+  const float* const* ptr;   // [nt * ni * nj] device pointers
+  const int* th;             // [ni] tile heights (output pixels)
+  const int* tw;             // [nj] tile widths
+  const int* tlen;           // [nt] frames per temporal tile (after the drop)
+  const int* tf0;            // [nt] first output frame of temporal tile ti
+  int nt, ni, nj, C, F, H, W;
+  int rl, E;                 // spatial row_limit / blend extent (0 = untiled in space: ni == nj == 1)
+  int tl, Et;                // temporal keep limit / blend extent
+};
+
+__device__ __forceinline__ float tile_at(const TileAsm& a, int ti, int i, int j, int c, int f, int y, int x) {
+  const float* t = a.ptr[(ti * a.ni + i) * a.nj + j];
+  const int skip = ti > 0 ? 1 : 0;   // later temporal tiles: the first decoded frame is dropped (dec[:, :, 1:], :519-520)
+  return t[((static_cast<long long>(c) * (a.tlen[ti] + skip) + f + skip) * a.th[i] + y) * a.tw[j] + x];
+}
+// fully blended value of spatial tile (i, j) of temporal tile ti at (y, x): blend_v with the upper neighbour first, then blend_h
+// with the left neighbour (the reference's order, :440-448); neighbours enter with THEIR blends applied, which for the rows /
+// columns read here (their last `ext` ones) reduces to one more blend with raw tiles
+__device__ __forceinline__ float spatial_value(const TileAsm& a, int ti, int i, int j, int c, int f, int y, int x) {
+  const int ev = i > 0 ? min(min(a.th[i - 1], a.th[i]), a.E) : 0;
+  const int eh = j > 0 ? min(min(a.tw[j - 1], a.tw[j]), a.E) : 0;
+  const bool bv = y < ev, bh = x < eh;
+  const float wv = bv ? static_cast<float>(y) / static_cast<float>(ev) : 1.f;
+  const float wh = bh ? static_cast<float>(x) / static_cast<float>(eh) : 1.f;
+  float v = tile_at(a, ti, i, j, c, f, y, x);
+  if (bv) {   // upper tile's row (already blended horizontally with ITS left neighbour on these columns)
+    const int r = a.th[i - 1] - ev + y;
+    float u = tile_at(a, ti, i - 1, j, c, f, r, x);
+    if (bh) {
+      const int eh_u = min(min(a.tw[j - 1], a.tw[j]), a.E);   // same column pair
+      const float ul = tile_at(a, ti, i - 1, j - 1, c, f, r, a.tw[j - 1] - eh_u + x);
+      u = ul * (1.f - wh) + u * wh;
+    }
+    v = u * (1.f - wv) + v * wv;
+  }
+  if (bh) {   // left tile's column (already blended vertically with ITS upper neighbour on these rows)
+    const int cx = a.tw[j - 1] - eh + x;
+    float lft = tile_at(a, ti, i, j - 1, c, f, y, cx);
+    if (bv) {
+      const float lu = tile_at(a, ti, i - 1, j - 1, c, f, a.th[i - 1] - ev + y, cx);
+      lft = lu * (1.f - wv) + lft * wv;
+    }
+    v = lft * (1.f - wh) + v * wh;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(256) vae_assemble_tiles_kernel(const TileAsm a, float* __restrict__ out) {
+  const long long total = static_cast<long long>(a.C) * a.F * a.H * a.W;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int X = static_cast<int>(idx % a.W);
+    const int Y = static_cast<int>((idx / a.W) % a.H);
+    const int Fo = static_cast<int>((idx / (static_cast<long long>(a.W) * a.H)) % a.F);
+    const int c = static_cast<int>(idx / (static_cast<long long>(a.W) * a.H * a.F));
+    int i = 0, y = Y, j = 0, x = X;
+    if (a.rl > 0) {
+      i = min(Y / a.rl, a.ni - 1); y = Y - i * a.rl;
+      j = min(X / a.rl, a.nj - 1); x = X - j * a.rl;
+    }
+    int ti = a.nt - 1;
+    while (ti > 0 && Fo < a.tf0[ti]) --ti;
+    const int f = Fo - a.tf0[ti];
+    float v = spatial_value(a, ti, i, j, c, f, y, x);
+    if (ti > 0) {
+      const int et = min(min(a.tlen[ti - 1], a.tlen[ti]), a.Et);
+      if (f < et) {
+        const float w = static_cast<float>(f) / static_cast<float>(et);
+        const float pv = spatial_value(a, ti - 1, i, j, c, a.tlen[ti - 1] - et + f, y, x);
+        v = pv * (1.f - w) + v * w;
+      }
+    }
+    out[idx] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Wan2.2 VAE glue (wan23/modules/vae2_2.py).
 // rms_act: one warp per OUTPUT voxel: [RMS_norm over channels (F.normalize * sqrt(C) * gamma, :47-61)] -> [SiLU] ->
 // nearest-exact 2x spatial upsample (:64-70, Resample :95-101), written channels-last [T, H*f, W*f, Cp] (no padding:
@@ -461,6 +551,26 @@ extern "C" int yb_blend(const void* a, void* b, long long outer, int ea, int eb,
   return check_launch("blend");
 }
 
+
+extern "C" int yb_vae_assemble_tiles(const void* const* tile_ptrs, const int* th, const int* tw, const int* tlen, const int* tf0,
+                                     int nt, int ni, int nj, int C, int F, int H, int W, int row_limit, int blend_extent,
+                                     int t_limit, int t_blend_extent, void* out, void* stream_) {
+  if (!tile_ptrs || !th || !tw || !tlen || !tf0 || !out) return YB_ERR_ARG;
+  if (nt <= 0 || ni <= 0 || nj <= 0 || C <= 0 || F <= 0 || H <= 0 || W <= 0) return YB_ERR_ARG;
+  if ((ni > 1 || nj > 1) && (row_limit <= 0 || blend_extent <= 0)) return YB_ERR_ARG;
+  if (nt > 1 && (t_limit <= 0 || t_blend_extent <= 0)) return YB_ERR_ARG;
+  TileAsm a;
+  a.ptr = reinterpret_cast<const float* const*>(tile_ptrs);
+  a.th = th; a.tw = tw; a.tlen = tlen; a.tf0 = tf0;
+  a.nt = nt; a.ni = ni; a.nj = nj; a.C = C; a.F = F; a.H = H; a.W = W;
+  a.rl = (ni > 1 || nj > 1) ? row_limit : 0;
+  a.E = blend_extent;
+  a.tl = t_limit;
+  a.Et = t_blend_extent;
+  vae_assemble_tiles_kernel<<<grid_for(static_cast<long long>(C) * F * H * W), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      a, static_cast<float*>(out));
+  return check_launch("vae_assemble_tiles");
+}
 
 extern "C" int yb_vae_rms_act(const void* x, long long ldx, void* out, const void* gamma, int T, int Hs, int Ws, int C,
                               int Cp, int up, int silu, void* stream_) {

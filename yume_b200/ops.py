@@ -420,6 +420,30 @@ def nhwc_to_nchw_f32(x: torch.Tensor, out: torch.Tensor, clamp: Optional[tuple] 
     return out
 
 
+def vae_assemble_tiles(tiles, th, tw, tlen, tf0, out: torch.Tensor, row_limit: int, blend_extent: int, t_limit: int,
+                       t_blend_extent: int) -> torch.Tensor:
+    """tiles[ti][i][j]: raw decoded tiles f32 [C, frames, th[i], tw[j]] (contiguous); out f32 [C, F, H, W] (yb_vae_assemble_tiles)."""
+    global _launches
+    nt, ni, nj = len(tiles), len(tiles[0]), len(tiles[0][0])
+    dev = out.device
+    flat = [tiles[a][b][c] for a in range(nt) for b in range(ni) for c in range(nj)]
+    for t in flat:
+        _need(t, torch.float32, "tile")
+        if not t.is_contiguous():
+            raise YumeB200Error("vae_assemble_tiles needs contiguous tiles")
+    table = torch.tensor([t.data_ptr() for t in flat], dtype=torch.int64).to(dev)
+    meta = torch.tensor(list(th) + list(tw) + list(tlen) + list(tf0), dtype=torch.int32).to(dev)
+    o_th, o_tw, o_tl, o_tf = 0, ni, ni + nj, ni + nj + nt
+    _need(out, torch.float32, "out")
+    C_, F_, H_, W_ = out.shape
+    base = meta.data_ptr()
+    check(_lib.load().yb_vae_assemble_tiles(table.data_ptr(), base + 4 * o_th, base + 4 * o_tw, base + 4 * o_tl, base + 4 * o_tf,
+                                            nt, ni, nj, C_, F_, H_, W_, row_limit, blend_extent, t_limit, t_blend_extent,
+                                            out.data_ptr(), _stream()), "yb_vae_assemble_tiles")
+    _launches += 1
+    return out
+
+
 def blend(a: torch.Tensor, b: torch.Tensor, dim: int, extent: int) -> torch.Tensor:
     """In place on b (contiguous f32): cross-fade the first `extent` slices of b along `dim` with the last of a."""
     global _launches

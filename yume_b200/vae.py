@@ -197,64 +197,92 @@ class HyVaeDecoder:
         ops.nhwc_to_nchw_f32(y, out)
         return out.view(1, self.out_channels, *dims)
 
-    # ---- tiling (order of in-place blends exactly as the reference) ---------------------------------------------
+    # ---- tiling -----------------------------------------------------------------------------------------------
     def enable_tiling(self, use_tiling: bool = True) -> None:
         self.use_spatial_tiling = self.use_temporal_tiling = use_tiling
 
-    def _spatial_tiled(self, z: Tensor) -> Tensor:
-        overlap = int(self.tile_latent_min_size * (1 - self.tile_overlap_factor))
-        blend_extent = int(self.tile_sample_min_size * self.tile_overlap_factor)
-        row_limit = self.tile_sample_min_size - blend_extent
-        ts = self.tile_latent_min_size
-        rows = [[self.decode_tile(z[0, :, :, i:i + ts, j:j + ts]) for j in range(0, z.shape[-1], overlap)]
-                for i in range(0, z.shape[-2], overlap)]
-        result_rows = []
-        for i, row in enumerate(rows):
-            result_row = []
-            for j, tile in enumerate(row):
-                if i > 0:
-                    ops.blend(rows[i - 1][j], tile, 3, blend_extent)
-                if j > 0:
-                    ops.blend(row[j - 1], tile, 4, blend_extent)
-                result_row.append(tile[:, :, :, :row_limit, :row_limit])
-            result_rows.append(torch.cat(result_row, dim=-1))
-        return torch.cat(result_rows, dim=-2)
+    def enable_tile_parallel(self, group) -> None:
+        """Spread the tiles of a tiled decode over the ranks of `group` (one process per GPU): tiles are independent, so rank r
+        decodes tiles r, r + P, ...; every rank then receives the others' raw tiles (one broadcast per tile) and assembles the
+        full video. SURVEY.md §8(e): 'VAE decode: tiles are independent -> tile-parallel replicas'
+        (fastvideo/models/hunyuan/vae/autoencoder_kl_causal_3d.py:620-741 does the same with an all-gather)."""
+        self.tile_group = group
 
-    def _temporal_tiled(self, z: Tensor) -> Tensor:
-        overlap = int(self.tile_latent_min_tsize * (1 - self.tile_overlap_factor))
-        blend_extent = int(self.tile_sample_min_tsize * self.tile_overlap_factor)
-        t_limit = self.tile_sample_min_tsize - blend_extent
-        row = []
-        for i in range(0, z.shape[2], overlap):
-            tile = z[:, :, i:i + self.tile_latent_min_tsize + 1]
-            if self.use_spatial_tiling and (tile.shape[-1] > self.tile_latent_min_size or tile.shape[-2] > self.tile_latent_min_size):
-                dec = self._spatial_tiled(tile)
-            else:
-                dec = self.decode_tile(tile[0])
-            if i > 0:
-                dec = dec[:, :, 1:]
-            row.append(dec.contiguous())
-        out = []
-        for i, tile in enumerate(row):
-            if i > 0:
-                ops.blend(row[i - 1], tile, 2, blend_extent)
-                out.append(tile[:, :, :t_limit])
-            else:
-                out.append(tile[:, :, :t_limit + 1])
-        return torch.cat(out, dim=2)
+    def tile_plan(self, T: int, H: int, W: int):
+        """Windows of the reference's tiled decode for a latent [T, H, W] (autoencoder_kl_causal_3d.py:417-463, 500-531):
+        (temporal windows [(t0, len)], row starts/sizes, column starts/sizes, spatially tiled?). Pure host arithmetic."""
+        tmin, smin = self.tile_latent_min_tsize, self.tile_latent_min_size
+        if self.use_temporal_tiling and T > tmin:
+            ov = int(tmin * (1 - self.tile_overlap_factor))
+            twin = [(i, min(tmin + 1, T - i)) for i in range(0, T, ov)]
+            # a window that decodes to nothing after its first frame is dropped contributes no output (torch.cat of an empty tile)
+            twin = [w for k, w in enumerate(twin) if k == 0 or 4 * (w[1] - 1) + 1 - 1 > 0]
+        else:
+            twin = [(0, T)]
+        spatial = self.use_spatial_tiling and (W > smin or H > smin)
+        if spatial:
+            ov = int(smin * (1 - self.tile_overlap_factor))
+            rows = [(i, min(smin, H - i)) for i in range(0, H, ov)]
+            cols = [(j, min(smin, W - j)) for j in range(0, W, ov)]
+        else:
+            rows, cols = [(0, H)], [(0, W)]
+        return twin, rows, cols, spatial
 
     @torch.no_grad()
     def decode(self, z: Tensor) -> Tensor:
-        """z [1, 16, T, H, W] -> f32 [1, 3, 4(T-1)+1, 8H, 8W]."""
+        """z [1, 16, T, H, W] -> f32 [1, 3, 4(T-1)+1, 8H, 8W]. Tiled decodes: every tile is decoded RAW (in any order, on any
+        rank), then one kernel (`yb_vae_assemble_tiles`) writes the final video, evaluating the reference's in-place
+        cross-fade / crop / concatenate sequence per output voxel — no torch.cat, no per-row blend launches."""
         assert len(z.shape) == 5, "The input tensor should have 5 dimensions."      # autoencoder_kl_causal_3d.py:298
         if z.shape[0] != 1:
             return torch.cat([self.decode(zi[None]) for zi in z])                   # use_slicing semantics (:335-337)
         z = z.to(device=self.device, dtype=_F32)
-        if self.use_temporal_tiling and z.shape[2] > self.tile_latent_min_tsize:
-            return self._temporal_tiled(z)
-        if self.use_spatial_tiling and (z.shape[-1] > self.tile_latent_min_size or z.shape[-2] > self.tile_latent_min_size):
-            return self._spatial_tiled(z)
-        return self.decode_tile(z[0])
+        _, _, T, H, W = z.shape
+        twin, rows, cols, spatial = self.tile_plan(T, H, W)
+        if len(twin) == 1 and not spatial:
+            return self.decode_tile(z[0])
+        group = getattr(self, "tile_group", None)
+        world, rank = 1, 0
+        if group is not None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+        C = self.out_channels
+        tiles, k = [], 0
+        for (t0, tl) in twin:
+            plane = []
+            for (i0, hs) in rows:
+                line = []
+                for (j0, ws) in cols:
+                    shape = (C, 4 * (tl - 1) + 1, 8 * hs, 8 * ws)
+                    if k % world == rank:
+                        tile = self.decode_tile(z[0, :, t0:t0 + tl, i0:i0 + hs, j0:j0 + ws]).reshape(shape)
+                    else:
+                        tile = torch.empty(shape, device=self.device, dtype=_F32)
+                    line.append(tile)
+                    k += 1
+                plane.append(line)
+            tiles.append(plane)
+        if world > 1:                                      # exchange the raw tiles: one broadcast per tile from its owner
+            k = 0
+            for plane in tiles:
+                for line in plane:
+                    for tile in line:
+                        dist.broadcast(tile, src=dist.get_global_rank(group, k % world), group=group)
+                        k += 1
+        # temporal layout: tile 0 keeps t_limit + 1 frames, later tiles drop their first frame and keep t_limit (:519-531)
+        t_blend = int(self.tile_sample_min_tsize * self.tile_overlap_factor)
+        t_limit = self.tile_sample_min_tsize - t_blend
+        tlen = [4 * (tl - 1) + 1 - (1 if n > 0 else 0) for n, (_, tl) in enumerate(twin)]
+        keep = [min(L, t_limit + (1 if n == 0 else 0)) for n, L in enumerate(tlen)] if len(twin) > 1 else [tlen[0]]
+        tf0 = [sum(keep[:n]) for n in range(len(twin))]
+        blend = int(self.tile_sample_min_size * self.tile_overlap_factor)
+        row_limit = self.tile_sample_min_size - blend
+        th, tw = [8 * hs for _, hs in rows], [8 * ws for _, ws in cols]
+        Ho = sum(min(row_limit, h) for h in th) if spatial else th[0]
+        Wo = sum(min(row_limit, w) for w in tw) if spatial else tw[0]
+        out = torch.empty(C, sum(keep), Ho, Wo, device=self.device, dtype=_F32)
+        ops.vae_assemble_tiles(tiles, th, tw, tlen, tf0, out, row_limit, blend, t_limit, t_blend)
+        return out[None]
 
 
 def decoder_param_shapes(block_out_channels=(128, 256, 512, 512), layers_per_block=2, latent_channels=16,
