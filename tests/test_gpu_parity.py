@@ -204,7 +204,7 @@ def test_attention_kv_split_matches_unsplit(dev, Lq, Lk, heads, split):
     k = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
     v = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
     one = ops.attention(q, k, v, torch.empty_like(q), heads, split=1)
-    two = ops.attention(q, k, v, torch.full_like(q, 9.0), heads, split=split, softmax=split % 4)   # schedules 2, 3 and 0 (split 4 -> 0)
+    two = ops.attention(q, k, v, torch.full_like(q, 9.0), heads, split=split, softmax=(split & 1) * 2)   # split 3 -> lookahead kernel, 2 / 4 -> round-1 kernel
     assert rel(two, one) < 3e-3                      # both bf16-rounded; segments change the fp32 summation order only
     qh, kh, vh = (x.float().view(-1, heads, 128).transpose(0, 1) for x in (q, k, v))
     ref = torch.softmax(qh @ kh.transpose(1, 2) / math.sqrt(128.0), dim=-1) @ vh
@@ -219,14 +219,14 @@ def test_attention_auto_tail_split_full_size_properties(dev):
     L, heads = 18480, 3
     q, k, v = (torch.randn(L, heads * 128, generator=g, device=dev).bfloat16() for _ in range(3))
     a = ops.attention(q, k, v, torch.empty_like(q), heads, split=1)
-    for sm in (0, 1, 2, 3):
+    for sm in (0, 2):
         b = ops.attention(q, k, v, torch.full_like(q, 7.0), heads, split=0, softmax=sm)
         assert bool(torch.isfinite(b.float()).all()) and rel(b, a) < 3e-3, sm
 
 
-# (variant, schedule): product kernels — round-1 schedule / lookahead schedule, each with F2FP or ALU-pipe packing of P
-# (include/yume_b200.h YB_ATT_SM_SHIFT) — and the debug variant that stages P through shared memory
-ATT_MODES = [(0, 0), (0, 1), (0, 2), (0, 3), (1, 0)]
+# (variant, schedule): product kernels — round-1 schedule / lookahead schedule (include/yume_b200.h YB_ATT_SM_SHIFT) — and the
+# debug variant that stages P through shared memory
+ATT_MODES = [(0, 0), (0, 2), (1, 0)]
 
 
 @pytest.mark.parametrize("variant,softmax", ATT_MODES)
@@ -243,7 +243,7 @@ def test_attention_matches_sdpa(dev, variant, softmax, Lq, Lk, heads):
     assert rel(out, _sdpa(q, k, v, heads)) < KERNEL_TOL
 
 
-@pytest.mark.parametrize("softmax", [0, 1, 2, 3])
+@pytest.mark.parametrize("softmax", [0, 2])
 def test_attention_large_logits_and_accumulate(dev, softmax):
     from yume_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(11)

@@ -295,23 +295,11 @@ __device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
   return f2_pack(p0, p1);
 }
 
-// bf16x2 pack on the ALU pipe (IADD + PRMT) instead of F2FP, which issues to the same XU pipe as MUFU.EX2.
-// Round-half-up on the magnitude (add 0x8000, truncate): differs from round-to-nearest-even only on exact ties.
-// Inputs must be finite and non-negative (softmax probabilities).
-__device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
-  return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
-}
 // 3-input max (sm_100: one FMNMX3 instead of two FMNMX)
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
-}
-// exp2 of two values in ONE MUFU operation on packed bf16: x = {hi, lo} bf16x2 -> {2^hi, 2^lo} bf16x2 (the format of P).
-__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
-  uint32_t y;
-  asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
 }
 // Zero-instruction data dependency: values produced by an asynchronous tcgen05.ld are only valid after tcgen05.wait::ld; routing
 // the registers through an empty volatile asm placed after the wait keeps the compiler from scheduling their uses above it.

@@ -201,8 +201,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
               split: int = 0, softmax: Optional[int] = None) -> torch.Tensor:
     """softmax(q k^T * scale) v, non-causal. q [Lq, heads*128], k/v [Lk, heads*128] bf16 (row strides arbitrary).
     split: KV split policy (YB_ATT_SPLIT_SHIFT): 0 automatic tail split, 1 never, 2..4 force that many KV segments.
-    softmax: kernel schedule (YB_ATT_SM_SHIFT): bit 0 = ALU-pipe bf16 pack, bit 1 = lookahead kernel (64-key tiles, S one tile
-    ahead of the softmax); None = product default (ATTENTION_SOFTMAX_MODE).
+    softmax: kernel schedule (YB_ATT_SM_SHIFT): 0 = round-1 kernel, 2 = lookahead kernel (64-key tiles, S one tile ahead of the
+    softmax); None = product default (ATTENTION_SOFTMAX_MODE).
     variant: 0 product kernel (P in TMEM), 1 debug (P through smem)."""
     global _launches, _flops
     for n, t in (("q", q), ("k", k), ("v", v), ("out", out)):
