@@ -172,9 +172,6 @@ int yb_attention_ex(const void* q, long long ldq, const void* k, long long ldk, 
 #define YB_ATT_SPLIT_SHIFT 4 /* flags bits 4-6: KV split policy. 0 = automatic (the units of a last wave that is at most
                                half full are cut into KV segments and merged by a combine kernel), 1 = never, 2..4 = cut
                                EVERY unit into that many segments (tests). Results are identical up to fp32 rounding. */
-#define YB_ATT_SM_SHIFT 8   /* flags bits 8-9: kernel schedule. 0 = round-1 kernel (128-key tiles, S(j+1) issued behind P.V(j)); 2 = LOOKAHEAD
-                               (64-key tiles, S double-buffered in TMEM and computed one tile ahead of the softmax:
-                               attention_la_kernel). attention.cu has the measurements. */
 /* Host-only: the work decomposition yb_attention would use on a GPU with `sms` SMs (no device access; the CPU test-suite
  * pins the scheduler with it). out4 = {CTAs running whole units, tail units that are split, KV segments per tail unit,
  * 128-key tiles per segment}. flags as for yb_attention (ACCUMULATE disables the split; bits 4-6 force it). */

@@ -204,7 +204,7 @@ def test_attention_kv_split_matches_unsplit(dev, Lq, Lk, heads, split):
     k = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
     v = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
     one = ops.attention(q, k, v, torch.empty_like(q), heads, split=1)
-    two = ops.attention(q, k, v, torch.full_like(q, 9.0), heads, split=split, softmax=(split & 1) * 2)   # split 3 -> lookahead kernel, 2 / 4 -> round-1 kernel
+    two = ops.attention(q, k, v, torch.full_like(q, 9.0), heads, split=split)
     assert rel(two, one) < 3e-3                      # both bf16-rounded; segments change the fp32 summation order only
     qh, kh, vh = (x.float().view(-1, heads, 128).transpose(0, 1) for x in (q, k, v))
     ref = torch.softmax(qh @ kh.transpose(1, 2) / math.sqrt(128.0), dim=-1) @ vh
@@ -219,32 +219,25 @@ def test_attention_auto_tail_split_full_size_properties(dev):
     L, heads = 18480, 3
     q, k, v = (torch.randn(L, heads * 128, generator=g, device=dev).bfloat16() for _ in range(3))
     a = ops.attention(q, k, v, torch.empty_like(q), heads, split=1)
-    for sm in (0, 2):
-        b = ops.attention(q, k, v, torch.full_like(q, 7.0), heads, split=0, softmax=sm)
-        assert bool(torch.isfinite(b.float()).all()) and rel(b, a) < 3e-3, sm
+    b = ops.attention(q, k, v, torch.full_like(q, 7.0), heads, split=0)
+    assert bool(torch.isfinite(b.float()).all()) and rel(b, a) < 3e-3
 
 
-# (variant, schedule): product kernels — round-1 schedule / lookahead schedule (include/yume_b200.h YB_ATT_SM_SHIFT) — and the
-# debug variant that stages P through shared memory
-ATT_MODES = [(0, 0), (0, 2), (1, 0)]
-
-
-@pytest.mark.parametrize("variant,softmax", ATT_MODES)
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("Lq,Lk,heads", [(128, 128, 1), (300, 200, 2), (1000, 512, 3), (777, 1500, 2), (257, 257, 2),
                                          (1, 1, 1), (130, 769, 2)])
-def test_attention_matches_sdpa(dev, variant, softmax, Lq, Lk, heads):
+def test_attention_matches_sdpa(dev, variant, Lq, Lk, heads):
     from yume_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(Lq * 7 + Lk)
     qkv = torch.randn(max(Lq, Lk), 3 * heads * 128, generator=g).to(dev).bfloat16()
     q, k, v = qkv[:Lq, :heads * 128], qkv[:Lk, heads * 128:2 * heads * 128], qkv[:Lk, 2 * heads * 128:]
     out = torch.zeros(Lq, heads * 128, device=dev, dtype=torch.bfloat16)
-    ops.attention(q, k, v, out, heads, variant=variant, softmax=softmax)
+    ops.attention(q, k, v, out, heads, variant=variant)
     assert torch.isfinite(out.float()).all()
     assert rel(out, _sdpa(q, k, v, heads)) < KERNEL_TOL
 
 
-@pytest.mark.parametrize("softmax", [0, 2])
-def test_attention_large_logits_and_accumulate(dev, softmax):
+def test_attention_large_logits_and_accumulate(dev):
     from yume_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(11)
     Lq, Lk, heads = 512, 1024, 2
@@ -252,12 +245,12 @@ def test_attention_large_logits_and_accumulate(dev, softmax):
     k = (torch.randn(Lk, heads * 128, generator=g) * 4).to(dev).bfloat16()
     v = torch.randn(Lk, heads * 128, generator=g).to(dev).bfloat16()
     out = torch.zeros(Lq, heads * 128, device=dev, dtype=torch.bfloat16)
-    ops.attention(q, k, v, out, heads, softmax=softmax)   # row maxima jump by >> 2^8: exercises the lazy O rescale
+    ops.attention(q, k, v, out, heads)            # row maxima jump by >> 2^8: exercises the lazy O rescale
     ref = _sdpa(q, k, v, heads)
     assert rel(out, ref) < KERNEL_TOL
     k2 = torch.randn(257, heads * 128, generator=g).to(dev).bfloat16()
     v2 = torch.randn(257, heads * 128, generator=g).to(dev).bfloat16()
-    ops.attention(q, k2, v2, out, heads, accumulate=True, softmax=softmax)
+    ops.attention(q, k2, v2, out, heads, accumulate=True)
     assert rel(out, ref + _sdpa(q, k2, v2, heads)) < 2 * KERNEL_TOL
 
 

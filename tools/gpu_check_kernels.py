@@ -262,9 +262,9 @@ def sec_attmodes():
         idx = torch.randint(0, L, (256,), device=dev)
         ref = sdpa_ref(q[idx].contiguous(), k, v, heads)
         fl = 4.0 * L * L * heads * 128
-        for sm, emu in ((0, 0), (2, 0), (2, 1)):
-            ms = min(timeit(lambda: ops.attention(q, k, v, out, heads, emu=emu, softmax=sm), n=5) for _ in range(3))
-            print(f"attmodes heads={heads} L={L} softmax={sm} emu={emu}: {ms:.3f} ms = {fl/ms/1e9:.0f} TF/s   rel/max {rel(out[idx], ref)}", flush=True)
+        for emu in (0, 1):
+            ms = min(timeit(lambda: ops.attention(q, k, v, out, heads, emu=emu), n=5) for _ in range(3))
+            print(f"attmodes heads={heads} L={L} emu={emu}: {ms:.3f} ms = {fl/ms/1e9:.0f} TF/s   rel/max {rel(out[idx], ref)}", flush=True)
     try:
         heads, L = 24, 18480
         qkv = torch.randn(L, 3 * heads * 128, device=dev).bfloat16()
@@ -321,10 +321,6 @@ def sec_convpair():
 
 
 def sec_atttrace():
-    _atttrace(0)
-
-
-def _atttrace(sm):
     from yume_b200 import _lib
     heads, L = 24, 18480
     qkv = torch.randn(L, 3 * heads * 128, device=dev).bfloat16()
@@ -334,7 +330,7 @@ def _atttrace(sm):
     lib = _lib.load()
     for _ in range(3):
         rc = lib.yb_attention_ex(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(),
-                                 out.stride(0), L, L, heads, 1.0 / math.sqrt(128.0), sm << 8, None, 0, tr.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                                 out.stride(0), L, L, heads, 1.0 / math.sqrt(128.0), 0, None, 0, tr.data_ptr(), torch.cuda.current_stream().cuda_stream)
         assert rc == 0
     torch.cuda.synchronize()
     t = tr.view(32, 32).cpu()

@@ -10,7 +10,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libyume_b200.so"
 YB_EPI_BF16, YB_EPI_GELU_BF16, YB_EPI_F32, YB_EPI_GATE_RES, YB_EPI_GELU_ERF_BF16, YB_EPI_RES_BF16 = 0, 1, 2, 3, 4, 5
 YB_ATT_P_SMEM, YB_ATT_ACCUMULATE = 1, 2
 ABI_VERSION = 2   # yb_abi_version() of the library this binding was written against
-YB_ATT_EMU_SHIFT, YB_ATT_SPLIT_SHIFT, YB_ATT_SM_SHIFT = 2, 4, 8
+YB_ATT_EMU_SHIFT, YB_ATT_SPLIT_SHIFT = 2, 4
 
 _ERRORS = {
     -1: "YB_ERR_ARG (null pointer / bad enum / non-positive size)",

@@ -125,12 +125,17 @@ struct AttCfg {
 // EMU: 0 = every exp2 on the MUFU; n > 0 = one of every n probability PAIRS is computed by exp2_poly2 on the FMA pipe
 // (the MUFU's 16 ex2/clk/SM is exactly co-saturated with the tensor pipe at head_dim 128, so part of the
 // exponentials has to move off it for the MMA to stay fed).
-// SM: reserved (0). Variants of THIS schedule measured and dropped in round 2 (profiles/r02_attention_schedules.md): exponentials
-// against a stale reference with a deferred max (3.30 vs 3.18 ms), packed `ex2.approx.ftz.bf16x2` exponentials (4.24 ms), a
-// pipelined softmax (FMNMX3 max under a split S load, one TMEM-store wait for both P halves: 3.29 vs 3.10 ms), bf16 packing on the
-// ALU pipe instead of F2FP (3.28 vs 3.17 ms). What does remove the serial softmax -> MMA -> softmax chain is the lookahead
-// schedule below (attention_la_kernel).
-template <bool P_TMEM, int EMU, int SM>
+// Round 2 measured seven variants of this kernel and kept none (profiles/r02_attention_schedules.md): Q resident in TMEM with 64-key
+// tiles (976 vs 1336 TFLOP/s), exponentials against a stale reference with a deferred max (3.30 vs 3.18 ms), packed
+// `ex2.approx.ftz.bf16x2` exponentials (4.24 ms), a pipelined softmax (FMNMX3 under a split S load, one TMEM-store wait: 3.29 vs
+// 3.10 ms), bf16 packing on the ALU pipe (3.28 vs 3.17 ms), FMA-pipe exponentials (3.46 ms at 1/4), and a LOOKAHEAD schedule (64-key
+// tiles, S double-buffered in TMEM and issued one tile ahead of the softmax so that neither side waits for the other's round
+// trip: correct, 4.50 ms). The last one is the informative failure: with both query tiles' softmax warps running concurrently the
+// kernel slowed down by exactly the amount two warps sharing one MUFU predict — the exponential phase costs ~11 cycles per
+// MUFU.EX2 warp instruction (700 cycles per 64, trace in profiles/r02_experimental_runbook.md), i.e. 2 x 128 x 11 = 2816 of the 3011
+// cycles of a KV iteration are MUFU time. The kernel is MUFU-bound, not latency-bound; the ping-pong of this schedule already
+// keeps the MUFU ~93 % busy, and only cheaper exponentials can move it.
+template <bool P_TMEM, int EMU>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttParams p) {
@@ -459,305 +464,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------------------
-// LOOKAHEAD schedule (YB_ATT_SM_SHIFT = 2). The cycle trace of the kernel above (profiles/r02_experimental_runbook.md) shows that
-// its two query tiles ping-pong, but each tile's own chain is strictly serial:
-//     S(j) ready -> softmax(j) ~1700 cycles -> P.V(j) + S(j+1) on the tensor pipe ~1150 -> hand-off ~100 -> S(j+1) ready -> ...
-// because S(j+1) overwrites the TMEM columns that hold P(j) and therefore has to be issued behind P.V(j). Period 3011 cycles for
-// 2048 cycles of MMA work and 2048 of MUFU work. Here the key tile is 64 wide and every query tile owns TWO S buffers (2 x 64
-// TMEM columns, the same 128 as before): S(j+1) goes to the other buffer and is issued one tile AHEAD — behind P.V(j-1), before
-// the softmax of tile j has produced anything. The softmax warps never wait for the tensor pipe (their next S is already there),
-// the MMA thread never waits for a full softmax round trip: the kernel becomes bound by the pipes themselves (MUFU 2 x 1024 and
-// tensor ~2 x 1160 cycles per 128 keys and CTA) instead of by their sum.
-//   TMEM   [X*128 + b*64, +64) S / P buffer b of query tile X;  [256 + X*128, +128) O_X
-//   smem   Q 2 x 32 KB | ring of 10 x 16 KB tiles (64 keys x 128 dims), loaded in consumption order K0 K1 V0 K2 V1 K3 ...
-//   MMA    prologue S_X(0), S_X(1); then per tile j and query tile X: P.V_X(j) [needs P_X(j)], S_X(j+2) -> buffer j&1 (just read)
-//   lazy O rescale: P.V(j-1) is no longer implied by "S(j) is there": the (rare) rescale waits on pv_done first
-// Same contract, decomposition (units, tail split, workspace) and epilogue as attention_kernel; results agree with it up to fp32
-// reassociation (64- instead of 128-key softmax steps).
-// ------------------------------------------------------------------------------------------------------------------------
-constexpr int LA_TILE_BYTES = 64 * 128 * 2;          // 64 keys x 128 dims bf16 = two swizzled slabs [64 x 64] of 8 KB
-constexpr int LA_NS = 10;
-constexpr int LA_Q_OFF = 0;
-constexpr int LA_KV_OFF = 2 * ATT_TILE_BYTES;
-constexpr int LA_BAR_OFF = LA_KV_OFF + LA_NS * LA_TILE_BYTES;
-constexpr int LA_SMEM_BYTES = LA_BAR_OFF + 512 + 1024;
-static_assert(LA_SMEM_BYTES <= 227 * 1024, "attention_la shared memory budget");
-
-template <int EMU>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-attention_la_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const AttParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + LA_BAR_OFF);
-  uint64_t* kv_full = q_full + 1;
-  uint64_t* kv_empty = kv_full + LA_NS;
-  uint64_t* s_full = kv_empty + LA_NS;    // [X][b]
-  uint64_t* p_ready = s_full + 4;         // [X][b]: one barrier per S/P buffer — the softmax may publish P(j+1) before the MMA
-                                          // thread has consumed P(j); a single barrier would complete two phases unobserved
-  uint64_t* pv_done = p_ready + 4;        // [X]
-  uint64_t* o_done = pv_done + 2;         // [X]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  // unit / first 64-key tile / number of 64-key tiles of this CTA (tail-split segments are planned in 128-key tiles)
-  auto decode = [&](int& unit, int& kv_begin, int& n) {
-    int bx = blockIdx.x;
-    asm volatile("" : "+r"(bx));
-    unit = bx;
-    int b128 = 0, n128 = p.nkv;
-    if (bx >= p.full_units) {
-      const int r = bx - p.full_units;
-      unit = p.full_units + r / p.ns;
-      const int per = (((p.nkv + p.ns - 1) / p.ns) + 1) & ~1;
-      b128 = (r % p.ns) * per;
-      n128 = min(per, p.nkv - b128);
-    }
-    kv_begin = 2 * b128;
-    n = min(2 * n128, (p.Lk + 63) / 64 - kv_begin);
-  };
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < LA_NS; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-    }
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 128);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&pv_done[i], 1);
-      mbar_init(&o_done[i], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_ptr, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp < 4) {
-    setmaxnreg_dec<80>();
-    if (warp == 0 && lane == 0) {
-      // ------------------------------- TMA producer: Q, then K0 K1 V0 K2 V1 K3 ... -------------------------------
-      int unit, kv_begin, n;
-      decode(unit, kv_begin, n);
-      const int head = unit / p.nq;
-      const int q0 = (unit - head * p.nq) * 256;
-      mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
-      for (int x = 0; x < 2; ++x)
-        for (int sl = 0; sl < 2; ++sl)
-          tma_load_2d(smem + LA_Q_OFF + x * ATT_TILE_BYTES + sl * 16384, &tmQ, q_full, head * 128 + sl * 64, q0 + x * 128);
-      int it = 0;
-      auto load = [&](const CUtensorMap* tm, int tile) {
-        const int slot = it % LA_NS;
-        mbar_wait(&kv_empty[slot], ((it / LA_NS) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[slot], LA_TILE_BYTES);
-        uint8_t* dst = smem + LA_KV_OFF + slot * LA_TILE_BYTES;
-        tma_load_2d(dst, tm, &kv_full[slot], head * 128, (kv_begin + tile) * 64);
-        tma_load_2d(dst + 8192, tm, &kv_full[slot], head * 128 + 64, (kv_begin + tile) * 64);
-        ++it;
-      };
-      load(&tmK, 0);
-      if (n > 1) load(&tmK, 1);
-      for (int j = 0; j < n; ++j) {
-        load(&tmV, j);
-        if (j + 2 < n) load(&tmK, j + 2);
-      }
-    } else if (warp == 1 && lane == 0) {
-      // ------------------------------- MMA issuer -------------------------------
-      int unit, kv_begin, n;
-      decode(unit, kv_begin, n);
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);     // S[128 q, 64 keys] = Q (K-major smem) x K^T (K-major smem)
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);   // O[128 q, 128 d] += P (TMEM) x V (MN-major smem)
-      const uint32_t sQ = smem_u32(smem + LA_Q_OFF);
-      const uint32_t sKV = smem_u32(smem + LA_KV_OFF);
-      const uint64_t kdesc0 = make_smem_desc_sw128(0, 16, 1024);       // K-major tiles: Q (two 16 KB slabs), K (two 8 KB slabs)
-      const uint64_t vdesc0 = make_smem_desc_sw128(0, 8192, 1024);     // MN-major V tile: the two 64-dim slabs are 8 KB apart
-      const uint64_t qdesc0 = kdesc0 + (sQ >> 4);
-      constexpr uint64_t kTileStep = ATT_TILE_BYTES >> 4;
-      auto issue_S = [&](int X, int b, uint32_t kbase) {
-        const uint64_t kd = kdesc0 + (kbase >> 4);
-        uint64_t qd = qdesc0 + X * kTileStep;
-        asm volatile("" : "+l"(qd));
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {   // 16 head-dim elements per MMA
-          const uint32_t qoff = ((kk >> 2) * 16384 + (kk & 3) * 32) >> 4;
-          const uint32_t koff = ((kk >> 2) * 8192 + (kk & 3) * 32) >> 4;
-          umma_ss(tmem_base + X * 128 + b * 64, qd + qoff, kd + koff, idesc_s, kk != 0 ? 1u : 0u);
-        }
-      };
-      auto issue_PV = [&](int X, int b, uint32_t vbase, bool acc) {
-        const uint64_t vd = vdesc0 + (vbase >> 4);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)     // 16 keys per MMA: 8 TMEM columns of packed P, 16 rows (2048 B) of the V tile
-          umma_ts(tmem_base + 256 + X * 128, tmem_base + X * 128 + b * 64 + kk * 8, vd + ((kk * 2048) >> 4), idesc_pv,
-                  (acc || kk != 0) ? 1u : 0u);
-      };
-      int it = 0;
-      auto take = [&]() -> uint32_t {       // next ring slot in consumption order: wait until it is full, return its address
-        const int slot = it % LA_NS;
-        mbar_wait(&kv_full[slot], (it / LA_NS) & 1);
-        ++it;
-        return sKV + slot * LA_TILE_BYTES;
-      };
-      auto release = [&](uint32_t base) { umma_commit(&kv_empty[(base - sKV) / LA_TILE_BYTES]); };
-      mbar_wait(q_full, 0);
-      for (int t = 0; t < 2 && t < n; ++t) {   // prologue: S(0) and S(1) of both query tiles
-        const uint32_t kbase = take();
-        tc_fence_after();
-        issue_S(0, t, kbase);
-        umma_commit(&s_full[t]);
-        issue_S(1, t, kbase);
-        umma_commit(&s_full[2 + t]);
-        release(kbase);
-      }
-      for (int j = 0; j < n; ++j) {
-        const int b = j & 1;
-        const bool has_k = (j + 2 < n);
-        const uint32_t vbase = take();
-        const uint32_t kbase = has_k ? take() : 0u;
-        tc_fence_after();
-#pragma unroll
-        for (int X = 0; X < 2; ++X) {
-          mbar_wait(&p_ready[2 * X + b], (j >> 1) & 1);
-          tc_fence_after();
-          issue_PV(X, b, vbase, j > 0);
-          umma_commit(&pv_done[X]);
-          if (has_k) {
-            issue_S(X, b, kbase);            // tile j+2 into the buffer P.V(j) has just read (in-order tensor pipe)
-            umma_commit(&s_full[2 * X + b]);
-          } else if (j + 1 == n) {
-            umma_commit(&o_done[X]);
-          }
-        }
-        release(vbase);
-        if (has_k) release(kbase);
-      }
-    }
-  } else {
-    // ------------------------------- softmax / correction / epilogue -------------------------------
-    setmaxnreg_inc<208>();
-    const int X = (warp - 4) >> 2;
-    const int quad = warp & 3;
-    const int row_in_tile = quad * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tO = tmem_base + lane_off + 256 + X * 128;
-    const float sc = p.scale_log2;
-    float m_used = -INFINITY;
-    float l = 0.f;
-    int unit, kv_begin, n;
-    decode(unit, kv_begin, n);
-    for (int j = 0; j < n; ++j) {           // LOCAL tile index: all barrier parities follow it
-      const int b = j & 1;
-      const uint32_t tS = tmem_base + lane_off + X * 128 + b * 64;
-      mbar_wait(&s_full[2 * X + b], (j >> 1) & 1);
-      tc_fence_after();
-      const int kv_rem = p.Lk - (kv_begin + j) * 64;
-      if (kv_rem < 64) {   // last, partial key tile: out-of-range columns of S become -inf (cold path)
-#pragma unroll 1
-        for (int c = kv_rem >> 5; c < 2; ++c) {
-          uint32_t t[32];
-          tmem_ld32(tS + c * 32, t);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= kv_rem) t[i] = 0xff800000u;
-          tmem_st32(tS + c * 32, t);
-        }
-        tmem_st_wait();
-      }
-      uint32_t s[2][32];
-      tmem_ld32(tS + 0, s[0]);
-      tmem_ld32(tS + 32, s[1]);
-      tmem_ld_wait();
-      reg_fence32(s[0]); reg_fence32(s[1]);
-      float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; i += 2)
-          mxa[(i >> 1) & 3] = fmax3(mxa[(i >> 1) & 3], __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
-      const float ms = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * sc;
-      if (j == 0) {
-        m_used = ms;
-      } else if (__any_sync(0xffffffffu, ms > m_used + 8.0f)) {   // lazy rescale: a row max grew by more than 2^8
-        mbar_wait(&pv_done[X], (j - 1) & 1);                      // O_X must be at rest: P.V(j-1) retired
-        tc_fence_after();
-        const float m_new = fmaxf(m_used, ms);
-        const float alpha = fast_exp2(m_used - m_new);
-        l *= alpha;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tO + c * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st32(tO + c * 32, o);
-        }
-        tmem_st_wait();
-        m_used = m_new;
-      }
-      const uint64_t sc2 = f2_pack(sc, sc);
-      const uint64_t negm2 = f2_pack(-m_used, -m_used);
-      uint64_t ls2[2] = {0ull, 0ull};
-      uint32_t pk[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int c0 = 2 * i;
-        const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[c0 >> 5][c0 & 31]), __uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31])),
-                                   sc2, negm2);
-        uint64_t p2;
-        float p0, p1;
-        if ((EMU > 0) && (i % (EMU > 0 ? EMU : 1) == EMU - 1)) {
-          p2 = exp2_poly2(x2);
-          f2_unpack(p2, p0, p1);
-        } else {
-          float x0, x1;
-          f2_unpack(x2, x0, x1);
-          p0 = fast_exp2(x0);
-          p1 = fast_exp2(x1);
-          p2 = f2_pack(p0, p1);
-        }
-        ls2[i & 1] = f2_add(ls2[i & 1], p2);
-        pk[i] = pack_bf16x2(p0, p1);
-      }
-      tmem_st32(tS, pk);     // P(j): 64 keys = 32 packed columns over the first half of this S buffer
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_ready[2 * X + b]);
-      {
-        float a0, a1, b0, b1;
-        f2_unpack(ls2[0], a0, a1);
-        f2_unpack(ls2[1], b0, b1);
-        l += (a0 + a1) + (b0 + b1);
-      }
-    }
-    mbar_wait(&o_done[X], 0);
-    tc_fence_after();
-    attention_epilogue(p, tO, m_used, l, X, row_in_tile, unit);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 // Merge the ns KV-segment partials of every tail unit and do the normal epilogue. One warp per query row, 4 columns per
 // lane: out = sum_s O_s 2^(m_s - M) / sum_s l_s 2^(m_s - M).
 __global__ void __launch_bounds__(256) attention_combine_kernel(const AttParams p, int tail_units) {
@@ -822,11 +528,11 @@ static size_t split_workspace_bytes(size_t ctas) { return ctas * 256 * 130 * siz
 static int g_debug_force_split = 0;   // yb_debug_force_split: tests force the KV split through paths that carry no flags
 
 // force_ns: 0 = automatic tail split, 1 = never, 2..4 = split EVERY unit into that many KV segments (tests)
-template <bool P_TMEM, int EMU, int SM>
+template <bool P_TMEM, int EMU>
 static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                             AttParams p, int heads, cudaStream_t stream, int force_ns, void* ws, long long ws_bytes) {
   using Cfg = AttCfg<P_TMEM>;
-  auto kern = attention_kernel<P_TMEM, EMU, SM>;
+  auto kern = attention_kernel<P_TMEM, EMU>;
   static bool attr_set[kMaxDevices] = {false};
   if (int rc = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_set, "attention")) return rc;
   if (force_ns == 0 && g_debug_force_split >= 1 && g_debug_force_split <= 4) force_ns = g_debug_force_split;
@@ -854,57 +560,12 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, cons
   return check_launch("attention_combine");
 }
 
-template <int EMU>
-static int launch_attention_la(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, AttParams p,
-                               int heads, cudaStream_t stream, int force_ns, void* ws, long long ws_bytes) {
-  auto kern = attention_la_kernel<EMU>;
-  static bool attr_set[kMaxDevices] = {false};
-  if (int rc = ensure_dynamic_smem(kern, LA_SMEM_BYTES, attr_set, "attention_la")) return rc;
-  CUtensorMap tmQ, tmK, tmV;
-  const uint64_t cols = static_cast<uint64_t>(heads) * 128;
-  int rc = make_tmap_bf16_2d(&tmQ, q, p.Lq, cols, ldq, 128, 64);
-  if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmK, k, p.Lk, cols, ldk, 64, 64);
-  if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmV, v, p.Lk, cols, ldv, 64, 64);
-  if (rc) return rc;
-  if (force_ns == 0 && g_debug_force_split >= 1 && g_debug_force_split <= 4) force_ns = g_debug_force_split;
-  p.nq = (p.Lq + 255) / 256;
-  const int units = p.nq * heads;
-  int tail = 0;
-  p.ws_o = p.ws_ml = nullptr;
-  attention_plan(units, p.nkv, sm_count(), !p.accumulate && ws != nullptr, force_ns, &p.full_units, &tail, &p.ns);
-  if (tail > 0) {
-    const size_t ctas = static_cast<size_t>(tail) * p.ns;
-    if (ws_bytes < 0 || static_cast<size_t>(ws_bytes) < split_workspace_bytes(ctas) || (reinterpret_cast<uintptr_t>(ws) & 0xF)) {
-      p.full_units = units;
-      tail = 0;
-      p.ns = 1;
-    } else {
-      p.ws_o = static_cast<float*>(ws);
-      p.ws_ml = p.ws_o + ctas * 256 * 128;
-    }
-  }
-  kern<<<p.full_units + tail * p.ns, ATT_THREADS, LA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
-  rc = check_launch("attention_la");
-  if (rc || tail == 0) return rc;
-  attention_combine_kernel<<<tail * 32, 256, 0, stream>>>(p, tail);
-  return check_launch("attention_combine");
-}
-
-// softmax schedule / exponent mode selected by flags bits 8-9 (YB_ATT_SM_SHIFT) and 2-3 (EMU)
+// exponent mode selected by flags bits 2-3 (EMU), debug variant by bit 0
 static int dispatch_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                               AttParams p, int heads, cudaStream_t stream, int flags, void* ws, long long ws_bytes) {
   const int force_ns = (flags >> YB_ATT_SPLIT_SHIFT) & 7;
   if (force_ns > 4) return YB_ERR_ARG;
-  const int emu = (flags >> YB_ATT_EMU_SHIFT) & 3, sm = (flags >> YB_ATT_SM_SHIFT) & 3;
-  if (sm == 2 && !(flags & YB_ATT_P_SMEM)) {            // lookahead schedule (64-key tiles: its own tensor maps)
-    if (p.trace != nullptr) return YB_ERR_ARG;
-    if (emu == 0) return launch_attention_la<0>(q, ldq, k, ldk, v, ldv, p, heads, stream, force_ns, ws, ws_bytes);
-    if (emu == 1) return launch_attention_la<4>(q, ldq, k, ldk, v, ldv, p, heads, stream, force_ns, ws, ws_bytes);
-    return YB_ERR_ARG;
-  }
-  if (sm != 0) return YB_ERR_ARG;
+  const int emu = (flags >> YB_ATT_EMU_SHIFT) & 3;
   CUtensorMap tmQ, tmK, tmV;
   const uint64_t cols = static_cast<uint64_t>(heads) * 128;
   int rc = make_tmap_bf16_2d(&tmQ, q, p.Lq, cols, ldq, 128, 64);
@@ -913,12 +574,13 @@ static int dispatch_attention(const void* q, long long ldq, const void* k, long 
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmV, v, p.Lk, cols, ldv, 128, 64);
   if (rc) return rc;
-  if (flags & YB_ATT_P_SMEM) return launch_attention<false, 0, 0>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-#define YB_ATT_CASE(E, EMUV, S)                                                                                     \
-  if (emu == (E) && sm == (S)) return launch_attention<true, EMUV, S>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-  YB_ATT_CASE(0, 0, 0) YB_ATT_CASE(1, 4, 0) YB_ATT_CASE(2, 3, 0) YB_ATT_CASE(3, 2, 0)
-#undef YB_ATT_CASE
-  return YB_ERR_ARG;
+  if (flags & YB_ATT_P_SMEM) return launch_attention<false, 0>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+  switch (emu) {
+    case 1: return launch_attention<true, 4>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+    case 2: return launch_attention<true, 3>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+    case 3: return launch_attention<true, 2>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+    default: return launch_attention<true, 0>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+  }
 }
 
 }  // namespace yb

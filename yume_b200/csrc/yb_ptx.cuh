@@ -295,18 +295,6 @@ __device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
   return f2_pack(p0, p1);
 }
 
-// 3-input max (sm_100: one FMNMX3 instead of two FMNMX)
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-// Zero-instruction data dependency: values produced by an asynchronous tcgen05.ld are only valid after tcgen05.wait::ld; routing
-// the registers through an empty volatile asm placed after the wait keeps the compiler from scheduling their uses above it.
-__device__ __forceinline__ void reg_fence32(uint32_t (&r)[32]) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(r[i]));
-}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

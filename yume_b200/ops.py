@@ -174,8 +174,6 @@ def qk_norm_rope(q: torch.Tensor, k: torch.Tensor, wq: torch.Tensor, wk: torch.T
     _launches += 1
 
 
-# softmax schedule of the attention kernel used by the product path (include/yume_b200.h YB_ATT_SM_SHIFT; attention.cu)
-ATTENTION_SOFTMAX_MODE = 0
 _sm_counts = {}
 
 
@@ -198,11 +196,9 @@ def _attention_ws(Lq: int, Lk: int, heads: int, flags: int, device: torch.device
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, heads: int,
               scale: Optional[float] = None, variant: int = 0, accumulate: bool = False, emu: int = 0,
-              split: int = 0, softmax: Optional[int] = None) -> torch.Tensor:
+              split: int = 0) -> torch.Tensor:
     """softmax(q k^T * scale) v, non-causal. q [Lq, heads*128], k/v [Lk, heads*128] bf16 (row strides arbitrary).
     split: KV split policy (YB_ATT_SPLIT_SHIFT): 0 automatic tail split, 1 never, 2..4 force that many KV segments.
-    softmax: kernel schedule (YB_ATT_SM_SHIFT): 0 = round-1 kernel, 2 = lookahead kernel (64-key tiles, S one tile ahead of the
-    softmax); None = product default (ATTENTION_SOFTMAX_MODE).
     variant: 0 product kernel (P in TMEM), 1 debug (P through smem)."""
     global _launches, _flops
     for n, t in (("q", q), ("k", k), ("v", v), ("out", out)):
@@ -212,9 +208,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
         raise YumeB200Error("attention supports head_dim 128 only")
     if scale is None:
         scale = 1.0 / math.sqrt(128.0)
-    sm = ATTENTION_SOFTMAX_MODE if softmax is None else softmax
-    flags = ((YB_ATT_P_SMEM if variant == 1 else 0) | (YB_ATT_ACCUMULATE if accumulate else 0) | ((emu & 3) << 2)
-             | ((split & 7) << 4) | ((sm & 3) << 8 if variant == 0 else 0))
+    flags = (YB_ATT_P_SMEM if variant == 1 else 0) | (YB_ATT_ACCUMULATE if accumulate else 0) | ((emu & 3) << 2) | ((split & 7) << 4)
     if variant not in (0, 1):
         raise YumeB200Error("attention variant must be 0 or 1")
     ws, ws_bytes = _attention_ws(Lq, Lk, heads, flags, q.device)
@@ -522,14 +516,13 @@ def sp_post_norm_rope(buf: torch.Tensor, sums: torch.Tensor, wq: torch.Tensor, w
 
 
 def attention_sp(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out_peer_ptrs, ldo: int, heads: int, rank: int,
-                 Lp: int, scale: Optional[float] = None, softmax: Optional[int] = None) -> None:
+                 Lp: int, scale: Optional[float] = None) -> None:
     global _launches, _flops
     for n, t in (("q", q), ("k", k), ("v", v)):
         _need(t, torch.bfloat16, n)
     if scale is None:
         scale = 1.0 / math.sqrt(128.0)
-    sm = ATTENTION_SOFTMAX_MODE if softmax is None else softmax
-    flags = (sm & 3) << 8
+    flags = 0
     ws, ws_bytes = _attention_ws(q.shape[0], k.shape[0], heads, flags, q.device)
     check(_lib.load().yb_attention_sp(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
                                       _ptr_array(out_peer_ptrs), ldo, q.shape[0], k.shape[0], heads, scale,
