@@ -315,7 +315,7 @@ template <int NCH>
 __global__ void __launch_bounds__(256, (NCH <= 12) ? 2 : 1)
 qk_norm_rope_warp_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, long long ld,
                          const float* __restrict__ wq, const float* __restrict__ wk,
-                         const float2* __restrict__ rope, int rope_len, int L, int D, float eps) {
+                         const float2* __restrict__ rope, int rope_len, int L, int D, float eps, int nparts) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= L) return;
@@ -325,7 +325,7 @@ qk_norm_rope_warp_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restric
   const bool rot = (rope != nullptr) && (row < rope_len);
   const float* rope_row = reinterpret_cast<const float*>(rope) + static_cast<long long>(row) * D;   // D/2 pairs x 2 floats
 #pragma unroll 1
-  for (int part = 0; part < 2; ++part) {
+  for (int part = 0; part < nparts; ++part) {   // nparts = 1: a single row set (cross-attention q, context k)
     __nv_bfloat16* base = part == 0 ? q : k;
     const float* weight = part == 0 ? wq : wk;
     uint4 raw[NCH];
@@ -719,6 +719,20 @@ extern "C" int yb_rmsnorm_rope_pieces(void* qk, long long ld, int piece_cols, lo
   if (C % 8 != 0 || C > RR_THREADS * RR_MAX_CHUNK * 8 || D % 8 != 0 || C % D != 0) return YB_ERR_SHAPE;
   if (piece_cols % 8 != 0 || C % piece_cols != 0) return YB_ERR_SHAPE;
   if ((ld % 8) || (piece_stride % 8) || (reinterpret_cast<uintptr_t>(qk) & 0xF)) return YB_ERR_ALIGNMENT;
+  // plain rows whose head_dim divides 256: the faster pass of yb_qk_norm_rope with one row set (ordered weight loads, the
+  // (cos, sin) quad of a lane loaded once per row) — the cross-attention q rows and the context k rows
+#define YB_RR_FAST(NCH)                                                                                              \
+  if (C == (NCH) * 256 && piece_cols == C && 256 % D == 0) {                                                         \
+    qk_norm_rope_warp_kernel<NCH><<<(L + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(                  \
+        static_cast<__nv_bfloat16*>(qk), static_cast<__nv_bfloat16*>(qk), ld, static_cast<const float*>(weight),     \
+        static_cast<const float*>(weight), static_cast<const float2*>(rope), rope_len, L, D, eps, 1);                \
+    return check_launch("rmsnorm_rope");                                                                             \
+  }
+  YB_RR_FAST(12)
+  YB_RR_FAST(20)
+  YB_RR_FAST(4)
+  YB_RR_FAST(1)
+#undef YB_RR_FAST
 #define YB_RR_WARP(NCH)                                                                                              \
   if (C == (NCH) * 256) {                                                                                            \
     rmsnorm_rope_warp_kernel<NCH><<<(L + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(                  \
@@ -758,7 +772,7 @@ extern "C" int yb_qk_norm_rope(void* q, void* k, long long ld, int piece_cols, l
     qk_norm_rope_warp_kernel<NCH><<<(L + 7) / 8, 256, 0, s>>>(                                                         \
         static_cast<__nv_bfloat16*>(q), static_cast<__nv_bfloat16*>(k), ld,                                            \
         static_cast<const float*>(wq), static_cast<const float*>(wk), static_cast<const float2*>(rope), rope_len, L, D, \
-        eps);                                                                                                          \
+        eps, 2);                                                                                                       \
     return check_launch("qk_norm_rope");                                                                              \
   }
   YB_QK_WARP(12)
