@@ -64,11 +64,13 @@ def main():
             times[mode] = float(ms)
             ref = out if mode == "single" else ref
             if mode == "parallel":
-                d = float((out - ref).abs().max())
-                bad += 0 if d == 0.0 else 1
+                # not bit-identical run to run: GroupNorm statistics are fp64 atomics (summation order), a last-bit change of a
+                # scale can flip bf16 roundings downstream
+                d = float((out - ref).norm() / ref.norm())
+                bad += 0 if d < 2e-3 else 1
                 if rank == 0:
                     print(f"full 720p decode: single GPU {times['single']:.1f} ms, tile-parallel x{world} {times['parallel']:.1f} ms "
-                          f"({times['single'] / times['parallel']:.2f}x), max |diff| {d}", flush=True)
+                          f"({times['single'] / times['parallel']:.2f}x), rel-Frobenius(parallel, single) {d:.2e}", flush=True)
     t = torch.tensor([bad], device=dev)
     dist.all_reduce(t)
     dist.destroy_process_group()
