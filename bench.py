@@ -359,10 +359,11 @@ def supplementary(args, dev, eng5, world, rank, peaks):
         from yume_b200.vae22 import Wan22VaeDecoder
         from yume_b200.vae22 import decoder_param_shapes as v22_shapes
 
-        def vae_entry(name, eng, z, frames_of, config):
-            ms, clocks, launches, tflop, res = _timed_simple(lambda: eng.decode(z), 2, 1, li)
+        def vae_entry(name, eng, z, frames_of, config, encode=False):
+            ms, clocks, launches, tflop, res = _timed_simple((lambda: eng.encode(z)) if encode else (lambda: eng.decode(z)), 2, 1, li)
             frames = frames_of(res)
-            out[name] = {"ms_per_decode": ms, "value": frames / (ms * 1e-3), "unit": "decoded frames/s", "frames": frames,
+            out[name] = {"ms_per_decode": ms, "value": frames / (ms * 1e-3), "unit": ("encoded" if encode else "decoded") + " frames/s",
+                         "frames": frames,
                          "gpu_launches": launches, "finite": bool(torch.isfinite(res).all()), "clocks": clocks, "config": config,
                          "roofline": {"bound": "tensor", "achieved": tflop / (ms * 1e-3), "peak": peak, "unit": "TFLOP/s",
                                       "frac": tflop / (ms * 1e-3) / peak, "tflop_per_decode": tflop,
@@ -384,6 +385,18 @@ def supplementary(args, dev, eng5, world, rank, peaks):
         vae_entry("vae21", v21, torch.randn(16, 21, 68, 120, generator=g, device=dev), lambda r: r.shape[1],
                   "Wan2.1 VAE one-pass decode z[16,21,68,120] -> [3,81,544,960] (what sample.py decodes with)")
         del v21
+        torch.cuda.empty_cache()
+        # ---- VAE encodes: the history / first-frame conditioning encodes of the two samplers ----
+        from yume_b200.vae_enc import Wan21VaeEncoder, Wan22VaeEncoder, encoder_param_shapes_21, encoder_param_shapes_22
+        e22 = Wan22VaeEncoder(_rand_sd(encoder_param_shapes_22(), dev), device=dev)
+        vae_entry("vae22-encode", e22, torch.randn(3, 81, 704, 1280, generator=g, device=dev).clamp_(-1, 1), lambda r: 81,
+                  "Wan2.2 VAE one-pass encode video[3,81,704,1280] -> mu[48,21,44,80] (sample_5b.py:892-893 history encode)", encode=True)
+        del e22
+        e21 = Wan21VaeEncoder(_rand_sd(encoder_param_shapes_21(), dev), device=dev)
+        vae_entry("vae21-encode", e21, torch.randn(3, 81, 544, 960, generator=g, device=dev).clamp_(-1, 1), lambda r: 81,
+                  "Wan2.1 VAE one-pass encode video[3,81,544,960] -> mu[16,21,68,120] (wan/image2video.py:348-367 conditioning encode)",
+                  encode=True)
+        del e21
         torch.cuda.empty_cache()
     return out
 

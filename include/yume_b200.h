@@ -105,6 +105,14 @@ typedef struct yb_conv3d_args {
   int oob_zero_pad;
   int out_t_mul, out_t_add;
   int fuse_w;
+  /* Strided form, the `Resample` convs of Encoder3d (wan23/modules/vae2_2.py:101-110, 158-170; wan/modules/vae.py:84-90, 125-139);
+   * needs oob_zero_pad. T, H, W stay the INPUT extents; out has To*Ho*Wo rows.
+   *   stride_hw  2: Conv2d(3x3, stride 2) behind ZeroPad2d((0,1,0,1)) — no padding in front, one zero row/column behind:
+   *              Ho = (H + 1 - kh) / 2 + 1, Wo likewise; output (ho, wo) reads input rows 2ho .. 2ho+2
+   *   stride_t   2: time_conv CausalConv3d((3,1,1), stride (2,1,1), padding 0) over the frames it is given:
+   *              To = (T - kt) / 2 + 1; output t reads input frames 2t .. 2t+2
+   * 0 or 1 = unit stride. The tensor map samples every second voxel, so no padded or gathered copy of the input exists. */
+  int stride_t, stride_hw;
 } yb_conv3d_args;
 int yb_conv3d_causal(const yb_conv3d_args* args, void* stream);
 /* Host-only: the tile plan yb_conv3d_causal would use (no device access; pins the chooser in the CPU test-suite).
@@ -292,6 +300,14 @@ int yb_vae_rms_act(const void* x, long long ldx, void* out, const void* gamma, i
                    int silu, void* stream);
 int yb_vae_dupup_add(void* main_, const void* x, int Ts, int Hs, int Ws, int in_c, int out_c, int ft, int fs, void* stream);
 int yb_vae_unpatchify2_clamp(const void* y, long long ldy, void* out, int T, int H, int W, void* stream);
+/* Wan2.2 VAE ENCODER glue (`Wan2_2_VAE.encode`, vae2_2.py:796-829):
+ *   yb_vae_avgdown_add: main += AvgDown3D(x) over the whole frame sequence (:320-373, :449-459): (ft - T % ft) % ft zero frames
+ *     in front, (c, a, q, r) flattened and averaged in groups of in_c*ft*fs*fs / out_c. x bf16 [T, H, W, in_c],
+ *     main bf16 [ceil(T/ft), H/fs, W/fs, out_c], both dense; H, W divisible by fs.
+ *   yb_vae_patchify2_bf16: video f32 [3, T, H, W] -> out bf16 [T*(H/2)*(W/2), ldo], 12 channels (c r q) (:284-300), the other
+ *     ldo - 12 columns zeroed. */
+int yb_vae_avgdown_add(void* main_, const void* x, int T, int H, int W, int in_c, int out_c, int ft, int fs, void* stream);
+int yb_vae_patchify2_bf16(const void* video, void* out, long long ldo, int T, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Self-test of the tcgen05 building blocks on one 128x128x128 tile (used by tests/, not by the product path).

@@ -890,3 +890,127 @@ def test_wan21_vae_decode_real_width_vs_oracle(dev):
     got = Wan21VaeDecoder(sd, mean=mean, std=std, device=dev, **cfg).decode(z).cpu()
     assert got.shape == want.shape and rel(got, want) < VAE_TOL and psnr(got, want) > VAE_PSNR_DB
     assert float(got.min()) >= -1.0 and float(got.max()) <= 1.0
+
+
+# ---- Wan VAE ENCODE: strided Resample convs, AvgDown3D shortcut, whole-sequence encoders ------------
+@pytest.mark.parametrize("T,H,W,ci,co", [(1, 16, 32, 64, 32), (3, 9, 14, 64, 64), (2, 44, 80, 128, 96), (5, 8, 258, 192, 160),
+                                         (1, 130, 6, 64, 320)])
+def test_conv3d_stride2_spatial_matches_torch(dev, T, H, W, ci, co):
+    """`Resample(downsample2d)`: ZeroPad2d((0,1,0,1)) + Conv2d(3x3, stride 2) per frame (vae2_2.py:101-104), the stride taken by
+    the tensor map (TMA elementStrides), the pad row / column behind the data by out-of-bounds fill; odd H / W included."""
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(T * 1000 + H * 10 + W)
+    x = torch.randn(T, H, W, ci, generator=g).to(dev).bfloat16()
+    wt = (torch.randn(co, ci, 3, 3, generator=g) / math.sqrt(9 * ci)).to(dev).bfloat16()
+    b = torch.randn(co, generator=g).to(dev)
+    wk = wt.permute(0, 2, 3, 1).reshape(co, 9 * ci).contiguous()
+    To, Ho, Wo = ops.conv_out_dims(T, H, W, (1, 3, 3), 1, 2)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), wt.float(), b, stride=2)
+    assert (To, Ho, Wo) == (T, ref.shape[-2], ref.shape[-1])
+    out = torch.empty(To * Ho * Wo, co, device=dev, dtype=torch.bfloat16)
+    ops.conv3d_causal(x, wk, b, out, T, H, W, ops.YB_EPI_BF16, taps=(1, 3, 3), oob_zero_pad=True, stride_hw=2)
+    assert rel(out.view(T, Ho, Wo, co), ref.permute(0, 2, 3, 1)) < KERNEL_TOL
+
+
+@pytest.mark.parametrize("T,H,W,ci,co", [(3, 4, 8, 64, 64), (5, 6, 10, 128, 96), (9, 3, 40, 192, 160), (17, 2, 6, 64, 320)])
+def test_conv3d_stride2_temporal_matches_torch(dev, T, H, W, ci, co):
+    """`Resample(downsample3d).time_conv`: CausalConv3d((3,1,1), stride (2,1,1), padding 0) over the frames it is given
+    (vae2_2.py:105-110, 158-170), output written one frame behind a frame 0 the caller copied."""
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(T * 100 + W)
+    x = torch.randn(T, H, W, ci, generator=g).to(dev).bfloat16()
+    wt = (torch.randn(co, ci, 3, 1, 1, generator=g) / math.sqrt(3 * ci)).to(dev).bfloat16()
+    b = torch.randn(co, generator=g).to(dev)
+    wk = wt.permute(0, 2, 3, 4, 1).reshape(co, 3 * ci).contiguous()
+    ref = torch.nn.functional.conv3d(x.float().permute(3, 0, 1, 2)[None], wt.float(), b, stride=(2, 1, 1))[0].permute(1, 2, 3, 0)
+    To = (T - 3) // 2 + 1
+    assert ops.conv_out_dims(T, H, W, (3, 1, 1), 2, 1) == (To, H, W) and ref.shape[0] == To
+    out = torch.full(((1 + To) * H * W, co), 7.0, device=dev, dtype=torch.bfloat16)
+    ops.conv3d_causal(x, wk, b, out, T, H, W, ops.YB_EPI_BF16, taps=(3, 1, 1), oob_zero_pad=True, stride_t=2, out_t_add=1)
+    got = out.view(1 + To, H, W, co)
+    assert rel(got[1:], ref) < KERNEL_TOL and bool((got[0] == 7.0).all())
+
+
+def test_wan22_vae_encode_glue_kernels(dev):
+    from oracle import wan22vae_enc
+    from yume_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(33)
+    # patchify(2): f32 [3, T, H, W] -> bf16 [T*H/2*W/2, 64], 12 channels (c r q), the rest zero — bit-exact after the bf16 rounding
+    T, H, W = 3, 8, 12
+    video = torch.randn(3, T, H, W, generator=g).to(dev)
+    out = torch.full((T * (H // 2) * (W // 2), 64), 7.0, device=dev, dtype=torch.bfloat16)
+    ops.vae_patchify2_bf16(video, out)
+    want = wan22vae_enc.patchify2(video[None].cpu())[0].permute(1, 2, 3, 0).reshape(-1, 12).to(dev).bfloat16()
+    assert torch.equal(out[:, :12], want) and bool((out[:, 12:] == 0).all())
+    # AvgDown3D shortcut add against the oracle's whole-sequence form: every (ft, fs) / width ratio the encoder uses, odd T
+    for Tn, Hn, Wn, ci, co, ft, fs in ((5, 4, 6, 32, 32, 1, 2), (5, 4, 6, 32, 64, 2, 2), (1, 4, 6, 32, 64, 2, 2), (9, 2, 4, 64, 128, 2, 2),
+                                       (3, 4, 6, 128, 128, 1, 1), (5, 2, 2, 160, 320, 2, 2)):
+        x = torch.randn(Tn * Hn * Wn, ci, generator=g).to(dev).bfloat16()
+        short = wan22vae_enc.avg_down(x.float().cpu().view(Tn, Hn, Wn, ci).permute(3, 0, 1, 2)[None], co, ft, fs)[0]   # [co, To, Ho, Wo]
+        To, Ho, Wo = short.shape[1:]
+        main = torch.randn(To * Ho * Wo, co, generator=g).to(dev).bfloat16()
+        want = main.float().view(To, Ho, Wo, co) + short.permute(1, 2, 3, 0).to(dev)
+        ops.vae_avgdown_add(main, x, (Tn, Hn, Wn), ci, co, ft, fs)
+        assert rel(main.view(To, Ho, Wo, co), want) < 6e-3, (Tn, ci, co, ft, fs)
+
+
+def _enc_gold(golden_dir, name, mod):
+    g = torch.load(golden_dir / name, weights_only=False)
+    sd = mod.make_state_dict(g["seed_w"], **g["cfg"])
+    got = float(sum(v.abs().sum() for v in sd.values()))
+    if abs(got - g["weight_abs_sum"]) > 1e-3 * g["weight_abs_sum"]:
+        pytest.skip("torch CPU RNG stream differs from the one that generated the golden weights")
+    return g, sd
+
+
+ENC_PSNR_DB = 35.0   # latents are unbounded: PSNR against the fixture's own range
+
+
+@pytest.mark.parametrize("case", ["t1", "t5", "t9", "t17_wide"])
+def test_wan21_vae_encode_vs_reference_golden(dev, golden_dir, case):
+    """One-pass whole-sequence ENCODE on the GPU against the reference's own chunked / feature-cached `WanVAE_.encode`."""
+    from oracle import wan21vae_enc
+    from yume_b200.vae_enc import Wan21VaeEncoder
+    g, sd = _enc_gold(golden_dir, "wan21vae_enc_tiny.pt", wan21vae_enc)
+    c = g["cases"][case]
+    eng = Wan21VaeEncoder(sd, mean=g["mean"], std=g["std"], device=dev, **g["cfg"])
+    x = torch.randn(3, c["T"], c["H"], c["W"], generator=torch.Generator().manual_seed(c["seed"])).clamp_(-1, 1)
+    mu = eng.encode(x).cpu()
+    assert tuple(mu.shape) == c["shape"]
+    assert rel(mu, c["mu"]) < VAE_TOL and psnr(mu, c["mu"]) > ENC_PSNR_DB
+
+
+@pytest.mark.parametrize("case", ["t1", "t5", "t9", "t17_wide"])
+def test_wan22_vae_encode_vs_reference_golden(dev, golden_dir, case):
+    from oracle import wan22vae_enc
+    from yume_b200.vae_enc import Wan22VaeEncoder
+    g, sd = _enc_gold(golden_dir, "wan22vae_enc_tiny.pt", wan22vae_enc)
+    c = g["cases"][case]
+    eng = Wan22VaeEncoder(sd, mean=g["mean"], std=g["std"], device=dev, **g["cfg"])
+    x = torch.randn(3, c["T"], c["H"], c["W"], generator=torch.Generator().manual_seed(c["seed"])).clamp_(-1, 1)
+    mu = eng.encode(x).cpu()
+    assert tuple(mu.shape) == c["shape"]
+    assert rel(mu, c["mu"]) < VAE_TOL and psnr(mu, c["mu"]) > ENC_PSNR_DB
+
+
+@pytest.mark.parametrize("which", ["wan21", "wan22"])
+def test_wan_vae_encode_real_width_vs_oracle(dev, which):
+    """Real channel widths (2.1: 96/192/384/384, z16; 2.2: 160/320/640/640, z48) on a small clip against the fp32 oracle; a
+    frame count that is not 1 + 4k is truncated like the reference's chunk loop (vae2_2.py:802-803)."""
+    from oracle import wan21vae_enc, wan22vae_enc
+    from yume_b200.vae_enc import Wan21VaeEncoder, Wan22VaeEncoder
+    gen = torch.Generator().manual_seed(9)
+    if which == "wan21":
+        cfg = dict(dim=96, z_dim=16, dim_mult=(1, 2, 4, 4), num_res_blocks=2, temperal_downsample=(False, True, True))
+        mod, Oracle, Engine, hw = wan21vae_enc, wan21vae_enc.Wan21VaeEncodeOracle, Wan21VaeEncoder, (32, 48)
+    else:
+        cfg = dict(dim=160, z_dim=48, dim_mult=(1, 2, 4, 4), num_res_blocks=2, temperal_downsample=(False, True, True))
+        mod, Oracle, Engine, hw = wan22vae_enc, wan22vae_enc.Wan22VaeEncodeOracle, Wan22VaeEncoder, (64, 96)
+    sd = mod.make_state_dict(51, **cfg)
+    z = cfg["z_dim"]
+    mean, std = 0.2 * torch.randn(z, generator=gen), 0.5 + torch.rand(z, generator=gen)
+    video = torch.randn(3, 7, *hw, generator=gen).clamp_(-1, 1)            # 7 frames -> the first 5 are encoded
+    want = Oracle(sd, mean=mean, std=std, **cfg).encode(video[:, :5])
+    got = Engine(sd, mean=mean, std=std, device=dev, **cfg).encode(video).cpu()
+    assert got.shape == want.shape == (z, 2, hw[0] // (8 if which == "wan21" else 16), hw[1] // (8 if which == "wan21" else 16))
+    assert rel(got, want) < VAE_TOL and psnr(got, want) > ENC_PSNR_DB

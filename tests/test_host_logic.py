@@ -23,7 +23,7 @@ def test_library_exports_every_header_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/yume_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), "ctypes signature table and header disagree"
-    assert lib.yb_abi_version() == 2
+    assert lib.yb_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_ops_have_no_cpu_path():

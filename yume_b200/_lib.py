@@ -9,7 +9,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libyume_b200.so"
 
 YB_EPI_BF16, YB_EPI_GELU_BF16, YB_EPI_F32, YB_EPI_GATE_RES, YB_EPI_GELU_ERF_BF16, YB_EPI_RES_BF16 = 0, 1, 2, 3, 4, 5
 YB_ATT_P_SMEM, YB_ATT_ACCUMULATE = 1, 2
-ABI_VERSION = 2   # yb_abi_version() of the library this binding was written against
+ABI_VERSION = 3   # yb_abi_version() of the library this binding was written against
 YB_ATT_EMU_SHIFT, YB_ATT_SPLIT_SHIFT = 2, 4
 
 _ERRORS = {
@@ -49,7 +49,7 @@ class Conv3dArgs(C.Structure):
         ("ldo", C.c_longlong), ("res_ld", C.c_longlong),
         ("T", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cp", C.c_int), ("Cout", C.c_int), ("epilogue", C.c_int),
         ("kt", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("oob_zero_pad", C.c_int), ("out_t_mul", C.c_int),
-        ("out_t_add", C.c_int), ("fuse_w", C.c_int),
+        ("out_t_add", C.c_int), ("fuse_w", C.c_int), ("stride_t", C.c_int), ("stride_hw", C.c_int),
     ]
 
 
@@ -73,6 +73,8 @@ SIGNATURES = {
     "yb_vae_rms_act": (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "yb_vae_dupup_add": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "yb_vae_unpatchify2_clamp": (_i, [_vp, _ll, _vp, _i, _i, _i, _vp]),
+    "yb_vae_avgdown_add": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "yb_vae_patchify2_bf16": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp]),
     "yb_ln_modulate": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp, _ll, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "yb_rmsnorm_rope": (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "yb_rmsnorm_rope_pieces": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp]),

@@ -51,6 +51,8 @@ struct GemmParams {
   int off_t, off_h, off_w;      // subtracted from the box coordinates: 0 when the padding is materialised in the input,
                                 // (kt-1, kh/2, kw/2) when it is TMA out-of-bounds zero fill on the unpadded input
   int out_t_mul, out_t_add;     // output frame of input frame t = t*out_t_mul + out_t_add (time_conv interleave)
+  int st_t, st_h, st_w;         // conv stride per axis (1 or 2): the tensor map samples every st-th voxel (elementStrides), so a box
+                                // still lands as 128 dense rows; cT/cH/cW are OUTPUT extents, the tile origin scales by the stride
   int num_m_tiles, num_n_tiles;
   int block_n, stages;          // SM-pair kernel (gemm_pair_kernel): runtime N tile (multiple of 32, <= 256) and ring depth
   // YB_EPI_SP_QKV (internal): the fused q|k|v projection of a Ulysses rank whose epilogue IS the all-to-all — column
@@ -331,8 +333,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int per_t = p.tiles_h * p.tiles_w;
             const int it = m_tile / per_t, rem = m_tile - it * per_t;
             const int ih = rem / p.tiles_w, iw = rem - ih * p.tiles_w;
-            tma_load_4d(sa, &tmA, &full_bar[stage], cc * GEMM_BLOCK_K, iw * p.TW + dw - p.off_w,
-                        ih * p.TH + dh - p.off_h, it * p.TT + dt - p.off_t);
+            tma_load_4d(sa, &tmA, &full_bar[stage], cc * GEMM_BLOCK_K, iw * p.TW * p.st_w + dw - p.off_w,
+                        ih * p.TH * p.st_h + dh - p.off_h, it * p.TT * p.st_t + dt - p.off_t);
           } else {
             const int chunk = kcol / p.a_split;
             tma_load_3d(sa, &tmA, &full_bar[stage], kcol - chunk * p.a_split, m_tile * GEMM_BLOCK_M, chunk);
@@ -563,8 +565,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int mt = m_tile * 2 + rank, per_t = p.tiles_h * p.tiles_w;
             const int it = mt / per_t, rem = mt - it * per_t;
             const int ih = rem / p.tiles_w, iw = rem - ih * p.tiles_w;
-            tma_load_4d_2cta(sa, &tmA, &full_bar[stage], cc * GEMM_BLOCK_K, iw * p.TW + dw - p.off_w, ih * p.TH + dh - p.off_h,
-                             it * p.TT + dt - p.off_t);   // (a pair's second box past the last tile is all out of bounds: zeros)
+            tma_load_4d_2cta(sa, &tmA, &full_bar[stage], cc * GEMM_BLOCK_K, iw * p.TW * p.st_w + dw - p.off_w,
+                             ih * p.TH * p.st_h + dh - p.off_h, it * p.TT * p.st_t + dt - p.off_t);   // (a pair's second box past the last tile is all out of bounds: zeros)
           } else {
             const int chunk = kcol / p.a_split;      // K-split A (Ulysses receive buffer): see the 1-CTA producer
             tma_load_3d_2cta(sa, &tmA, &full_bar[stage], kcol - chunk * p.a_split, (m_tile * 2 + rank) * GEMM_BLOCK_M, chunk);
@@ -986,25 +988,36 @@ extern "C" int yb_conv3d_causal(const yb_conv3d_args* a, void* stream_) {
   const int block_n = (a->Cout % 256 == 0) ? 256 : 128;
   bool fuse_w = false;
   if (a->cta_pair < 0 || a->cta_pair > 2) return YB_ERR_ARG;
+  // strided form (the Encoder3d `Resample` convs): input extents T/H/W, output extents (in + pad - k) / stride + 1 with the
+  // padding BEHIND the data (ZeroPad2d((0,1,0,1)), vae2_2.py:101-104) or none at all (time_conv, :105-110)
+  const int st_t = a->stride_t > 0 ? a->stride_t : 1, st_hw = a->stride_hw > 0 ? a->stride_hw : 1;
+  if (st_t > 2 || st_hw > 2) return YB_ERR_ARG;
+  const bool strided = st_t > 1 || st_hw > 1;
+  if (strided && !a->oob_zero_pad) return YB_ERR_ARG;
+  int oT = a->T, oH = a->H, oW = a->W;
+  if (st_t > 1) oT = (a->T - kt) / st_t + 1;
+  if (st_hw > 1) { oH = (a->H + 1 - kh) / st_hw + 1; oW = (a->W + 1 - kw) / st_hw + 1; }
+  if (oT <= 0 || oH <= 0 || oW <= 0) return YB_ERR_SHAPE;
   // SM-pair kernel: 1 = forced, 2 = forced off, 0 = automatic — taken for output widths the 1-CTA kernel has to cut into a 128-wide
   // tile plus a padded remainder (192, 384 channels of the Wan2.1 decoder: 1006 vs 678 and 832 vs 787 TFLOP/s measured); the other
   // widths keep the 1-CTA kernel, whose kw-fused mode (3x less A traffic) wins there (profiles/r02_gemm_pair.md)
   const bool conv_pair = a->cta_pair == 1 || (a->cta_pair == 0 && a->fuse_w != 2 && a->Cout > 128 && a->Cout % 256 != 0 && a->Cout <= 512);
-  conv_plan(a->T, a->H, a->W, block_n, kw, conv_pair ? 1 : a->fuse_w, &p.TW, &p.TH, &p.TT, &fuse_w);
-  p.tiles_w = (a->W + p.TW - 1) / p.TW;
-  p.tiles_h = (a->H + p.TH - 1) / p.TH;
-  const int tiles_t = (a->T + p.TT - 1) / p.TT;
+  conv_plan(oT, oH, oW, block_n, kw, (conv_pair || strided) ? 1 : a->fuse_w, &p.TW, &p.TH, &p.TT, &fuse_w);
+  p.tiles_w = (oW + p.TW - 1) / p.TW;
+  p.tiles_h = (oH + p.TH - 1) / p.TH;
+  const int tiles_t = (oT + p.TT - 1) / p.TT;
   const int taps = kt * kh * kw;
   p.conv = fuse_w ? 2 : 1;
   p.cin_chunks = a->Cp / 64;
-  p.cT = a->T; p.cH = a->H; p.cW = a->W;
+  p.cT = oT; p.cH = oH; p.cW = oW;
   p.kh = kh; p.kw = kw;
-  p.off_t = a->oob_zero_pad ? kt - 1 : 0;
-  p.off_h = a->oob_zero_pad ? kh / 2 : 0;
-  p.off_w = a->oob_zero_pad ? kw / 2 : 0;
+  p.st_t = st_t; p.st_h = st_hw; p.st_w = st_hw;
+  p.off_t = (a->oob_zero_pad && st_t == 1) ? kt - 1 : 0;
+  p.off_h = (a->oob_zero_pad && st_hw == 1) ? kh / 2 : 0;
+  p.off_w = (a->oob_zero_pad && st_hw == 1) ? kw / 2 : 0;
   p.out_t_mul = a->out_t_mul > 0 ? a->out_t_mul : 1;
   p.out_t_add = a->out_t_add;
-  p.M = a->T * a->H * a->W;
+  p.M = oT * oH * oW;
   p.N = a->Cout;
   p.K = taps * a->Cp;
   p.num_m_tiles = tiles_t * p.tiles_h * p.tiles_w;
@@ -1018,7 +1031,7 @@ extern "C" int yb_conv3d_causal(const yb_conv3d_args* a, void* stream_) {
   CUtensorMap tmA, tmB;
   const int padT = a->oob_zero_pad ? 0 : kt - 1, padH = a->oob_zero_pad ? 0 : kh - 1, padW = a->oob_zero_pad ? 0 : kw - 1;
   int rc = make_tmap_bf16_4d(&tmA, a->xpad, a->T + padT, a->H + padH, a->W + padW, a->Cp, p.TT, p.TH,
-                             fuse_w ? CONVW_ROWS : p.TW, 64);
+                             fuse_w ? CONVW_ROWS : p.TW, 64, st_t, st_hw, st_hw);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, a->w, a->Cout, static_cast<uint64_t>(taps) * a->Cp, static_cast<uint64_t>(taps) * a->Cp,
                          block_n, GEMM_BLOCK_K);

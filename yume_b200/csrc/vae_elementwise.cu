@@ -445,6 +445,74 @@ dupup_add_kernel(__nv_bfloat16* __restrict__ main_, const __nv_bfloat16* __restr
   }
 }
 
+// AvgDown3D shortcut of the Wan2.2 encoder's Down_ResidualBlock (vae2_2.py:320-373, 449-459) over the whole frame sequence:
+// pad_t = (ft - T % ft) % ft zero frames in FRONT, 'b c (t a) (h q) (w r) -> b (c a q r) t h w', then the mean over groups of
+// G = in_c*ft*fs*fs / out_c consecutive channels. main[to, ho, wo, oc] += mean_g x[c, to*ft + a - pad_t, ho*fs + q, wo*fs + r]
+// with ((c*ft + a)*fs + q)*fs + r = oc*G + g. One thread = 8 consecutive output channels of one output voxel.
+__global__ void __launch_bounds__(256)
+avgdown_add_kernel(__nv_bfloat16* __restrict__ main_, const __nv_bfloat16* __restrict__ x, int T, int H, int W, int in_c,
+                   int out_c, int ft, int fs) {
+  const int pad_t = (ft - T % ft) % ft;
+  const int To = (T + pad_t) / ft, Ho = H / fs, Wo = W / fs;
+  const int G = in_c * ft * fs * fs / out_c, per_c = ft * fs * fs;
+  const int chunks = out_c >> 3;
+  const float inv = 1.0f / static_cast<float>(G);
+  const long long total = static_cast<long long>(To) * Ho * Wo * chunks;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i / chunks);
+    const int oc = static_cast<int>(i - static_cast<long long>(v) * chunks) << 3;
+    const int wo = v % Wo;
+    const int rr = v / Wo;
+    const int ho = rr % Ho;
+    const int to = rr / Ho;
+    uint4* mp = reinterpret_cast<uint4*>(main_ + static_cast<long long>(v) * out_c + oc);
+    uint4 raw = *mp;
+    __nv_bfloat16* hh = reinterpret_cast<__nv_bfloat16*>(&raw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float acc = 0.0f;
+      for (int g = 0; g < G; ++g) {
+        const int j = (oc + k) * G + g;
+        const int c = j / per_c, rem = j - c * per_c;
+        const int a = rem / (fs * fs), q = (rem / fs) % fs, r = rem % fs;
+        const int ti = to * ft + a - pad_t;
+        if (ti >= 0)
+          acc += __bfloat162float(x[((static_cast<long long>(ti) * H + ho * fs + q) * W + wo * fs + r) * in_c + c]);
+      }
+      hh[k] = __float2bfloat16_rn(__bfloat162float(hh[k]) + acc * inv);
+    }
+    *mp = raw;
+  }
+}
+
+// video f32 [3, T, H, W] -> out bf16 [T*(H/2)*(W/2), ldo], channel (c r q) = c*4 + r*2 + q <- video[c, f, 2h + q, 2w + r]
+// (patchify 'b c f (h q) (w r) -> b (c r q) f h w', vae2_2.py:284-300); columns 12..ldo-1 are zeroed (TMA reads 64-channel chunks)
+__global__ void patchify2_bf16_kernel(const float* __restrict__ video, __nv_bfloat16* __restrict__ out, long long ldo, int T,
+                                      int H, int W) {
+  const int Hh = H / 2, Wh = W / 2;
+  const long long total = static_cast<long long>(T) * Hh * Wh;
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(v % Wh);
+    const long long rr = v / Wh;
+    const int h = static_cast<int>(rr % Hh);
+    const int f = static_cast<int>(rr / Hh);
+    __nv_bfloat16* o = out + v * ldo;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* src = video + ((static_cast<long long>(c) * T + f) * H + 2 * h) * W + 2 * w;
+      const float2 top = *reinterpret_cast<const float2*>(src);          // q = 0: r = 0, 1
+      const float2 bot = *reinterpret_cast<const float2*>(src + W);      // q = 1
+      o[c * 4 + 0] = __float2bfloat16_rn(top.x);   // r = 0, q = 0
+      o[c * 4 + 1] = __float2bfloat16_rn(bot.x);   // r = 0, q = 1
+      o[c * 4 + 2] = __float2bfloat16_rn(top.y);   // r = 1, q = 0
+      o[c * 4 + 3] = __float2bfloat16_rn(bot.y);   // r = 1, q = 1
+    }
+    for (int c = 12; c < ldo; ++c) o[c] = __float2bfloat16_rn(0.0f);
+  }
+}
+
 // y f32 [T*H*W, ldy] (12 valid channels) -> out f32 [3, T, 2H, 2W], clamp to [-1, 1]:
 // unpatchify 'b (c r q) f h w -> b c f (h q) (w r)' (:305-319) + Wan2_2_VAE.decode's clamp_ (:1066-1067)
 __global__ void unpatchify2_clamp_kernel(const float* __restrict__ y, long long ldy, float* __restrict__ out, int T, int H,
@@ -610,6 +678,29 @@ extern "C" int yb_vae_dupup_add(void* main_, const void* x, int Ts, int Hs, int 
   dupup_add_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
       static_cast<__nv_bfloat16*>(main_), static_cast<const __nv_bfloat16*>(x), Ts, Hs, Ws, in_c, out_c, ft, fs);
   return check_launch("vae_dupup_add");
+}
+
+extern "C" int yb_vae_avgdown_add(void* main_, const void* x, int T, int H, int W, int in_c, int out_c, int ft, int fs,
+                                  void* stream_) {
+  if (!main_ || !x || T <= 0 || H <= 0 || W <= 0 || in_c <= 0 || out_c <= 0 || ft < 1 || fs < 1) return YB_ERR_ARG;
+  if ((in_c * ft * fs * fs) % out_c != 0 || out_c % 8 != 0 || H % fs != 0 || W % fs != 0) return YB_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(main_) & 0xF) return YB_ERR_ALIGNMENT;
+  const long long To = (T + (ft - T % ft) % ft) / ft;
+  if (To * (H / fs) * (W / fs) > 0x7fffffffLL) return YB_ERR_SHAPE;
+  const long long total = To * (H / fs) * (W / fs) * (out_c / 8);
+  avgdown_add_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      static_cast<__nv_bfloat16*>(main_), static_cast<const __nv_bfloat16*>(x), T, H, W, in_c, out_c, ft, fs);
+  return check_launch("vae_avgdown_add");
+}
+
+extern "C" int yb_vae_patchify2_bf16(const void* video, void* out, long long ldo, int T, int H, int W, void* stream_) {
+  if (!video || !out || T <= 0 || H <= 0 || W <= 0 || ldo < 12) return YB_ERR_ARG;
+  if ((H % 2) || (W % 2)) return YB_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(video) & 0x7) return YB_ERR_ALIGNMENT;
+  patchify2_bf16_kernel<<<grid_for(static_cast<long long>(T) * (H / 2) * (W / 2)), 256, 0,
+                          reinterpret_cast<cudaStream_t>(stream_)>>>(static_cast<const float*>(video),
+                                                                     static_cast<__nv_bfloat16*>(out), ldo, T, H, W);
+  return check_launch("vae_patchify2_bf16");
 }
 
 extern "C" int yb_vae_unpatchify2_clamp(const void* y, long long ldy, void* out, int T, int H, int W, void* stream_) {

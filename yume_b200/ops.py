@@ -322,10 +322,11 @@ CONV_CTA_PAIR = 0
 def conv3d_causal(xpad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, T: int, H: int,
                   W: int, epilogue: int = YB_EPI_BF16, res: Optional[torch.Tensor] = None, taps=(3, 3, 3),
                   oob_zero_pad: bool = False, out_t_mul: int = 1, out_t_add: int = 0, fuse_w: int = 0,
-                  cta_pair: Optional[int] = None) -> torch.Tensor:
+                  cta_pair: Optional[int] = None, stride_t: int = 1, stride_hw: int = 1) -> torch.Tensor:
     """Implicit-GEMM causal conv. Default: xpad bf16 [T+2, H+2, W+2, Cp] replicate padded (hyvideo VAE). With
     oob_zero_pad the input is the unpadded [T, H, W, Cp] and the zero padding is TMA out-of-bounds fill (Wan2.2 VAE).
-    w bf16 [Cout, kt*kh*kw*Cp]; out rows are output voxels (frame t -> t*out_t_mul + out_t_add)."""
+    w bf16 [Cout, kt*kh*kw*Cp]; out rows are output voxels (frame t -> t*out_t_mul + out_t_add). stride_hw / stride_t = 2:
+    the Encoder3d Resample convs (see include/yume_b200.h); T, H, W stay the input extents."""
     global _launches, _flops
     _need(xpad, torch.bfloat16, "xpad")
     _need(w, torch.bfloat16, "w")
@@ -341,11 +342,21 @@ def conv3d_causal(xpad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tens
                       xpad=xpad.data_ptr(), w=w.data_ptr(), bias=_ptr(bias), out=out.data_ptr(), res=_ptr(res),
                       ldo=out.stride(0), res_ld=(res.stride(0) if res is not None else 0), T=T, H=H, W=W, Cp=Cp,
                       Cout=w.shape[0], epilogue=epilogue, kt=kt, kh=kh, kw=kw, oob_zero_pad=1 if oob_zero_pad else 0,
-                      out_t_mul=out_t_mul, out_t_add=out_t_add, fuse_w=fuse_w)
+                      out_t_mul=out_t_mul, out_t_add=out_t_add, fuse_w=fuse_w, stride_t=stride_t, stride_hw=stride_hw)
     check(_lib.load().yb_conv3d_causal(C.byref(args), _stream()), "yb_conv3d_causal")
     _launches += 1
-    _flops += 2.0 * T * H * W * kt * kh * kw * Cp * w.shape[0]
+    To, Ho, Wo = conv_out_dims(T, H, W, taps, stride_t, stride_hw)
+    _flops += 2.0 * To * Ho * Wo * kt * kh * kw * Cp * w.shape[0]
     return out
+
+
+def conv_out_dims(T: int, H: int, W: int, taps=(3, 3, 3), stride_t: int = 1, stride_hw: int = 1):
+    """Output extents of yb_conv3d_causal: unit stride keeps the extents; the strided forms follow the reference's
+    `Resample` (ZeroPad2d((0,1,0,1)) + Conv2d stride 2; unpadded time_conv stride 2)."""
+    kt, kh, kw = taps
+    To = (T - kt) // stride_t + 1 if stride_t > 1 else T
+    Ho, Wo = ((H + 1 - kh) // stride_hw + 1, (W + 1 - kw) // stride_hw + 1) if stride_hw > 1 else (H, W)
+    return To, Ho, Wo
 
 
 def gn_stats(x: torch.Tensor, groups: int) -> torch.Tensor:
@@ -555,6 +566,33 @@ def vae_dupup_add(main: torch.Tensor, x: torch.Tensor, dims, in_c: int, out_c: i
                                        _stream()), "yb_vae_dupup_add")
     _launches += 1
     return main
+
+
+def vae_avgdown_add(main: torch.Tensor, x: torch.Tensor, dims, in_c: int, out_c: int, ft: int, fs: int) -> torch.Tensor:
+    """main bf16 [ceil(T/ft), H/fs, W/fs, out_c] += AvgDown3D(x bf16 [T, H, W, in_c]) (dims = the INPUT extents)."""
+    global _launches
+    _need(main, torch.bfloat16, "main")
+    _need(x, torch.bfloat16, "x")
+    if not (main.is_contiguous() and x.is_contiguous()) or x.shape[-1] != in_c or main.shape[-1] != out_c:
+        raise YumeB200Error("vae_avgdown_add needs dense [.., in_c] / [.., out_c] tensors")
+    check(_lib.load().yb_vae_avgdown_add(main.data_ptr(), x.data_ptr(), dims[0], dims[1], dims[2], in_c, out_c, ft, fs,
+                                         _stream()), "yb_vae_avgdown_add")
+    _launches += 1
+    return main
+
+
+def vae_patchify2_bf16(video: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """video f32 [3, T, H, W] -> out bf16 [T*(H/2)*(W/2), ldo] (12 patch channels, rest zero)."""
+    global _launches
+    _need(video, torch.float32, "video")
+    _need(out, torch.bfloat16, "out")
+    if video.dim() != 4 or video.shape[0] != 3 or not video.is_contiguous() or not out.is_contiguous():
+        raise YumeB200Error("vae_patchify2_bf16: video must be a contiguous [3, T, H, W]")
+    _, T, H, W = video.shape
+    check(_lib.load().yb_vae_patchify2_bf16(video.data_ptr(), out.data_ptr(), out.shape[-1], T, H, W, _stream()),
+          "yb_vae_patchify2_bf16")
+    _launches += 1
+    return out
 
 
 def vae_unpatchify2_clamp(y: torch.Tensor, out: torch.Tensor, T: int, H: int, W: int) -> torch.Tensor:

@@ -46,20 +46,54 @@ class KernelTimer:
 
 
 class ClockSampler:
-    """Samples `nvidia-smi` SM clocks and throttle reasons every 200 ms in a background thread
-    (the query line of /opt/skills/guides/B200_PROFILING.md)."""
+    """Samples SM clocks and throttle reasons of one GPU in a background thread while a timed region runs: NVML every 20 ms
+    when `pynvml` can open the device (a 40 ms multi-GPU step still gets several samples under load), else the `nvidia-smi`
+    query line of /opt/skills/guides/B200_PROFILING.md every 200 ms. Both read the same driver counters."""
 
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # NVML clocks-event-reason bits (nvml.h: nvmlClocksEventReason*)
+    _NVML_BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index: int = 0):
         self.gpu_index = gpu_index
         self.samples: List[List[str]] = []
+        self.source = "nvidia-smi"
         self._stop = threading.Event()
         self._thread: Optional[threading.Thread] = None
+        self._nvml = None
+
+    def _open_nvml(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            try:                                                   # CUDA ordinal -> NVML handle through the UUID
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.gpu_index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            return pynvml, handle
+        except Exception:
+            return None
 
     def _run(self):
+        if self._nvml is not None:
+            nv, h = self._nvml
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop.is_set():
+                try:
+                    bits = int(get_reasons(h))
+                    self.samples.append([str(self.gpu_index), str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), "", ""]
+                                        + [("Active" if bits & b else "Not Active") for _, b in self._NVML_BITS])
+                except Exception:
+                    pass
+                self._stop.wait(0.02)
+            return
         while not self._stop.is_set():
             try:
                 r = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
@@ -71,6 +105,8 @@ class ClockSampler:
             self._stop.wait(0.2)
 
     def __enter__(self):
+        self._nvml = self._open_nvml()
+        self.source = "nvml" if self._nvml is not None else "nvidia-smi"
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
         return self
@@ -95,4 +131,4 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no_samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": self.source}

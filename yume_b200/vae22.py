@@ -88,10 +88,13 @@ class Wan22VaeDecoder:
         self._repack(sd, mean.detach().to(self.device, _F32), std.detach().to(self.device, _F32))
 
     # ---- weights -------------------------------------------------------------------------------------------
-    def _repack(self, sd: Dict[str, Tensor], mean: Tensor, std: Tensor) -> None:
+    def _pack_side(self, sd: Dict[str, Tensor], prefixes: Tuple[str, ...], latent_conv: str, attn: str, width: int,
+                   split_time_conv: bool) -> Dict[str, Tensor]:
+        """Re-pack one side of a `WanVAE_` state dict (decode: `decoder.*` + `conv2`; encode: `encoder.*` + `conv1`): 3-D / 2-D
+        convs as [cop, taps*cp] bf16 GEMM weights, 1x1x1 shortcuts as plain matrices, gammas flat, the mid attention with the
+        softmax scale folded into q and the v bias folded through `proj`. Returns the fp32 device copy of that side."""
         dev = self.device
-        # decode-side modules only (`conv2`, `decoder.*`); a live WanVAE_ also carries `encoder.*` and `conv1.*`
-        sd = {k: v.detach().to(dev, _F32) for k, v in sd.items() if k.startswith(("decoder.", "conv2."))}
+        sd = {k: v.detach().to(dev, _F32) for k, v in sd.items() if k.startswith(prefixes)}
         self.conv: Dict[str, Tuple[Tensor, Tensor, tuple]] = {}    # name -> (w bf16 [cop, taps*cp], bias f32 [cop], taps)
         self.lin: Dict[str, Tuple[Tensor, Tensor]] = {}            # 1x1x1 convs as plain GEMM weights
         self.gamma: Dict[str, Tensor] = {}
@@ -108,10 +111,11 @@ class Wan22VaeDecoder:
             bp[:co] = b.detach().float()
             self.conv[name] = (wt.reshape(cop, -1).to(dev, _BF16).contiguous(), bp.to(dev), (kt, kh, kw))
 
+        latent_w = latent_conv + ".weight"
         for k, v in sd.items():
             if k.endswith(".gamma"):
                 self.gamma[k[:-6]] = v.detach().to(dev, _F32).reshape(-1).contiguous()
-            elif k.endswith(".weight") and v.dim() == 5 and tuple(v.shape[2:]) == (1, 1, 1) and k != "conv2.weight":
+            elif k.endswith(".weight") and v.dim() == 5 and tuple(v.shape[2:]) == (1, 1, 1) and k != latent_w:
                 name = k[:-7]                                       # ResidualBlock.shortcut: plain GEMM
                 co, ci = v.shape[:2]
                 w = torch.zeros(_rup(co, 32), _rup(ci, 8), dtype=_F32, device=dev)
@@ -119,13 +123,30 @@ class Wan22VaeDecoder:
                 b = torch.zeros(_rup(co, 32), dtype=_F32, device=dev)
                 b[:co] = sd[name + ".bias"].detach().float()
                 self.lin[name] = (w.to(dev, _BF16).contiguous(), b.to(dev))
-            elif k.endswith(".time_conv.weight"):
+            elif k.endswith(".time_conv.weight") and split_time_conv:
                 name = k[:-7]
                 C2 = v.shape[0]
                 for g in (0, 1):                                    # the two channel groups become two output frames
                     pack_conv(f"{name}.{g}", v[g * C2 // 2:(g + 1) * C2 // 2], sd[name + ".bias"][g * C2 // 2:(g + 1) * C2 // 2])
-            elif k.endswith(".weight") and v.dim() in (4, 5) and "to_qkv" not in k and ".proj." not in k and k != "conv2.weight":
+            elif k.endswith(".weight") and v.dim() in (4, 5) and "to_qkv" not in k and ".proj." not in k and k != latent_w:
                 pack_conv(k[:-7], v, sd[k[:-7] + ".bias"])
+        # attention: scale folded into q; v bias folded through proj (softmax rows sum to 1)
+        C = width
+        Wqkv = sd[attn + ".to_qkv.weight"].detach().float().reshape(3 * C, C)
+        bqkv = sd[attn + ".to_qkv.bias"].detach().float()
+        Wo = sd[attn + ".proj.weight"].detach().float().reshape(C, C)
+        scale = C ** -0.5
+        self.att = dict(wq=(Wqkv[:C] * scale).to(dev, _BF16).contiguous(), bq=(bqkv[:C] * scale).to(dev),
+                        wk=Wqkv[C:2 * C].to(dev, _BF16).contiguous(), bk=bqkv[C:2 * C].to(dev).contiguous(),
+                        wv=Wqkv[2 * C:].to(dev, _BF16).contiguous(),
+                        wo=Wo.to(dev, _BF16).contiguous(),
+                        bo=(sd[attn + ".proj.bias"].detach().float() + Wo @ bqkv[2 * C:]).to(dev).contiguous())
+        return sd
+
+    def _repack(self, sd: Dict[str, Tensor], mean: Tensor, std: Tensor) -> None:
+        dev = self.device
+        # decode-side modules only (`conv2`, `decoder.*`); a live WanVAE_ also carries `encoder.*` and `conv1.*`
+        sd = self._pack_side(sd, ("decoder.", "conv2."), "conv2", "decoder.middle.1", self.dims[0], True)
         # conv2 (1x1x1, z -> z) with the latent de-normalisation folded in: conv2(z*std + mean) = (W diag(std)) z + (W mean + b)
         zd = self.z_dim
         W2 = sd["conv2.weight"].detach().float().reshape(zd, zd)
@@ -134,34 +155,23 @@ class Wan22VaeDecoder:
         b = torch.zeros(_rup(zd, 32), dtype=_F32, device=dev)
         b[:zd] = W2 @ mean + sd["conv2.bias"].detach().float()
         self.lin["conv2"] = (w.to(dev, _BF16).contiguous(), b.to(dev))
-        # attention: scale folded into q; v bias folded through proj (softmax rows sum to 1)
-        a = "decoder.middle.1"
-        C = self.dims[0]
-        Wqkv = sd[a + ".to_qkv.weight"].detach().float().reshape(3 * C, C)
-        bqkv = sd[a + ".to_qkv.bias"].detach().float()
-        Wo = sd[a + ".proj.weight"].detach().float().reshape(C, C)
-        scale = C ** -0.5
-        self.att = dict(wq=(Wqkv[:C] * scale).to(dev, _BF16).contiguous(), bq=(bqkv[:C] * scale).to(dev),
-                        wk=Wqkv[C:2 * C].to(dev, _BF16).contiguous(), bk=bqkv[C:2 * C].to(dev).contiguous(),
-                        wv=Wqkv[2 * C:].to(dev, _BF16).contiguous(),
-                        wo=Wo.to(dev, _BF16).contiguous(),
-                        bo=(sd[a + ".proj.bias"].detach().float() + Wo @ bqkv[2 * C:]).to(dev).contiguous())
 
     # ---- building blocks -----------------------------------------------------------------------------------
     def _new(self, *shape, dtype=_BF16) -> Tensor:
         return torch.empty(*shape, device=self.device, dtype=dtype)
 
     def _conv(self, name: str, a: Tensor, dims, epilogue=None, res: Optional[Tensor] = None, out: Optional[Tensor] = None,
-              out_t_mul: int = 1, out_t_add: int = 0) -> Tensor:
-        """a bf16 [T, H, W, Cp] (unpadded, dense) -> [T*H*W (or interleaved frames), cop]."""
+              out_t_mul: int = 1, out_t_add: int = 0, stride_t: int = 1, stride_hw: int = 1) -> Tensor:
+        """a bf16 [T, H, W, Cp] (unpadded, dense) -> [To*Ho*Wo (or interleaved frames), cop]."""
         w, b, taps = self.conv[name]
         T, H, W = dims
         if epilogue is None:
             epilogue = ops.YB_EPI_RES_BF16 if res is not None else ops.YB_EPI_BF16
         if out is None:
-            out = self._new(T * H * W, w.shape[0], dtype=_F32 if epilogue == ops.YB_EPI_F32 else _BF16)
+            To, Ho, Wo = ops.conv_out_dims(T, H, W, taps, stride_t, stride_hw)
+            out = self._new(To * Ho * Wo, w.shape[0], dtype=_F32 if epilogue == ops.YB_EPI_F32 else _BF16)
         ops.conv3d_causal(a, w, b, out, T, H, W, epilogue, res, taps=taps, oob_zero_pad=True, out_t_mul=out_t_mul,
-                          out_t_add=out_t_add)
+                          out_t_add=out_t_add, stride_t=stride_t, stride_hw=stride_hw)
         return out
 
     def _act(self, x: Tensor, dims, gamma: Optional[str], silu: bool, up: int = 1) -> Tensor:
@@ -185,23 +195,37 @@ class Wan22VaeDecoder:
         T, H, W = dims
         N, C = x.shape
         HW = H * W
-        if HW % 8:
-            raise YumeB200Error("Wan2.2 VAE attention needs H*W % 8 == 0 (16-byte aligned per-frame slices)")
         Lf = _rup(HW, 32)                                        # per-frame key count padded for the GEMM tile
-        Next = _rup(N, 32) + 32
-        hn = torch.zeros(Next, C, device=self.device, dtype=_BF16)
-        ops.vae_rms_act(x, dims, hn[:N].view(T, H, W, C), self.gamma[p + ".norm"], 1, False)
         a = self.att
-        q, k = self._new(N, C), torch.zeros(Next, C, device=self.device, dtype=_BF16)
-        ops.gemm(hn[:N], a["wq"], a["bq"], q, ops.YB_EPI_BF16)
-        ops.gemm(hn[:N], a["wk"], a["bk"], k[:N], ops.YB_EPI_BF16)
-        vT = self._new(C, Next)
-        ops.gemm(a["wv"], hn, None, vT, ops.YB_EPI_BF16)
         S, P, o = self._new(HW, Lf, dtype=_F32), self._new(HW, Lf), self._new(N, C)
-        for f in range(T):
-            ops.gemm(q[f * HW:(f + 1) * HW], k[f * HW:f * HW + Lf], None, S, ops.YB_EPI_F32)
-            ops.masked_softmax(S, P, HW, HW)                     # keys >= HW (padding / next frame) get probability 0
-            ops.gemm(P, vT[:, f * HW:f * HW + Lf], None, o[f * HW:(f + 1) * HW], ops.YB_EPI_BF16)
+        if HW % 8:
+            # frames whose H*W rows are not 16-byte multiples in the transposed V (tiny latents only): every frame gets its own
+            # zero-padded Lf-row slot, so per-frame slices of q, k and v^T start on aligned addresses
+            tmp = self._new(T, H, W, C)
+            ops.vae_rms_act(x, dims, tmp, self.gamma[p + ".norm"], 1, False)
+            hn = torch.zeros(T * Lf + 32, C, device=self.device, dtype=_BF16)
+            hn[:T * Lf].view(T, Lf, C)[:, :HW].copy_(tmp.view(T, HW, C))
+            q, k, vT = self._new(T * Lf, C), self._new(T * Lf, C), self._new(C, T * Lf + 32)
+            ops.gemm(hn[:T * Lf], a["wq"], a["bq"], q, ops.YB_EPI_BF16)
+            ops.gemm(hn[:T * Lf], a["wk"], a["bk"], k, ops.YB_EPI_BF16)
+            ops.gemm(a["wv"], hn, None, vT, ops.YB_EPI_BF16)
+            for f in range(T):
+                ops.gemm(q[f * Lf:f * Lf + HW], k[f * Lf:(f + 1) * Lf], None, S, ops.YB_EPI_F32)
+                ops.masked_softmax(S, P, HW, HW)
+                ops.gemm(P, vT[:, f * Lf:(f + 1) * Lf], None, o[f * HW:(f + 1) * HW], ops.YB_EPI_BF16)
+        else:
+            Next = _rup(N, 32) + 32
+            hn = torch.zeros(Next, C, device=self.device, dtype=_BF16)
+            ops.vae_rms_act(x, dims, hn[:N].view(T, H, W, C), self.gamma[p + ".norm"], 1, False)
+            q, k = self._new(N, C), torch.zeros(Next, C, device=self.device, dtype=_BF16)
+            ops.gemm(hn[:N], a["wq"], a["bq"], q, ops.YB_EPI_BF16)
+            ops.gemm(hn[:N], a["wk"], a["bk"], k[:N], ops.YB_EPI_BF16)
+            vT = self._new(C, Next)
+            ops.gemm(a["wv"], hn, None, vT, ops.YB_EPI_BF16)
+            for f in range(T):
+                ops.gemm(q[f * HW:(f + 1) * HW], k[f * HW:f * HW + Lf], None, S, ops.YB_EPI_F32)
+                ops.masked_softmax(S, P, HW, HW)                 # keys >= HW (padding / next frame) get probability 0
+                ops.gemm(P, vT[:, f * HW:f * HW + Lf], None, o[f * HW:(f + 1) * HW], ops.YB_EPI_BF16)
         out = self._new(N, C)
         ops.gemm(o, a["wo"], a["bo"], out, ops.YB_EPI_RES_BF16, res=x)
         return out
