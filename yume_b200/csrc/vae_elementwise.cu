@@ -12,15 +12,17 @@ namespace yb {
 
 // ---------------------------------------------------------------------------------------------------------
 // GroupNorm statistics: x bf16 [N, C] (row stride ld) -> stats f64 [G][2] += (sum, sum of squares).
-// Thread owns one 8-channel chunk and strides over voxels; per-channel fp32 partials -> smem per-group -> fp64 atomics.
+// Thread owns one 8-channel chunk and strides over voxels; per-channel fp32 partials (fixed order) -> fp64 atomics in smem per
+// group -> fp64 global atomics: the only order-dependent sums are in double, so a decode is reproducible run to run (a float
+// smem stage made statistics differ at 1e-7 between runs, enough to flip bf16 roundings that a deep decoder amplifies).
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ld, double* __restrict__ stats, long long N, int C, int G) {
-  __shared__ float sg[64][2];
+  __shared__ double sg[64][2];
   const int chunks = C >> 3;                 // 8-channel chunks per voxel
   const int vox_per_block = 256 / chunks;    // voxels handled per block iteration (chunks <= 256)
   const int tid = threadIdx.x;
-  if (tid < 64) sg[tid][0] = sg[tid][1] = 0.f;
+  if (tid < 64) sg[tid][0] = sg[tid][1] = 0.0;
   __syncthreads();
   const int cg = C / G;                      // channels per group
   float s[8], q[8];
@@ -42,14 +44,14 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ld, double* __res
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int g = (chunk * 8 + i) / cg;
-      atomicAdd(&sg[g][0], s[i]);
-      atomicAdd(&sg[g][1], q[i]);
+      atomicAdd(&sg[g][0], static_cast<double>(s[i]));
+      atomicAdd(&sg[g][1], static_cast<double>(q[i]));
     }
   }
   __syncthreads();
   if (tid < G) {
-    atomicAdd(&stats[2 * tid], static_cast<double>(sg[tid][0]));
-    atomicAdd(&stats[2 * tid + 1], static_cast<double>(sg[tid][1]));
+    atomicAdd(&stats[2 * tid], sg[tid][0]);
+    atomicAdd(&stats[2 * tid + 1], sg[tid][1]);
   }
 }
 
