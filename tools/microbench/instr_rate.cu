@@ -1,0 +1,134 @@
+// Issue-rate microbenchmark for the softmax inner loop of the attention kernel (sm_100a): how many cycles does one warp
+// instruction of each kind cost per SM sub-partition, alone and in the mixes the kernel issues? Answers (profiles/r02_instr_rate.md):
+// the MUFU.EX2 rate, whether the fp32->bf16x2 pack (F2FP) shares a pipe with it, what a packed-FMA polynomial costs beside it.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench/instr_rate tools/microbench/instr_rate.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t pack(float lo, float hi) {
+  uint32_t r; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r;
+}
+__device__ __forceinline__ float fma_(float a, float b, float c) { float d; asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+__device__ __forceinline__ float add_(float a, float b) { float d; asm volatile("add.rn.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b) { uint32_t d; asm volatile("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d; asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) { uint32_t y; asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ float max3(float a, float b, float c) { float d; asm volatile("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+
+constexpr int U = 16;   // independent chains per thread
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) rate_kernel(int iters, float seed, long long* cycles, float* sink) {
+  float x[U];
+  uint32_t w[U / 2];
+#pragma unroll
+  for (int i = 0; i < U; ++i) x[i] = seed + 0.001f * (threadIdx.x + i);
+#pragma unroll
+  for (int i = 0; i < U / 2; ++i) w[i] = threadIdx.x + i;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (MODE == 0) {            // MUFU.EX2 only
+#pragma unroll
+      for (int i = 0; i < U; ++i) x[i] = ex2(x[i]);
+    } else if (MODE == 1) {     // F2FP pack only (one per pair)
+#pragma unroll
+      for (int i = 0; i < U / 2; ++i) { w[i] = pack(x[2 * i], x[2 * i + 1]); x[2 * i] = __uint_as_float(w[i]); }
+    } else if (MODE == 2) {     // 2 ex2 + 1 pack per pair
+#pragma unroll
+      for (int i = 0; i < U / 2; ++i) { x[2 * i] = ex2(x[2 * i]); x[2 * i + 1] = ex2(x[2 * i + 1]); w[i] ^= pack(x[2 * i], x[2 * i + 1]); }
+    } else if (MODE == 3) {     // FFMA only
+#pragma unroll
+      for (int i = 0; i < U; ++i) x[i] = fma_(x[i], 1.0001f, 0.5f);
+    } else if (MODE == 4) {     // the kernel's mix per pair: 2 FFMA (scale, -max), 2 ex2, 2 FADD (row sum), 1 pack
+#pragma unroll
+      for (int i = 0; i < U / 2; ++i) {
+        const float a = ex2(fma_(x[2 * i], 1.0001f, -0.5f)), b = ex2(fma_(x[2 * i + 1], 1.0001f, -0.5f));
+        x[2 * i] = add_(x[2 * i], a); x[2 * i + 1] = add_(x[2 * i + 1], b);
+        w[i] ^= pack(a, b);
+      }
+    } else if (MODE == 5) {     // same mix, bf16 rounding on the FMA pipe (Veltkamp split: 1 FMUL + 2 FADD per value) + PRMT
+#pragma unroll
+      for (int i = 0; i < U / 2; ++i) {
+        const float a = ex2(fma_(x[2 * i], 1.0001f, -0.5f)), b = ex2(fma_(x[2 * i + 1], 1.0001f, -0.5f));
+        x[2 * i] = add_(x[2 * i], a); x[2 * i + 1] = add_(x[2 * i + 1], b);
+        const float ca = a * 65537.0f, cb = b * 65537.0f;
+        const float ha = add_(ca, -add_(ca, -a)), hb = add_(cb, -add_(cb, -b));
+        w[i] ^= prmt(__float_as_uint(ha), __float_as_uint(hb));
+      }
+    } else if (MODE == 6) {     // same mix, truncating pack (PRMT only)
+#pragma unroll
+      for (int i = 0; i < U / 2; ++i) {
+        const float a = ex2(fma_(x[2 * i], 1.0001f, -0.5f)), b = ex2(fma_(x[2 * i + 1], 1.0001f, -0.5f));
+        x[2 * i] = add_(x[2 * i], a); x[2 * i + 1] = add_(x[2 * i + 1], b);
+        w[i] ^= prmt(__float_as_uint(a), __float_as_uint(b));
+      }
+    } else if (MODE == 7) {     // packed bf16x2 exponentials only
+#pragma unroll
+      for (int i = 0; i < U / 2; ++i) w[i] = ex2_bf16x2(w[i]);
+    } else if (MODE == 8) {     // packed FMA (FFMA2) only
+      unsigned long long* p = reinterpret_cast<unsigned long long*>(x);
+#pragma unroll
+      for (int i = 0; i < U / 2; ++i) p[i] = fma2(p[i], 0x3f8003473f800347ull, 0x3f0000003f000000ull);
+    } else if (MODE == 9) {     // 3-input max only
+#pragma unroll
+      for (int i = 0; i < U / 2; ++i) x[2 * i] = max3(x[2 * i], x[2 * i + 1], seed);
+    } else if (MODE == 10) {    // mix of MODE 4 with the row sum on packed adds (1 FADD2 per pair)
+      unsigned long long* p = reinterpret_cast<unsigned long long*>(x);
+#pragma unroll
+      for (int i = 0; i < U / 2; ++i) {
+        const float a = ex2(fma_(x[2 * i], 1.0001f, -0.5f)), b = ex2(fma_(x[2 * i + 1], 1.0001f, -0.5f));
+        unsigned long long ab = (static_cast<unsigned long long>(__float_as_uint(b)) << 32) | __float_as_uint(a);
+        p[i] = fma2(ab, 0x3f8000003f800000ull, p[i]);
+        w[i] ^= pack(a, b);
+      }
+    }
+  }
+  const long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < U; ++i) s += x[i];
+#pragma unroll
+  for (int i = 0; i < U / 2; ++i) s += __uint_as_float(w[i]);
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (s == 12345.678f) sink[0] = s;
+}
+
+template <int MODE>
+static void run(const char* name, int ops_per_iter_per_thread) {
+  long long* cyc; float* sink;
+  cudaMalloc(&cyc, 148 * sizeof(long long)); cudaMalloc(&sink, 4);
+  const int iters = 4096;
+  for (int threads : {128, 256, 512}) {
+    rate_kernel<MODE><<<148, threads>>>(iters, 0.25f, cyc, sink);   // warm-up
+    rate_kernel<MODE><<<148, threads>>>(iters, 0.25f, cyc, sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
+    long long h[148]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double mean = 0; for (int i = 0; i < 148; ++i) mean += h[i]; mean /= 148;
+    const double warps_per_smsp = threads / 128.0;
+    const double winstr = static_cast<double>(iters) * ops_per_iter_per_thread * warps_per_smsp;
+    printf("%-46s warps/SMSP %.0f: %8.0f cycles, %.2f cycles per warp instruction per SMSP (%.1f thread-ops/clk/SM)\n", name,
+           warps_per_smsp, mean, mean / winstr, 4.0 * 32.0 * winstr / mean);
+  }
+  cudaFree(cyc); cudaFree(sink);
+}
+
+int main() {
+  run<0>("MUFU.EX2", U);
+  run<1>("F2FP pack (cvt.rn.bf16x2.f32)", U / 2);
+  run<2>("2 EX2 + 1 F2FP", U + U / 2);
+  run<3>("FFMA", U);
+  run<8>("FFMA2 (fma.rn.f32x2)", U / 2);
+  run<9>("FMNMX3", U / 2);
+  run<7>("MUFU.EX2 bf16x2", U / 2);
+  run<4>("mix: 2 FFMA + 2 EX2 + 2 FADD + 1 F2FP", 7 * U / 2);
+  run<10>("mix: 2 FFMA + 2 EX2 + 1 FADD2 + 1 F2FP", 6 * U / 2);
+  run<5>("mix, bf16 rounding on FMA pipe + PRMT", 13 * U / 2);
+  run<6>("mix, truncating PRMT pack", 7 * U / 2);
+  return 0;
+}
