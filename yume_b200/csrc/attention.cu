@@ -135,7 +135,7 @@ struct AttCfg {
 // MUFU.EX2 warp instruction (700 cycles per 64, trace in profiles/r02_experimental_runbook.md), i.e. 2 x 128 x 11 = 2816 of the 3011
 // cycles of a KV iteration are MUFU time. The kernel is MUFU-bound, not latency-bound; the ping-pong of this schedule already
 // keeps the MUFU ~93 % busy, and only cheaper exponentials can move it.
-template <bool P_TMEM, int EMU>
+template <bool P_TMEM, int SMV>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttParams p) {
@@ -357,7 +357,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tmem_ld32(tS + 96, s[3]);
       tmem_ld_wait();
       if (tr) tr[2] = clock64();
-      // 8 independent running maxima (a single fmaxf chain is 128 dependent ops of 4-cycle latency each)
+      // 8 independent running maxima (a single fmaxf chain is 128 dependent ops of 4-cycle latency each); ptxas pairs them into
+      // 64 FMNMX3
       float mxa[8];
 #pragma unroll
       for (int a = 0; a < 8; ++a) mxa[a] = -INFINITY;
@@ -393,37 +394,46 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           m_used = m_new;
         }
       }
-      // probabilities on packed fp32 pairs: one FFMA2 scales+shifts two scores, one FADD2 accumulates two sums;
-      // every EMU-th pair takes the FMA-pipe polynomial instead of two MUFU.EX2
+      // probabilities. SMV bit 0 clear: packed fp32 pairs (one FFMA2 scales+shifts two scores, one FADD2 accumulates two sums);
+      // set: scalar FFMA / FADD — profiles/r02_instr_rate.md: for ONE warp per scheduler the packed forms cost 19.9 cycles per
+      // pair of exponentials against 17.5 for the scalar mix (the MUFU alone needs 16)
       const uint64_t sc2 = f2_pack(sc, sc);
       const uint64_t negm2 = f2_pack(-m_used, -m_used);
+      const float negm = -m_used;
       uint64_t ls2[2] = {0ull, 0ull};  // two independent packed partial row sums (0ull == (+0.f, +0.f))
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t pk[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int c0 = h * 64 + 2 * i;
-          const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[c0 >> 5][c0 & 31]),
-                                             __uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31])), sc2, negm2);
-          uint64_t p2;
           float p0, p1;
-          if ((EMU > 0) && (i % (EMU > 0 ? EMU : 1) == EMU - 1)) {
-            p2 = exp2_poly2(x2);
-            f2_unpack(p2, p0, p1);
+          if (P_TMEM && (SMV & 2) && h == 1 && i == 8) {
+            // SMV bit 1: the TMEM store of P half 0 completes under the first exponentials of half 1 instead of stalling the warp
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_half[2 * X]);
+          }
+          if (SMV & 1) {
+            p0 = fast_exp2(fmaf(__uint_as_float(s[c0 >> 5][c0 & 31]), sc, negm));
+            p1 = fast_exp2(fmaf(__uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31]), sc, negm));
+            ls[(2 * i) & 3] += p0;
+            ls[(2 * i + 1) & 3] += p1;
           } else {
+            const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[c0 >> 5][c0 & 31]),
+                                               __uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31])), sc2, negm2);
             float x0, x1;
             f2_unpack(x2, x0, x1);
             p0 = fast_exp2(x0);
             p1 = fast_exp2(x1);
-            p2 = f2_pack(p0, p1);
+            ls2[i & 1] = f2_add(ls2[i & 1], f2_pack(p0, p1));
           }
-          ls2[i & 1] = f2_add(ls2[i & 1], p2);
           pk[i] = pack_bf16x2(p0, p1);
         }
         if (P_TMEM) {
           tmem_st32(tS + h * 32, pk);
-          tmem_st_wait();
+          if (!(SMV & 2) || h == 1) tmem_st_wait();
         } else {
           // K-major 128B-swizzled slab h of the P tile: row r, 16-byte chunk c -> r*128 + ((c ^ (r & 7)) << 4)
           uint8_t* slab = smem + Cfg::P_OFF + X * ATT_TILE_BYTES + h * 16384 + row_in_tile * 128;
@@ -435,10 +445,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           fence_proxy_async_smem();
         }
         if (tr) tr[4 + h] = clock64();
-        tc_fence_before();
-        mbar_arrive(&p_half[2 * X + h]);
+        if (!(P_TMEM && (SMV & 2)) || h == 1) {
+          tc_fence_before();
+          mbar_arrive(&p_half[2 * X + h]);
+        }
       }
-      {
+      if (SMV & 1) {
+        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      } else {
         float a0, a1, b0, b1;
         f2_unpack(ls2[0], a0, a1);
         f2_unpack(ls2[1], b0, b1);
@@ -528,11 +542,11 @@ static size_t split_workspace_bytes(size_t ctas) { return ctas * 256 * 130 * siz
 static int g_debug_force_split = 0;   // yb_debug_force_split: tests force the KV split through paths that carry no flags
 
 // force_ns: 0 = automatic tail split, 1 = never, 2..4 = split EVERY unit into that many KV segments (tests)
-template <bool P_TMEM, int EMU>
+template <bool P_TMEM, int SMV>
 static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                             AttParams p, int heads, cudaStream_t stream, int force_ns, void* ws, long long ws_bytes) {
   using Cfg = AttCfg<P_TMEM>;
-  auto kern = attention_kernel<P_TMEM, EMU>;
+  auto kern = attention_kernel<P_TMEM, SMV>;
   static bool attr_set[kMaxDevices] = {false};
   if (int rc = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_set, "attention")) return rc;
   if (force_ns == 0 && g_debug_force_split >= 1 && g_debug_force_split <= 4) force_ns = g_debug_force_split;
@@ -575,10 +589,10 @@ static int dispatch_attention(const void* q, long long ldq, const void* k, long 
   rc = make_tmap_bf16_2d(&tmV, v, p.Lk, cols, ldv, 128, 64);
   if (rc) return rc;
   if (flags & YB_ATT_P_SMEM) return launch_attention<false, 0>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-  switch (emu) {
-    case 1: return launch_attention<true, 4>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-    case 2: return launch_attention<true, 3>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-    case 3: return launch_attention<true, 2>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+  switch (emu) {   // experiment selector: bit 0 scalar exponent math, bit 1 P half 0's TMEM store completes under half 1's exponentials
+    case 1: return launch_attention<true, 1>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+    case 2: return launch_attention<true, 2>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+    case 3: return launch_attention<true, 3>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
     default: return launch_attention<true, 0>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
   }
 }
