@@ -262,7 +262,7 @@ def sec_attmodes():
         idx = torch.randint(0, L, (256,), device=dev)
         ref = sdpa_ref(q[idx].contiguous(), k, v, heads)
         fl = 4.0 * L * L * heads * 128
-        for emu in (0, 1, 2, 3):
+        for emu in range(8):
             ms = min(timeit(lambda: ops.attention(q, k, v, out, heads, emu=emu), n=5) for _ in range(3))
             print(f"attmodes heads={heads} L={L} emu={emu}: {ms:.3f} ms = {fl/ms/1e9:.0f} TF/s   rel/max {rel(out[idx], ref)}", flush=True)
     try:
@@ -328,15 +328,15 @@ def sec_atttrace():
     out = torch.empty(L, heads * 128, device=dev, dtype=torch.bfloat16)
     tr = torch.zeros(32 * 32, device=dev, dtype=torch.int64)
     lib = _lib.load()
-    for emu in (0, 1, 2, 3):
-        print(f"--- softmax variant (flags EMU field) {emu}")
+    for emu in (0, 1, 4, 5, 7):
+        print(f"--- softmax variant (bit 0 scalar math, bit 1 deferred P store wait, bit 2 split S issue) {emu}")
         _trace_one(lib, q, k, v, out, tr, L, heads, emu)
 
 
 def _trace_one(lib, q, k, v, out, tr, L, heads, emu):
     for _ in range(3):
         rc = lib.yb_attention_ex(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(),
-                                 out.stride(0), L, L, heads, 1.0 / math.sqrt(128.0), emu << 2, None, 0, tr.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                                 out.stride(0), L, L, heads, 1.0 / math.sqrt(128.0), ((emu & 3) << 2) | (128 if emu & 4 else 0), None, 0, tr.data_ptr(), torch.cuda.current_stream().cuda_stream)
         assert rc == 0
     torch.cuda.synchronize()
     t = tr.view(32, 32).cpu()

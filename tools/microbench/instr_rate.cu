@@ -98,6 +98,78 @@ __global__ void __launch_bounds__(512, 1) rate_kernel(int iters, float seed, lon
   if (s == 12345.678f) sink[0] = s;
 }
 
+
+// ---- does a warp parked on an mbarrier slow down a computing warp on the same scheduler? (attention kernel: while query tile A
+// runs its exponentials, tile B's softmax warp waits for its S on the same SM sub-partition)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+template <int WAITER>   // 0 = partner warps exit, 1 = try_wait loop, 2 = try_wait with a 1 ms suspend hint, 3 = test_wait + nanosleep(256)
+__global__ void __launch_bounds__(256, 1) parked_kernel(int iters, float seed, long long* cycles, float* sink) {
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(128));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x >= 128) {
+    if (WAITER == 0) return;
+    uint32_t ok = 0;
+    while (!ok) {
+      if (WAITER == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0) : "memory");
+      else if (WAITER == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0), "r"(1000000) : "memory");
+      else {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0) : "memory");
+        if (!ok) __nanosleep(256);
+      }
+    }
+    return;
+  }
+  float x[U];
+  uint32_t w[U / 2];
+#pragma unroll
+  for (int i = 0; i < U; ++i) x[i] = seed + 0.001f * (threadIdx.x + i);
+#pragma unroll
+  for (int i = 0; i < U / 2; ++i) w[i] = threadIdx.x + i;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < U / 2; ++i) {
+      const float a = ex2(fma_(x[2 * i], 1.0001f, -0.5f)), b = ex2(fma_(x[2 * i + 1], 1.0001f, -0.5f));
+      x[2 * i] = add_(x[2 * i], a); x[2 * i + 1] = add_(x[2 * i + 1], b);
+      w[i] ^= pack(a, b);
+    }
+  }
+  const long long t1 = clock64();
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar)) : "memory");
+  float sacc = 0.f;
+#pragma unroll
+  for (int i = 0; i < U; ++i) sacc += x[i];
+#pragma unroll
+  for (int i = 0; i < U / 2; ++i) sacc += __uint_as_float(w[i]);
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (sacc == 12345.678f) sink[0] = sacc;
+}
+
+template <int WAITER>
+static void run_parked(const char* name) {
+  long long* cyc; float* sink;
+  cudaMalloc(&cyc, 148 * sizeof(long long)); cudaMalloc(&sink, 4);
+  const int iters = 4096;
+  parked_kernel<WAITER><<<148, 256>>>(iters, 0.25f, cyc, sink);
+  parked_kernel<WAITER><<<148, 256>>>(iters, 0.25f, cyc, sink);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
+  long long h[148]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+  double mean = 0; for (int i = 0; i < 148; ++i) mean += h[i]; mean /= 148;
+  printf("mix on 1 warp/SMSP, partner warp: %-44s %8.0f cycles, %.2f cycles per pair of exponentials\n", name, mean,
+         mean / (static_cast<double>(iters) * U / 2));
+  cudaFree(cyc); cudaFree(sink);
+}
+
 template <int MODE>
 static void run(const char* name, int ops_per_iter_per_thread) {
   long long* cyc; float* sink;
@@ -130,5 +202,9 @@ int main() {
   run<10>("mix: 2 FFMA + 2 EX2 + 1 FADD2 + 1 F2FP", 6 * U / 2);
   run<5>("mix, bf16 rounding on FMA pipe + PRMT", 13 * U / 2);
   run<6>("mix, truncating PRMT pack", 7 * U / 2);
+  run_parked<0>("none (exits)");
+  run_parked<1>("mbarrier.try_wait loop");
+  run_parked<2>("mbarrier.try_wait, 1 ms suspend hint");
+  run_parked<3>("mbarrier.test_wait + nanosleep(256)");
   return 0;
 }

@@ -248,6 +248,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           umma_ss(tmem_base + X * 128, qd + off16, kd + off16, idesc_s, kk != 0 ? 1u : 0u);
         }
       };
+      // SMV bit 2: S(j+1) in two key halves. P(j) lives in packed columns [0, 64) of the tile's 128 S columns, so columns [64, 128)
+      // are free as soon as the softmax has S(j) in registers — which P half 0's arrival implies. Keys 64..127 of tile j+1 are
+      // issued BEFORE P.V(j) (they run under the second half of the exponentials), only keys 0..63 behind it: the chain from the
+      // last exponential to the next S shrinks by half a QK^T.
+      constexpr uint32_t idesc_s64 = make_idesc_bf16(128, 64, 0, 0);
+      auto issue_S_half = [&](int X, uint32_t kbase, int nh) {
+        const uint64_t kd = kdesc0 + ((kbase + nh * 8192) >> 4);   // key rows 64*nh .. of both 64-dim slabs (128 B per row)
+        uint64_t qd = qdesc0 + X * kTileStep;
+        asm volatile("" : "+l"(qd));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off16 = ((kk >> 2) * 16384 + (kk & 3) * 32) >> 4;
+          umma_ss(tmem_base + X * 128 + nh * 64, qd + off16, kd + off16, idesc_s64, kk != 0 ? 1u : 0u);
+        }
+      };
       auto issue_PV = [&](int X, uint32_t vbase, bool acc, int half) {
         const uint64_t vd = vdesc0 + (vbase >> 4);
 #pragma unroll
@@ -292,12 +307,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mbar_wait(&p_half[2 * X], j & 1);
           if (tr) tr[1] = clock64();
           tc_fence_after();
+          if ((SMV & 4) && has_next) issue_S_half(X, kbase, 1);
           issue_PV(X, vbase, j > 0, 0);             // keys 0..63 of the tile, while the softmax warps finish 64..127
           mbar_wait(&p_half[2 * X + 1], j & 1);
           tc_fence_after();
           issue_PV(X, vbase, true, 1);
           if (has_next) {
-            issue_S(X, kbase);
+            if (SMV & 4) issue_S_half(X, kbase, 0); else issue_S(X, kbase);
             umma_commit(&s_full[X]);
           } else {
             umma_commit(&o_done[X]);
@@ -589,10 +605,16 @@ static int dispatch_attention(const void* q, long long ldq, const void* k, long 
   rc = make_tmap_bf16_2d(&tmV, v, p.Lk, cols, ldv, 128, 64);
   if (rc) return rc;
   if (flags & YB_ATT_P_SMEM) return launch_attention<false, 0>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-  switch (emu) {   // experiment selector: bit 0 scalar exponent math, bit 1 P half 0's TMEM store completes under half 1's exponentials
+  // experiment selector: bit 0 scalar exponent math, bit 1 P half 0's TMEM store completes under half 1's exponentials,
+  // bit 2 (flags bit 7) S(j+1) issued in two key halves around P.V(j)
+  switch (emu | ((flags & 128) ? 4 : 0)) {
     case 1: return launch_attention<true, 1>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
     case 2: return launch_attention<true, 2>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
     case 3: return launch_attention<true, 3>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+    case 4: return launch_attention<true, 4>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+    case 5: return launch_attention<true, 5>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+    case 6: return launch_attention<true, 6>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+    case 7: return launch_attention<true, 7>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
     default: return launch_attention<true, 0>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
   }
 }

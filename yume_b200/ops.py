@@ -208,7 +208,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
         raise YumeB200Error("attention supports head_dim 128 only")
     if scale is None:
         scale = 1.0 / math.sqrt(128.0)
-    flags = (YB_ATT_P_SMEM if variant == 1 else 0) | (YB_ATT_ACCUMULATE if accumulate else 0) | ((emu & 3) << 2) | ((split & 7) << 4)
+    flags = (YB_ATT_P_SMEM if variant == 1 else 0) | (YB_ATT_ACCUMULATE if accumulate else 0) | ((emu & 3) << 2) | ((split & 7) << 4) | (128 if (emu & 4) else 0)
     if variant not in (0, 1):
         raise YumeB200Error("attention variant must be 0 or 1")
     ws, ws_bytes = _attention_ws(Lq, Lk, heads, flags, q.device)
