@@ -170,6 +170,120 @@ static void run_parked(const char* name) {
   cudaFree(cyc); cudaFree(sink);
 }
 
+
+// ---- the attention kernel's softmax body on registers only (no TMEM, no barriers): 128 scores per thread, row max, then the two
+// 64-column halves of exponentials + row sums + bf16 packs exactly as attention.cu writes them. One warp per scheduler.
+// VARIANT 0: packed FFMA2/FADD2 (the product kernel); 1: scalar FFMA/FADD; 2: scalar, software-pipelined by hand — the MUFU
+// stream of the whole tile is issued in program order (volatile asm) and the FADD / F2FP of pair i - DIST ride in its shadow
+__device__ __forceinline__ unsigned long long f2pack(float lo, float hi) {
+  return (static_cast<unsigned long long>(__float_as_uint(hi)) << 32) | __float_as_uint(lo);
+}
+__device__ __forceinline__ unsigned long long f2add(unsigned long long a, unsigned long long b) {
+  unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ unsigned long long f2fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+template <int VARIANT>
+__global__ void __launch_bounds__(128, 3) softmax_body_kernel(int iters, const float* __restrict__ in, long long* cycles, float* sink) {
+  __shared__ uint4 stage[128][9];
+  float s[128];
+#pragma unroll
+  for (int i = 0; i < 128; ++i) s[i] = in[(threadIdx.x * 131 + i * 7) & 4095];
+  const float sc = 0.1275f;
+  float m_used = -1e30f, l = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    float mxa[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) mxa[a] = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 128; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], s[i]);
+    const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+    m_used = fmaxf(m_used, mx * sc) + 1e-3f * it;      // varies per iteration: nothing below is loop-invariant
+    const float negm = -m_used;
+    auto store_half = [&](const uint32_t (&pk)[32], int h) {   // stands in for one TMEM store of P: 4 x 16-byte smem stores
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        stage[threadIdx.x][h * 4 + c] = make_uint4(pk[8 * c] ^ pk[8 * c + 4], pk[8 * c + 1] ^ pk[8 * c + 5], pk[8 * c + 2] ^ pk[8 * c + 6], pk[8 * c + 3] ^ pk[8 * c + 7]);
+    };
+    if (VARIANT == 0) {
+      const unsigned long long sc2 = f2pack(sc, sc), negm2 = f2pack(negm, negm);
+      unsigned long long ls2[2] = {0ull, 0ull};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c0 = h * 64 + 2 * i;
+          const unsigned long long x2 = fma2(f2pack(s[c0], s[c0 + 1]), sc2, negm2);
+          const float p0 = ex2(__uint_as_float(static_cast<uint32_t>(x2))), p1 = ex2(__uint_as_float(static_cast<uint32_t>(x2 >> 32)));
+          ls2[i & 1] = f2add(ls2[i & 1], f2pack(p0, p1));
+          pk[i] = pack(p0, p1);
+        }
+        store_half(pk, h);
+      }
+      l += (__uint_as_float(static_cast<uint32_t>(ls2[0])) + __uint_as_float(static_cast<uint32_t>(ls2[0] >> 32))) +
+           (__uint_as_float(static_cast<uint32_t>(ls2[1])) + __uint_as_float(static_cast<uint32_t>(ls2[1] >> 32)));
+    } else if (VARIANT == 1) {
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c0 = h * 64 + 2 * i;
+          const float p0 = ex2(fma_(s[c0], sc, negm)), p1 = ex2(fma_(s[c0 + 1], sc, negm));
+          ls[(2 * i) & 3] += p0; ls[(2 * i + 1) & 3] += p1;
+          pk[i] = pack(p0, p1);
+        }
+        store_half(pk, h);
+      }
+      l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+    } else {
+      constexpr int DIST = 6;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      float pv[128];
+      uint32_t pk0[32], pk1[32];
+#pragma unroll
+      for (int i = 0; i < 64 + DIST; ++i) {
+        if (i < 64) { pv[2 * i] = ex2(fma_(s[2 * i], sc, negm)); pv[2 * i + 1] = ex2(fma_(s[2 * i + 1], sc, negm)); }
+        if (i >= DIST) {
+          const int k = i - DIST;
+          ls[(2 * k) & 3] = add_(ls[(2 * k) & 3], pv[2 * k]);
+          ls[(2 * k + 1) & 3] = add_(ls[(2 * k + 1) & 3], pv[2 * k + 1]);
+          if (k < 32) pk0[k] = pack(pv[2 * k], pv[2 * k + 1]); else pk1[k - 32] = pack(pv[2 * k], pv[2 * k + 1]);
+          if (k == 31) store_half(pk0, 0);
+          if (k == 63) store_half(pk1, 1);
+        }
+      }
+      l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+    }
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (l == 12345.678f) sink[0] = l + stage[threadIdx.x][3].x;
+}
+
+template <int VARIANT>
+static void run_body(const char* name) {
+  long long* cyc; float* sink; float* in;
+  cudaMalloc(&cyc, 148 * sizeof(long long)); cudaMalloc(&sink, 4); cudaMalloc(&in, 4096 * 4);
+  float h_in[4096];
+  for (int i = 0; i < 4096; ++i) h_in[i] = static_cast<float>((i * 2654435761u) % 2001) / 100.0f - 10.0f;
+  cudaMemcpy(in, h_in, sizeof(h_in), cudaMemcpyHostToDevice);
+  const int iters = 2048;
+  softmax_body_kernel<VARIANT><<<148, 128>>>(iters, in, cyc, sink);
+  softmax_body_kernel<VARIANT><<<148, 128>>>(iters, in, cyc, sink);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
+  long long h[148]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+  double mean = 0; for (int i = 0; i < 148; ++i) mean += h[i]; mean /= 148;
+  printf("softmax body (128 scores/thread, 1 warp/SMSP), %-40s %7.0f cycles per tile (ideal MUFU time 1024)\n", name, mean / iters);
+  cudaFree(cyc); cudaFree(sink); cudaFree(in);
+}
+
 template <int MODE>
 static void run(const char* name, int ops_per_iter_per_thread) {
   long long* cyc; float* sink;
@@ -202,6 +316,9 @@ int main() {
   run<10>("mix: 2 FFMA + 2 EX2 + 1 FADD2 + 1 F2FP", 6 * U / 2);
   run<5>("mix, bf16 rounding on FMA pipe + PRMT", 13 * U / 2);
   run<6>("mix, truncating PRMT pack", 7 * U / 2);
+  run_body<0>("packed FFMA2 / FADD2 (product kernel)");
+  run_body<1>("scalar FFMA / FADD");
+  run_body<2>("scalar, hand-pipelined (distance 6 pairs)");
   run_parked<0>("none (exits)");
   run_parked<1>("mbarrier.try_wait loop");
   run_parked<2>("mbarrier.try_wait, 1 ms suspend hint");

@@ -248,21 +248,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           umma_ss(tmem_base + X * 128, qd + off16, kd + off16, idesc_s, kk != 0 ? 1u : 0u);
         }
       };
-      // SMV bit 2: S(j+1) in two key halves. P(j) lives in packed columns [0, 64) of the tile's 128 S columns, so columns [64, 128)
-      // are free as soon as the softmax has S(j) in registers — which P half 0's arrival implies. Keys 64..127 of tile j+1 are
-      // issued BEFORE P.V(j) (they run under the second half of the exponentials), only keys 0..63 behind it: the chain from the
-      // last exponential to the next S shrinks by half a QK^T.
-      constexpr uint32_t idesc_s64 = make_idesc_bf16(128, 64, 0, 0);
-      auto issue_S_half = [&](int X, uint32_t kbase, int nh) {
-        const uint64_t kd = kdesc0 + ((kbase + nh * 8192) >> 4);   // key rows 64*nh .. of both 64-dim slabs (128 B per row)
-        uint64_t qd = qdesc0 + X * kTileStep;
-        asm volatile("" : "+l"(qd));
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t off16 = ((kk >> 2) * 16384 + (kk & 3) * 32) >> 4;
-          umma_ss(tmem_base + X * 128 + nh * 64, qd + off16, kd + off16, idesc_s64, kk != 0 ? 1u : 0u);
-        }
-      };
       auto issue_PV = [&](int X, uint32_t vbase, bool acc, int half) {
         const uint64_t vd = vdesc0 + (vbase >> 4);
 #pragma unroll
@@ -307,13 +292,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mbar_wait(&p_half[2 * X], j & 1);
           if (tr) tr[1] = clock64();
           tc_fence_after();
-          if ((SMV & 4) && has_next) issue_S_half(X, kbase, 1);
           issue_PV(X, vbase, j > 0, 0);             // keys 0..63 of the tile, while the softmax warps finish 64..127
           mbar_wait(&p_half[2 * X + 1], j & 1);
           tc_fence_after();
           issue_PV(X, vbase, true, 1);
           if (has_next) {
-            if (SMV & 4) issue_S_half(X, kbase, 0); else issue_S(X, kbase);
+            issue_S(X, kbase);
             umma_commit(&s_full[X]);
           } else {
             umma_commit(&o_done[X]);
@@ -410,46 +394,67 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           m_used = m_new;
         }
       }
-      // probabilities. SMV bit 0 clear: packed fp32 pairs (one FFMA2 scales+shifts two scores, one FADD2 accumulates two sums);
-      // set: scalar FFMA / FADD — profiles/r02_instr_rate.md: for ONE warp per scheduler the packed forms cost 19.9 cycles per
-      // pair of exponentials against 17.5 for the scalar mix (the MUFU alone needs 16)
+      if (P_TMEM && SMV >= 1) {
+        // EXPERIMENT (SMV = pair distance): hand-ordered exponential stream. Every instruction of the loop is a volatile asm, so
+        // ptxas keeps this order: the MUFU.EX2 of pair i is followed by the row-sum FADDs and the bf16 pack of pair i - SMV, whose
+        // results left the MUFU SMV pairs (16 * SMV cycles of issue) earlier — far enough for the MUFU latency, near enough for
+        // the six scoreboards. One continuous MUFU stream over both halves; P half 0 is published when its 32 packs are done.
+        constexpr int DIST = SMV;
+        const float negm = -m_used;
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk0[32], pk1[32];
+#pragma unroll
+        for (int i = 0; i < 64 + DIST; ++i) {
+          if (i < 64) {
+            const int c0 = 2 * i, c1 = 2 * i + 1;
+            s[c0 >> 5][c0 & 31] = __float_as_uint(fast_exp2(fma_ordered(__uint_as_float(s[c0 >> 5][c0 & 31]), sc, negm)));
+            s[c1 >> 5][c1 & 31] = __float_as_uint(fast_exp2(fma_ordered(__uint_as_float(s[c1 >> 5][c1 & 31]), sc, negm)));
+          }
+          if (i >= DIST) {
+            const int k = i - DIST, c0 = 2 * k, c1 = 2 * k + 1;
+            const float p0 = __uint_as_float(s[c0 >> 5][c0 & 31]), p1 = __uint_as_float(s[c1 >> 5][c1 & 31]);
+            ls[c0 & 3] = add_ordered(ls[c0 & 3], p0);
+            ls[c1 & 3] = add_ordered(ls[c1 & 3], p1);
+            if (k < 32) pk0[k] = pack_bf16x2_ordered(p0, p1); else pk1[k - 32] = pack_bf16x2_ordered(p0, p1);
+            if (k == 31) {
+              tmem_st32(tS, pk0);
+              tmem_st_wait();
+              if (tr) tr[4] = clock64();
+              tc_fence_before();
+              mbar_arrive(&p_half[2 * X]);
+            }
+            if (k == 63) {
+              tmem_st32(tS + 32, pk1);
+              tmem_st_wait();
+              if (tr) tr[5] = clock64();
+              tc_fence_before();
+              mbar_arrive(&p_half[2 * X + 1]);
+            }
+          }
+        }
+        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      } else {
+      // probabilities on packed fp32 pairs: one FFMA2 scales+shifts two scores, one FADD2 accumulates two sums
       const uint64_t sc2 = f2_pack(sc, sc);
       const uint64_t negm2 = f2_pack(-m_used, -m_used);
-      const float negm = -m_used;
       uint64_t ls2[2] = {0ull, 0ull};  // two independent packed partial row sums (0ull == (+0.f, +0.f))
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t pk[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int c0 = h * 64 + 2 * i;
-          float p0, p1;
-          if (P_TMEM && (SMV & 2) && h == 1 && i == 8) {
-            // SMV bit 1: the TMEM store of P half 0 completes under the first exponentials of half 1 instead of stalling the warp
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&p_half[2 * X]);
-          }
-          if (SMV & 1) {
-            p0 = fast_exp2(fmaf(__uint_as_float(s[c0 >> 5][c0 & 31]), sc, negm));
-            p1 = fast_exp2(fmaf(__uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31]), sc, negm));
-            ls[(2 * i) & 3] += p0;
-            ls[(2 * i + 1) & 3] += p1;
-          } else {
-            const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[c0 >> 5][c0 & 31]),
-                                               __uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31])), sc2, negm2);
-            float x0, x1;
-            f2_unpack(x2, x0, x1);
-            p0 = fast_exp2(x0);
-            p1 = fast_exp2(x1);
-            ls2[i & 1] = f2_add(ls2[i & 1], f2_pack(p0, p1));
-          }
+          const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[c0 >> 5][c0 & 31]),
+                                             __uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31])), sc2, negm2);
+          float x0, x1;
+          f2_unpack(x2, x0, x1);
+          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+          ls2[i & 1] = f2_add(ls2[i & 1], f2_pack(p0, p1));
           pk[i] = pack_bf16x2(p0, p1);
         }
         if (P_TMEM) {
           tmem_st32(tS + h * 32, pk);
-          if (!(SMV & 2) || h == 1) tmem_st_wait();
+          tmem_st_wait();
         } else {
           // K-major 128B-swizzled slab h of the P tile: row r, 16-byte chunk c -> r*128 + ((c ^ (r & 7)) << 4)
           uint8_t* slab = smem + Cfg::P_OFF + X * ATT_TILE_BYTES + h * 16384 + row_in_tile * 128;
@@ -461,18 +466,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           fence_proxy_async_smem();
         }
         if (tr) tr[4 + h] = clock64();
-        if (!(P_TMEM && (SMV & 2)) || h == 1) {
-          tc_fence_before();
-          mbar_arrive(&p_half[2 * X + h]);
-        }
+        tc_fence_before();
+        mbar_arrive(&p_half[2 * X + h]);
       }
-      if (SMV & 1) {
-        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      } else {
+      {
         float a0, a1, b0, b1;
         f2_unpack(ls2[0], a0, a1);
         f2_unpack(ls2[1], b0, b1);
         l += (a0 + a1) + (b0 + b1);
+      }
       }
     }
 
@@ -605,16 +607,14 @@ static int dispatch_attention(const void* q, long long ldq, const void* k, long 
   rc = make_tmap_bf16_2d(&tmV, v, p.Lk, cols, ldv, 128, 64);
   if (rc) return rc;
   if (flags & YB_ATT_P_SMEM) return launch_attention<false, 0>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-  // experiment selector: bit 0 scalar exponent math, bit 1 P half 0's TMEM store completes under half 1's exponentials,
-  // bit 2 (flags bit 7) S(j+1) issued in two key halves around P.V(j)
+  // experiment selector (flags EMU field, + 4 with flags bit 7): 0 = product schedule, n = hand-ordered exponential stream with the
+  // consumers n pairs behind their MUFU
   switch (emu | ((flags & 128) ? 4 : 0)) {
     case 1: return launch_attention<true, 1>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
     case 2: return launch_attention<true, 2>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
     case 3: return launch_attention<true, 3>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
     case 4: return launch_attention<true, 4>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-    case 5: return launch_attention<true, 5>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-    case 6: return launch_attention<true, 6>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-    case 7: return launch_attention<true, 7>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+    case 5: return launch_attention<true, 6>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
     default: return launch_attention<true, 0>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
   }
 }

@@ -295,6 +295,23 @@ __device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
   return f2_pack(p0, p1);
 }
 
+// ordered (volatile) forms: ptxas keeps volatile asm statements in program order — used to hand-schedule the exponential stream
+__device__ __forceinline__ float fma_ordered(float a, float b, float c) {
+  float d;
+  asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float add_ordered(float a, float b) {
+  float d;
+  asm volatile("add.rn.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_ordered(float lo, float hi) {
+  uint32_t r;
+  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
