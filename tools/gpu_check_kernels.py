@@ -262,7 +262,8 @@ def sec_attmodes():
         idx = torch.randint(0, L, (256,), device=dev)
         ref = sdpa_ref(q[idx].contiguous(), k, v, heads)
         fl = 4.0 * L * L * heads * 128
-        for emu in range(8):
+        for emu in (0, 1):
+            out.zero_()
             ms = min(timeit(lambda: ops.attention(q, k, v, out, heads, emu=emu), n=5) for _ in range(3))
             print(f"attmodes heads={heads} L={L} emu={emu}: {ms:.3f} ms = {fl/ms/1e9:.0f} TF/s   rel/max {rel(out[idx], ref)}", flush=True)
     try:

@@ -51,14 +51,15 @@ struct AttParams {
 // Epilogue shared by the attention kernels: thread = query row (TMEM lane), tO = its O accumulator. A KV segment of a tail unit
 // leaves (unnormalised O, m, l) in the workspace for attention_combine_kernel; a whole unit stores O / l as bf16 into
 // out[Lq, heads*128] (accumulating, or into the owner rank's receive buffer under Ulysses).
+// c_begin..c_end: the 32-column chunks of the row this thread owns (0..4 when one thread owns the row; a half when two do).
 __device__ __forceinline__ void attention_epilogue(const AttParams& p, uint32_t tO, float m_used, float l, int X, int row_in_tile,
-                                                   int unit) {
+                                                   int unit, int c_begin = 0, int c_end = 4) {
   if (static_cast<int>(blockIdx.x) >= p.full_units) {
     const long long prow = static_cast<long long>(blockIdx.x - p.full_units) * 256 + X * 128 + row_in_tile;
     float* wo = p.ws_o + prow * 128;
-    *reinterpret_cast<float2*>(p.ws_ml + prow * 2) = make_float2(m_used, l);
+    if (c_begin == 0) *reinterpret_cast<float2*>(p.ws_ml + prow * 2) = make_float2(m_used, l);
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       uint32_t o[32];
       tmem_ld32(tO + c * 32, o);
       tmem_ld_wait();
@@ -80,7 +81,7 @@ __device__ __forceinline__ void attention_epilogue(const AttParams& p, uint32_t 
       orow = p.out_peers[owner] + (static_cast<long long>(p.sp_rank) * p.sp_Lp + t) * p.ldo + head * 128;
   }
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     uint32_t o[32];
     tmem_ld32(tO + c * 32, o);
     tmem_ld_wait();
@@ -120,7 +121,11 @@ struct AttCfg {
   static constexpr int KV_OFF = P_TMEM ? 2 * ATT_TILE_BYTES : 4 * ATT_TILE_BYTES;
   static constexpr int BAR_OFF = KV_OFF + NS * ATT_TILE_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256;
+  // two-threads-per-row variant: [X][column half][row] fp32 exchange of the row maxima (and, once, the row sums)
+  static constexpr int XCH_OFF = BAR_OFF + 256;
+  static constexpr int SMEM_BYTES_W16 = 232448;   // the 227 KB maximum; the kernel traps if its layout does not fit behind the alignment pad
 };
+constexpr int ATT_THREADS_W16 = 576;   // 18 warps, 112 registers each from launch (no setmaxnreg: 576 x 112 = 64512)
 
 // EMU: 0 = every exp2 on the MUFU; n > 0 = one of every n probability PAIRS is computed by exp2_poly2 on the FMA pipe
 // (the MUFU's 16 ex2/clk/SM is exactly co-saturated with the tensor pipe at head_dim 128, so part of the
@@ -135,8 +140,12 @@ struct AttCfg {
 // MUFU.EX2 warp instruction (700 cycles per 64, trace in profiles/r02_experimental_runbook.md), i.e. 2 x 128 x 11 = 2816 of the 3011
 // cycles of a KV iteration are MUFU time. The kernel is MUFU-bound, not latency-bound; the ping-pong of this schedule already
 // keeps the MUFU ~93 % busy, and only cheaper exponentials can move it.
-template <bool P_TMEM, int SMV>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+// W16: TWO threads per query row. Softmax warps 2..17: warp w serves query tile (w-2)/8, columns 64*(((w-2)/4)&1).. of its rows
+// (TMEM lane quad w%4), so the two warps that share a row also share a scheduler: their LDTM / max / MUFU / pack / STTM streams
+// interleave in hardware, which is what one in-order warp cannot do for itself (profiles/r02_instr_rate.md: ptxas schedules the
+// exponential stream at 8.1 cycles per MUFU, one warp alone runs it at 10.9 because every consumer waits on a scoreboard).
+template <bool P_TMEM, bool W16>
+__global__ void __launch_bounds__(W16 ? ATT_THREADS_W16 : ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttParams p) {
   using Cfg = AttCfg<P_TMEM>;
@@ -149,7 +158,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* s_full = kv_empty + NS;
   uint64_t* p_half = s_full + 2;  // [X][half]: P columns [64*half, 64*half+64) of query tile X are in place
   uint64_t* o_done = p_half + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* x_read = o_done + 2;    // W16: [X] both column halves have read each other's row maximum (256 arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(x_read + 2);
+  if (W16 && threadIdx.x == 0 && smem + Cfg::XCH_OFF + 2048 > smem_raw + Cfg::SMEM_BYTES_W16) __trap();
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -184,6 +195,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&p_half[2 * i], 128);
       mbar_init(&p_half[2 * i + 1], 128);
       mbar_init(&o_done[i], 1);
+      mbar_init(&x_read[i], 256);
     }
     fence_barrier_init();
   }
@@ -196,8 +208,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp < 4) {
-    setmaxnreg_dec<80>();
+  if (warp < (W16 ? 2 : 4)) {
+    if (!W16) setmaxnreg_dec<80>();
     if (warp == 0 && lane == 0) {
       // ------------------------------- TMA producer -------------------------------
       int unit, kv_begin, nkv;
@@ -310,6 +322,120 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else {
     // ------------------------------- softmax / correction / epilogue -------------------------------
+    if constexpr (W16) {
+      const int g = (warp - 2) >> 2;   // warps 2..17: every run of four consecutive warps covers the four TMEM lane quads
+      const int X = g >> 1, hc = g & 1;
+      const int quad = warp & 3;
+      const int row_in_tile = quad * 32 + lane;
+      const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+      const uint32_t tS = tmem_base + lane_off + X * 128;
+      const uint32_t tO = tmem_base + lane_off + 256 + X * 128;
+      float* xmine = reinterpret_cast<float*>(smem + Cfg::XCH_OFF) + (X * 2 + hc) * 128 + row_in_tile;
+      const float* xother = reinterpret_cast<const float*>(smem + Cfg::XCH_OFF) + (X * 2 + (hc ^ 1)) * 128 + row_in_tile;
+      const float sc = p.scale_log2;
+      float m_used = -INFINITY;
+      float l = 0.f;
+      int kv_begin, kv_end;
+      {
+        int unit, nkv;
+        decode(unit, kv_begin, nkv);
+        kv_end = kv_begin + nkv;
+      }
+      for (int j = kv_begin; j < kv_end; ++j) {
+        mbar_wait(&s_full[X], j & 1);
+        tc_fence_after();
+        const int kv_rem = p.Lk - j * 128;
+        if (kv_rem < 128) {   // last, partial KV tile: this thread's out-of-range columns of S become -inf in TMEM
+#pragma unroll 1                 // (cold; 16-column pieces keep its registers out of the hot loop's budget)
+          for (int c = 4 * hc; c < 4 * hc + 4; ++c) {
+            if (c * 16 + 16 <= kv_rem) continue;
+            uint32_t t[16];
+            tmem_ld16(tS + c * 16, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c * 16 + i >= kv_rem) t[i] = 0xff800000u;
+            tmem_st16(tS + c * 16, t);
+          }
+          tmem_st_wait();
+        }
+        uint32_t s[2][32];
+        tmem_ld32(tS + hc * 64, s[0]);
+        tmem_ld32(tS + hc * 64 + 32, s[1]);
+        tmem_ld_wait();
+        float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mxa[i & 3] = fmaxf(mxa[i & 3], __uint_as_float(s[c][i]));
+        const float mloc = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+        // row maximum = max over the two column halves: one fp32 through shared memory each way. The partner must have read the
+        // previous tile's value before it is overwritten (x_read, completed long ago in steady state), and see this one (bar).
+        if (j > kv_begin) mbar_wait(&x_read[X], (j - kv_begin - 1) & 1);
+        *xmine = mloc;
+        named_bar_sync(1 + X, 256);
+        const float ms = fmaxf(mloc, *xother) * sc;
+        mbar_arrive(&x_read[X]);
+        if (j == kv_begin) {
+          m_used = ms;
+        } else {
+          const bool need = ms > m_used + 8.0f;   // both halves of a row hold the same ms and m_used: same decision
+          if (__any_sync(0xffffffffu, need)) {
+            const float m_new = fmaxf(m_used, ms);
+            const float alpha = fast_exp2(m_used - m_new);
+            l *= alpha;
+#pragma unroll 1
+            for (int c = 4 * hc; c < 4 * hc + 4; ++c) {
+              uint32_t o[16];
+              tmem_ld16(tO + c * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(tO + c * 16, o);
+            }
+            tmem_st_wait();
+            m_used = m_new;
+          }
+        }
+        const uint64_t sc2 = f2_pack(sc, sc);
+        const uint64_t negm2 = f2_pack(-m_used, -m_used);
+        uint64_t ls2[2] = {0ull, 0ull};
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c0 = 2 * i;
+          const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[c0 >> 5][c0 & 31]), __uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31])),
+                                     sc2, negm2);
+          float x0, x1;
+          f2_unpack(x2, x0, x1);
+          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+          ls2[i & 1] = f2_add(ls2[i & 1], f2_pack(p0, p1));
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st32(tS + hc * 32, pk);   // packed P columns of key half hc
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_half[2 * X + hc]);
+        {
+          float a0, a1, b0, b1;
+          f2_unpack(ls2[0], a0, a1);
+          f2_unpack(ls2[1], b0, b1);
+          l += (a0 + a1) + (b0 + b1);
+        }
+      }
+      mbar_wait(&o_done[X], 0);
+      tc_fence_after();
+      // row sum = this half's + the partner's (same exchange slots; the last maximum has been read: x_read)
+      mbar_wait(&x_read[X], (kv_end - kv_begin - 1) & 1);
+      *xmine = l;
+      named_bar_sync(1 + X, 256);
+      l += *xother;
+      {
+        int unit, kvb, nk;
+        decode(unit, kvb, nk);
+        attention_epilogue(p, tO, m_used, l, X, row_in_tile, unit, 2 * hc, 2 * hc + 2);
+      }
+    } else {
     setmaxnreg_inc<208>();  // 128*80 + 256*208 = 63488 <= 384*168 (the CTA's register pool)
     const int X = (warp - 4) >> 2;
     const int quad = warp & 3;
@@ -394,46 +520,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           m_used = m_new;
         }
       }
-      if (P_TMEM && SMV >= 1) {
-        // EXPERIMENT (SMV = pair distance): hand-ordered exponential stream. Every instruction of the loop is a volatile asm, so
-        // ptxas keeps this order: the MUFU.EX2 of pair i is followed by the row-sum FADDs and the bf16 pack of pair i - SMV, whose
-        // results left the MUFU SMV pairs (16 * SMV cycles of issue) earlier — far enough for the MUFU latency, near enough for
-        // the six scoreboards. One continuous MUFU stream over both halves; P half 0 is published when its 32 packs are done.
-        constexpr int DIST = SMV;
-        const float negm = -m_used;
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t pk0[32], pk1[32];
-#pragma unroll
-        for (int i = 0; i < 64 + DIST; ++i) {
-          if (i < 64) {
-            const int c0 = 2 * i, c1 = 2 * i + 1;
-            s[c0 >> 5][c0 & 31] = __float_as_uint(fast_exp2(fma_ordered(__uint_as_float(s[c0 >> 5][c0 & 31]), sc, negm)));
-            s[c1 >> 5][c1 & 31] = __float_as_uint(fast_exp2(fma_ordered(__uint_as_float(s[c1 >> 5][c1 & 31]), sc, negm)));
-          }
-          if (i >= DIST) {
-            const int k = i - DIST, c0 = 2 * k, c1 = 2 * k + 1;
-            const float p0 = __uint_as_float(s[c0 >> 5][c0 & 31]), p1 = __uint_as_float(s[c1 >> 5][c1 & 31]);
-            ls[c0 & 3] = add_ordered(ls[c0 & 3], p0);
-            ls[c1 & 3] = add_ordered(ls[c1 & 3], p1);
-            if (k < 32) pk0[k] = pack_bf16x2_ordered(p0, p1); else pk1[k - 32] = pack_bf16x2_ordered(p0, p1);
-            if (k == 31) {
-              tmem_st32(tS, pk0);
-              tmem_st_wait();
-              if (tr) tr[4] = clock64();
-              tc_fence_before();
-              mbar_arrive(&p_half[2 * X]);
-            }
-            if (k == 63) {
-              tmem_st32(tS + 32, pk1);
-              tmem_st_wait();
-              if (tr) tr[5] = clock64();
-              tc_fence_before();
-              mbar_arrive(&p_half[2 * X + 1]);
-            }
-          }
-        }
-        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      } else {
       // probabilities on packed fp32 pairs: one FFMA2 scales+shifts two scores, one FADD2 accumulates two sums
       const uint64_t sc2 = f2_pack(sc, sc);
       const uint64_t negm2 = f2_pack(-m_used, -m_used);
@@ -475,7 +561,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         f2_unpack(ls2[1], b0, b1);
         l += (a0 + a1) + (b0 + b1);
       }
-      }
     }
 
     // epilogue: O / l -> bf16 -> global [Lq, heads*128] (or the KV-segment workspace / the owner rank's receive buffer)
@@ -486,6 +571,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       decode(unit, kvb, nk);
       attention_epilogue(p, tO, m_used, l, X, row_in_tile, unit);
     }
+    }   // !W16
   }
 
   tc_fence_before();
@@ -560,13 +646,15 @@ static size_t split_workspace_bytes(size_t ctas) { return ctas * 256 * 130 * siz
 static int g_debug_force_split = 0;   // yb_debug_force_split: tests force the KV split through paths that carry no flags
 
 // force_ns: 0 = automatic tail split, 1 = never, 2..4 = split EVERY unit into that many KV segments (tests)
-template <bool P_TMEM, int SMV>
+template <bool P_TMEM, bool W16>
 static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                             AttParams p, int heads, cudaStream_t stream, int force_ns, void* ws, long long ws_bytes) {
   using Cfg = AttCfg<P_TMEM>;
-  auto kern = attention_kernel<P_TMEM, SMV>;
+  auto kern = attention_kernel<P_TMEM, W16>;
+  constexpr int kSmem = W16 ? Cfg::SMEM_BYTES_W16 : Cfg::SMEM_BYTES;
+  constexpr int kThreads = W16 ? ATT_THREADS_W16 : ATT_THREADS;
   static bool attr_set[kMaxDevices] = {false};
-  if (int rc = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_set, "attention")) return rc;
+  if (int rc = ensure_dynamic_smem(kern, kSmem, attr_set, "attention")) return rc;
   if (force_ns == 0 && g_debug_force_split >= 1 && g_debug_force_split <= 4) force_ns = g_debug_force_split;
   p.nq = (p.Lq + 255) / 256;
   const int units = p.nq * heads;
@@ -585,7 +673,7 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, cons
       p.ws_ml = p.ws_o + ctas * 256 * 128;
     }
   }
-  kern<<<p.full_units + tail * p.ns, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  kern<<<p.full_units + tail * p.ns, kThreads, kSmem, stream>>>(tmQ, tmK, tmV, p);
   int rc = check_launch("attention");
   if (rc || tail == 0) return rc;
   attention_combine_kernel<<<tail * 32, 256, 0, stream>>>(p, tail);
@@ -606,17 +694,10 @@ static int dispatch_attention(const void* q, long long ldq, const void* k, long 
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmV, v, p.Lk, cols, ldv, 128, 64);
   if (rc) return rc;
-  if (flags & YB_ATT_P_SMEM) return launch_attention<false, 0>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-  // experiment selector (flags EMU field, + 4 with flags bit 7): 0 = product schedule, n = hand-ordered exponential stream with the
-  // consumers n pairs behind their MUFU
-  switch (emu | ((flags & 128) ? 4 : 0)) {
-    case 1: return launch_attention<true, 1>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-    case 2: return launch_attention<true, 2>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-    case 3: return launch_attention<true, 3>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-    case 4: return launch_attention<true, 4>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-    case 5: return launch_attention<true, 6>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-    default: return launch_attention<true, 0>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-  }
+  if (flags & YB_ATT_P_SMEM) return launch_attention<false, false>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+  // experiment selector (flags EMU field): 1 = two threads per query row (16 softmax warps)
+  if (emu == 1) return launch_attention<true, true>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+  return launch_attention<true, false>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
 }
 
 }  // namespace yb
