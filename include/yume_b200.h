@@ -173,8 +173,7 @@ int yb_attention_ex(const void* q, long long ldq, const void* k, long long ldk, 
                     long long ldo, int Lq, int Lk, int heads, float scale, int flags, void* ws, long long ws_bytes,
                     void* trace, void* stream);
 #define YB_ATT_P_SMEM 1     /* flags bit 0: stage P through shared memory instead of TMEM (debug variant) */
-#define YB_ATT_EMU_SHIFT 2  /* flags bits 2-3: fraction of exponentials evaluated on the FMA pipe instead of the MUFU:
-                               0 = none, 1 = 1/4, 2 = 1/3, 3 = 1/2 (tuning knob; results agree to < 2e-4 relative) */
+#define YB_ATT_EMU_SHIFT 2  /* flags bits 2-3: retired (FMA-pipe exponentials: measured slower in rounds 1 and 2, removed); must be 0 */
 #define YB_ATT_ACCUMULATE 2 /* flags bit 1: out += result (WanI2VCrossAttention sums the text and image branches,
                                wan/modules/model.py:380-387) */
 #define YB_ATT_SPLIT_SHIFT 4 /* flags bits 4-6: KV split policy. 0 = automatic (the units of a last wave that is at most

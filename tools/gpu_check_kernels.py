@@ -232,9 +232,8 @@ def sec_atttune():
     idx = torch.randint(0, L, (256,), device=dev)
     ref = sdpa_ref(q[idx].contiguous(), k, v, heads)
     fl = 4.0 * L * L * heads * 128
-    for emu in (0, 1, 2, 3):
-        ms = min(timeit(lambda: ops.attention(q, k, v, out, heads, emu=emu), n=5) for _ in range(3))
-        print(f"attention emu={emu}: {ms:.3f} ms = {fl/ms/1e9:.0f} TF/s   rel/max {rel(out[idx], ref)}")
+    ms = min(timeit(lambda: ops.attention(q, k, v, out, heads), n=5) for _ in range(3))
+    print(f"attention: {ms:.3f} ms = {fl/ms/1e9:.0f} TF/s   rel/max {rel(out[idx], ref)}")
 
 
 def sec_attsplit():
@@ -262,10 +261,8 @@ def sec_attmodes():
         idx = torch.randint(0, L, (256,), device=dev)
         ref = sdpa_ref(q[idx].contiguous(), k, v, heads)
         fl = 4.0 * L * L * heads * 128
-        for emu in (0, 1):
-            out.zero_()
-            ms = min(timeit(lambda: ops.attention(q, k, v, out, heads, emu=emu), n=5) for _ in range(3))
-            print(f"attmodes heads={heads} L={L} emu={emu}: {ms:.3f} ms = {fl/ms/1e9:.0f} TF/s   rel/max {rel(out[idx], ref)}", flush=True)
+        ms = min(timeit(lambda: ops.attention(q, k, v, out, heads), n=5) for _ in range(3))
+        print(f"attmodes heads={heads} L={L}: {ms:.3f} ms = {fl/ms/1e9:.0f} TF/s   rel/max {rel(out[idx], ref)}", flush=True)
     try:
         heads, L = 24, 18480
         qkv = torch.randn(L, 3 * heads * 128, device=dev).bfloat16()
@@ -329,9 +326,7 @@ def sec_atttrace():
     out = torch.empty(L, heads * 128, device=dev, dtype=torch.bfloat16)
     tr = torch.zeros(32 * 32, device=dev, dtype=torch.int64)
     lib = _lib.load()
-    for emu in (0, 1, 4, 5, 7):
-        print(f"--- softmax variant (bit 0 scalar math, bit 1 deferred P store wait, bit 2 split S issue) {emu}")
-        _trace_one(lib, q, k, v, out, tr, L, heads, emu)
+    _trace_one(lib, q, k, v, out, tr, L, heads, 0)
 
 
 def _trace_one(lib, q, k, v, out, tr, L, heads, emu):

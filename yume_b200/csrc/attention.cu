@@ -51,15 +51,14 @@ struct AttParams {
 // Epilogue shared by the attention kernels: thread = query row (TMEM lane), tO = its O accumulator. A KV segment of a tail unit
 // leaves (unnormalised O, m, l) in the workspace for attention_combine_kernel; a whole unit stores O / l as bf16 into
 // out[Lq, heads*128] (accumulating, or into the owner rank's receive buffer under Ulysses).
-// c_begin..c_end: the 32-column chunks of the row this thread owns (0..4 when one thread owns the row; a half when two do).
 __device__ __forceinline__ void attention_epilogue(const AttParams& p, uint32_t tO, float m_used, float l, int X, int row_in_tile,
-                                                   int unit, int c_begin = 0, int c_end = 4) {
+                                                   int unit) {
   if (static_cast<int>(blockIdx.x) >= p.full_units) {
     const long long prow = static_cast<long long>(blockIdx.x - p.full_units) * 256 + X * 128 + row_in_tile;
     float* wo = p.ws_o + prow * 128;
-    if (c_begin == 0) *reinterpret_cast<float2*>(p.ws_ml + prow * 2) = make_float2(m_used, l);
+    *reinterpret_cast<float2*>(p.ws_ml + prow * 2) = make_float2(m_used, l);
 #pragma unroll 1
-    for (int c = c_begin; c < c_end; ++c) {
+    for (int c = 0; c < 4; ++c) {
       uint32_t o[32];
       tmem_ld32(tO + c * 32, o);
       tmem_ld_wait();
@@ -81,7 +80,7 @@ __device__ __forceinline__ void attention_epilogue(const AttParams& p, uint32_t 
       orow = p.out_peers[owner] + (static_cast<long long>(p.sp_rank) * p.sp_Lp + t) * p.ldo + head * 128;
   }
 #pragma unroll 1
-  for (int c = c_begin; c < c_end; ++c) {
+  for (int c = 0; c < 4; ++c) {
     uint32_t o[32];
     tmem_ld32(tO + c * 32, o);
     tmem_ld_wait();
@@ -121,31 +120,19 @@ struct AttCfg {
   static constexpr int KV_OFF = P_TMEM ? 2 * ATT_TILE_BYTES : 4 * ATT_TILE_BYTES;
   static constexpr int BAR_OFF = KV_OFF + NS * ATT_TILE_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256;
-  // two-threads-per-row variant: [X][column half][row] fp32 exchange of the row maxima (and, once, the row sums)
-  static constexpr int XCH_OFF = BAR_OFF + 256;
-  static constexpr int SMEM_BYTES_W16 = 232448;   // the 227 KB maximum; the kernel traps if its layout does not fit behind the alignment pad
 };
-constexpr int ATT_THREADS_W16 = 576;   // 18 warps, 112 registers each from launch (no setmaxnreg: 576 x 112 = 64512)
 
-// EMU: 0 = every exp2 on the MUFU; n > 0 = one of every n probability PAIRS is computed by exp2_poly2 on the FMA pipe
-// (the MUFU's 16 ex2/clk/SM is exactly co-saturated with the tensor pipe at head_dim 128, so part of the
-// exponentials has to move off it for the MMA to stay fed).
-// Round 2 measured seven variants of this kernel and kept none (profiles/r02_attention_schedules.md): Q resident in TMEM with 64-key
-// tiles (976 vs 1336 TFLOP/s), exponentials against a stale reference with a deferred max (3.30 vs 3.18 ms), packed
-// `ex2.approx.ftz.bf16x2` exponentials (4.24 ms), a pipelined softmax (FMNMX3 under a split S load, one TMEM-store wait: 3.29 vs
-// 3.10 ms), bf16 packing on the ALU pipe (3.28 vs 3.17 ms), FMA-pipe exponentials (3.46 ms at 1/4), and a LOOKAHEAD schedule (64-key
-// tiles, S double-buffered in TMEM and issued one tile ahead of the softmax so that neither side waits for the other's round
-// trip: correct, 4.50 ms). The last one is the informative failure: with both query tiles' softmax warps running concurrently the
-// kernel slowed down by exactly the amount two warps sharing one MUFU predict — the exponential phase costs ~11 cycles per
-// MUFU.EX2 warp instruction (700 cycles per 64, trace in profiles/r02_experimental_runbook.md), i.e. 2 x 128 x 11 = 2816 of the 3011
-// cycles of a KV iteration are MUFU time. The kernel is MUFU-bound, not latency-bound; the ping-pong of this schedule already
-// keeps the MUFU ~93 % busy, and only cheaper exponentials can move it.
-// W16: TWO threads per query row. Softmax warps 2..17: warp w serves query tile (w-2)/8, columns 64*(((w-2)/4)&1).. of its rows
-// (TMEM lane quad w%4), so the two warps that share a row also share a scheduler: their LDTM / max / MUFU / pack / STTM streams
-// interleave in hardware, which is what one in-order warp cannot do for itself (profiles/r02_instr_rate.md: ptxas schedules the
-// exponential stream at 8.1 cycles per MUFU, one warp alone runs it at 10.9 because every consumer waits on a scoreboard).
-template <bool P_TMEM, bool W16>
-__global__ void __launch_bounds__(W16 ? ATT_THREADS_W16 : ATT_THREADS, 1)
+// Where the time goes (profiles/r02_ncu_block.md, r02_instr_rate.md): per 128-key step a CTA spends ~3000 cycles for 2048 cycles of tensor
+// work and 2048 cycles of MUFU work; both pipes are ~67 % busy. Each query tile's chain softmax (~1720) -> P.V + next S (~1150) ->
+// hand-off (~100) is serial, the two tiles run it in ping-pong. The exponential phase of the one softmax warp per scheduler runs at
+// 10.9 cycles per MUFU.EX2 against the unit's 8: ptxas schedules the loop at 8.1, the rest are scoreboard waits of an in-order warp
+// that has nothing else to issue. Round 2 measured eleven alternatives against this kernel and kept none (profiles/r02_attention_
+// schedules.md): Q in TMEM with 64-key tiles, deferred max, packed bf16x2 exponentials, pipelined softmax, ALU-pipe packing, FMA-pipe
+// polynomial exponentials, a lookahead schedule with double-buffered S, scalar instead of packed fp32 math, a deferred P store wait,
+// S(j+1) issued in two 64-key halves (N = 64 MMAs run at the N = 128 rate), and two threads per query row (16 softmax warps:
+// correct, 3.75 vs 3.13 ms). cuDNN's fused attention is 14-17 % ahead on the same tensors (profiles/r02_attention_comparators.json).
+template <bool P_TMEM>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttParams p) {
   using Cfg = AttCfg<P_TMEM>;
@@ -158,9 +145,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* s_full = kv_empty + NS;
   uint64_t* p_half = s_full + 2;  // [X][half]: P columns [64*half, 64*half+64) of query tile X are in place
   uint64_t* o_done = p_half + 4;
-  uint64_t* x_read = o_done + 2;    // W16: [X] both column halves have read each other's row maximum (256 arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(x_read + 2);
-  if (W16 && threadIdx.x == 0 && smem + Cfg::XCH_OFF + 2048 > smem_raw + Cfg::SMEM_BYTES_W16) __trap();
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -195,7 +180,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&p_half[2 * i], 128);
       mbar_init(&p_half[2 * i + 1], 128);
       mbar_init(&o_done[i], 1);
-      mbar_init(&x_read[i], 256);
     }
     fence_barrier_init();
   }
@@ -208,8 +192,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp < (W16 ? 2 : 4)) {
-    if (!W16) setmaxnreg_dec<80>();
+  if (warp < 4) {
+    setmaxnreg_dec<80>();
     if (warp == 0 && lane == 0) {
       // ------------------------------- TMA producer -------------------------------
       int unit, kv_begin, nkv;
@@ -322,120 +306,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else {
     // ------------------------------- softmax / correction / epilogue -------------------------------
-    if constexpr (W16) {
-      const int g = (warp - 2) >> 2;   // warps 2..17: every run of four consecutive warps covers the four TMEM lane quads
-      const int X = g >> 1, hc = g & 1;
-      const int quad = warp & 3;
-      const int row_in_tile = quad * 32 + lane;
-      const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-      const uint32_t tS = tmem_base + lane_off + X * 128;
-      const uint32_t tO = tmem_base + lane_off + 256 + X * 128;
-      float* xmine = reinterpret_cast<float*>(smem + Cfg::XCH_OFF) + (X * 2 + hc) * 128 + row_in_tile;
-      const float* xother = reinterpret_cast<const float*>(smem + Cfg::XCH_OFF) + (X * 2 + (hc ^ 1)) * 128 + row_in_tile;
-      const float sc = p.scale_log2;
-      float m_used = -INFINITY;
-      float l = 0.f;
-      int kv_begin, kv_end;
-      {
-        int unit, nkv;
-        decode(unit, kv_begin, nkv);
-        kv_end = kv_begin + nkv;
-      }
-      for (int j = kv_begin; j < kv_end; ++j) {
-        mbar_wait(&s_full[X], j & 1);
-        tc_fence_after();
-        const int kv_rem = p.Lk - j * 128;
-        if (kv_rem < 128) {   // last, partial KV tile: this thread's out-of-range columns of S become -inf in TMEM
-#pragma unroll 1                 // (cold; 16-column pieces keep its registers out of the hot loop's budget)
-          for (int c = 4 * hc; c < 4 * hc + 4; ++c) {
-            if (c * 16 + 16 <= kv_rem) continue;
-            uint32_t t[16];
-            tmem_ld16(tS + c * 16, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c * 16 + i >= kv_rem) t[i] = 0xff800000u;
-            tmem_st16(tS + c * 16, t);
-          }
-          tmem_st_wait();
-        }
-        uint32_t s[2][32];
-        tmem_ld32(tS + hc * 64, s[0]);
-        tmem_ld32(tS + hc * 64 + 32, s[1]);
-        tmem_ld_wait();
-        float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mxa[i & 3] = fmaxf(mxa[i & 3], __uint_as_float(s[c][i]));
-        const float mloc = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-        // row maximum = max over the two column halves: one fp32 through shared memory each way. The partner must have read the
-        // previous tile's value before it is overwritten (x_read, completed long ago in steady state), and see this one (bar).
-        if (j > kv_begin) mbar_wait(&x_read[X], (j - kv_begin - 1) & 1);
-        *xmine = mloc;
-        named_bar_sync(1 + X, 256);
-        const float ms = fmaxf(mloc, *xother) * sc;
-        mbar_arrive(&x_read[X]);
-        if (j == kv_begin) {
-          m_used = ms;
-        } else {
-          const bool need = ms > m_used + 8.0f;   // both halves of a row hold the same ms and m_used: same decision
-          if (__any_sync(0xffffffffu, need)) {
-            const float m_new = fmaxf(m_used, ms);
-            const float alpha = fast_exp2(m_used - m_new);
-            l *= alpha;
-#pragma unroll 1
-            for (int c = 4 * hc; c < 4 * hc + 4; ++c) {
-              uint32_t o[16];
-              tmem_ld16(tO + c * 16, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st16(tO + c * 16, o);
-            }
-            tmem_st_wait();
-            m_used = m_new;
-          }
-        }
-        const uint64_t sc2 = f2_pack(sc, sc);
-        const uint64_t negm2 = f2_pack(-m_used, -m_used);
-        uint64_t ls2[2] = {0ull, 0ull};
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c0 = 2 * i;
-          const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(s[c0 >> 5][c0 & 31]), __uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31])),
-                                     sc2, negm2);
-          float x0, x1;
-          f2_unpack(x2, x0, x1);
-          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-          ls2[i & 1] = f2_add(ls2[i & 1], f2_pack(p0, p1));
-          pk[i] = pack_bf16x2(p0, p1);
-        }
-        tmem_st32(tS + hc * 32, pk);   // packed P columns of key half hc
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_half[2 * X + hc]);
-        {
-          float a0, a1, b0, b1;
-          f2_unpack(ls2[0], a0, a1);
-          f2_unpack(ls2[1], b0, b1);
-          l += (a0 + a1) + (b0 + b1);
-        }
-      }
-      mbar_wait(&o_done[X], 0);
-      tc_fence_after();
-      // row sum = this half's + the partner's (same exchange slots; the last maximum has been read: x_read)
-      mbar_wait(&x_read[X], (kv_end - kv_begin - 1) & 1);
-      *xmine = l;
-      named_bar_sync(1 + X, 256);
-      l += *xother;
-      {
-        int unit, kvb, nk;
-        decode(unit, kvb, nk);
-        attention_epilogue(p, tO, m_used, l, X, row_in_tile, unit, 2 * hc, 2 * hc + 2);
-      }
-    } else {
     setmaxnreg_inc<208>();  // 128*80 + 256*208 = 63488 <= 384*168 (the CTA's register pool)
     const int X = (warp - 4) >> 2;
     const int quad = warp & 3;
@@ -571,7 +441,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       decode(unit, kvb, nk);
       attention_epilogue(p, tO, m_used, l, X, row_in_tile, unit);
     }
-    }   // !W16
   }
 
   tc_fence_before();
@@ -646,15 +515,13 @@ static size_t split_workspace_bytes(size_t ctas) { return ctas * 256 * 130 * siz
 static int g_debug_force_split = 0;   // yb_debug_force_split: tests force the KV split through paths that carry no flags
 
 // force_ns: 0 = automatic tail split, 1 = never, 2..4 = split EVERY unit into that many KV segments (tests)
-template <bool P_TMEM, bool W16>
+template <bool P_TMEM>
 static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                             AttParams p, int heads, cudaStream_t stream, int force_ns, void* ws, long long ws_bytes) {
   using Cfg = AttCfg<P_TMEM>;
-  auto kern = attention_kernel<P_TMEM, W16>;
-  constexpr int kSmem = W16 ? Cfg::SMEM_BYTES_W16 : Cfg::SMEM_BYTES;
-  constexpr int kThreads = W16 ? ATT_THREADS_W16 : ATT_THREADS;
+  auto kern = attention_kernel<P_TMEM>;
   static bool attr_set[kMaxDevices] = {false};
-  if (int rc = ensure_dynamic_smem(kern, kSmem, attr_set, "attention")) return rc;
+  if (int rc = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_set, "attention")) return rc;
   if (force_ns == 0 && g_debug_force_split >= 1 && g_debug_force_split <= 4) force_ns = g_debug_force_split;
   p.nq = (p.Lq + 255) / 256;
   const int units = p.nq * heads;
@@ -673,19 +540,19 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, cons
       p.ws_ml = p.ws_o + ctas * 256 * 128;
     }
   }
-  kern<<<p.full_units + tail * p.ns, kThreads, kSmem, stream>>>(tmQ, tmK, tmV, p);
+  kern<<<p.full_units + tail * p.ns, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   int rc = check_launch("attention");
   if (rc || tail == 0) return rc;
   attention_combine_kernel<<<tail * 32, 256, 0, stream>>>(p, tail);
   return check_launch("attention_combine");
 }
 
-// exponent mode selected by flags bits 2-3 (EMU), debug variant by bit 0
+// debug variant (P through shared memory) selected by flags bit 0
 static int dispatch_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                               AttParams p, int heads, cudaStream_t stream, int flags, void* ws, long long ws_bytes) {
   const int force_ns = (flags >> YB_ATT_SPLIT_SHIFT) & 7;
   if (force_ns > 4) return YB_ERR_ARG;
-  const int emu = (flags >> YB_ATT_EMU_SHIFT) & 3;
+  if ((flags >> YB_ATT_EMU_SHIFT) & 3) return YB_ERR_ARG;   // retired: FMA-pipe exponentials (measured slower, removed)
   CUtensorMap tmQ, tmK, tmV;
   const uint64_t cols = static_cast<uint64_t>(heads) * 128;
   int rc = make_tmap_bf16_2d(&tmQ, q, p.Lq, cols, ldq, 128, 64);
@@ -694,10 +561,8 @@ static int dispatch_attention(const void* q, long long ldq, const void* k, long 
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmV, v, p.Lk, cols, ldv, 128, 64);
   if (rc) return rc;
-  if (flags & YB_ATT_P_SMEM) return launch_attention<false, false>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-  // experiment selector (flags EMU field): 1 = two threads per query row (16 softmax warps)
-  if (emu == 1) return launch_attention<true, true>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
-  return launch_attention<true, false>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+  if (flags & YB_ATT_P_SMEM) return launch_attention<false>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
+  return launch_attention<true>(tmQ, tmK, tmV, p, heads, stream, force_ns, ws, ws_bytes);
 }
 
 }  // namespace yb

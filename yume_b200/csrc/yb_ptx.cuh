@@ -236,23 +236,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {   // 16 columns
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {   // 16 columns
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
@@ -281,67 +264,10 @@ __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-// exp2 of two values on the FMA pipe: same algorithm as exp2_poly, the arithmetic on packed pairs.
-__device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
-  float x0, x1;
-  f2_unpack(x2, x0, x1);
-  x2 = f2_pack(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
-  const uint64_t kMagic = f2_pack(12582912.0f, 12582912.0f);
-  const uint64_t kNegMagic = f2_pack(-12582912.0f, -12582912.0f);
-  const uint64_t kNegOne = f2_pack(-1.0f, -1.0f);
-  const uint64_t t2 = f2_add(x2, kMagic);
-  const uint64_t r2 = f2_add(t2, kNegMagic);
-  const uint64_t f2 = f2_fma(r2, kNegOne, x2);
-  uint64_t p2 = f2_fma(f2_pack(0.053027521818876266f, 0.053027521818876266f), f2,
-                       f2_pack(0.24221394956111908f, 0.24221394956111908f));
-  p2 = f2_fma(p2, f2, f2_pack(0.6935725808143616f, 0.6935725808143616f));
-  p2 = f2_fma(p2, f2, f2_pack(0.9999590516090393f, 0.9999590516090393f));
-  float p0, p1, t0, t1;
-  f2_unpack(p2, p0, p1);
-  f2_unpack(t2, t0, t1);
-  p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-  p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-  return f2_pack(p0, p1);
-}
-
-// ordered (volatile) forms: ptxas keeps volatile asm statements in program order — used to hand-schedule the exponential stream
-__device__ __forceinline__ float fma_ordered(float a, float b, float c) {
-  float d;
-  asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-__device__ __forceinline__ float add_ordered(float a, float b) {
-  float d;
-  asm volatile("add.rn.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
-  return d;
-}
-__device__ __forceinline__ uint32_t pack_bf16x2_ordered(float lo, float hi) {
-  uint32_t r;
-  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {   // bar.sync over a subset of the CTA's warps
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-// exp2 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax
-// polynomial for 2^f (max rel. error 2.0e-4, an order of magnitude below the bf16 rounding of P), exponent added
-// with integer arithmetic. Valid for x <= ~120; inputs below -125 are clamped (result ~2^-125, i.e. 0 for softmax).
-__device__ __forceinline__ float exp2_poly(float x) {
-  x = fmaxf(x, -125.0f);
-  const float kMagic = 12582912.0f;  // 1.5 * 2^23: the low mantissa bits of (x + kMagic) hold round(x)
-  const float t = x + kMagic;
-  const float f = x - (t - kMagic);
-  float p = fmaf(0.053027521818876266f, f, 0.24221394956111908f);
-  p = fmaf(p, f, 0.6935725808143616f);
-  p = fmaf(p, f, 0.9999590516090393f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;

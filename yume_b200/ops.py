@@ -195,7 +195,7 @@ def _attention_ws(Lq: int, Lk: int, heads: int, flags: int, device: torch.device
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, heads: int,
-              scale: Optional[float] = None, variant: int = 0, accumulate: bool = False, emu: int = 0,
+              scale: Optional[float] = None, variant: int = 0, accumulate: bool = False,
               split: int = 0) -> torch.Tensor:
     """softmax(q k^T * scale) v, non-causal. q [Lq, heads*128], k/v [Lk, heads*128] bf16 (row strides arbitrary).
     split: KV split policy (YB_ATT_SPLIT_SHIFT): 0 automatic tail split, 1 never, 2..4 force that many KV segments.
@@ -208,7 +208,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
         raise YumeB200Error("attention supports head_dim 128 only")
     if scale is None:
         scale = 1.0 / math.sqrt(128.0)
-    flags = (YB_ATT_P_SMEM if variant == 1 else 0) | (YB_ATT_ACCUMULATE if accumulate else 0) | ((emu & 3) << 2) | ((split & 7) << 4) | (128 if (emu & 4) else 0)
+    flags = (YB_ATT_P_SMEM if variant == 1 else 0) | (YB_ATT_ACCUMULATE if accumulate else 0) | ((split & 7) << 4)
     if variant not in (0, 1):
         raise YumeB200Error("attention variant must be 0 or 1")
     ws, ws_bytes = _attention_ws(Lq, Lk, heads, flags, q.device)
