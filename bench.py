@@ -257,7 +257,7 @@ def supplementary(args, dev, eng5, world, rank, peaks):
     out = {}
     li = dev.index or 0
 
-    def loop_entry(name, fn, new_frames, fwd_per_loop, flops_per_fwd, reps=2):
+    def loop_entry(name, fn, new_frames, fwd_per_loop, flops_per_fwd, reps=2, parity_engine=None):
         fn()                                                   # warm-up (fills the context cache / captures graphs)
         if world > 1:
             dist.barrier()
@@ -285,6 +285,15 @@ def supplementary(args, dev, eng5, world, rank, peaks):
         if world > 1:
             out[name]["roofline"]["achieved"] = tf / world
             out[name]["roofline"]["frac"] = tf / world / peak
+            if parity_engine is not None:                      # correctness on the record: same engine, rank 0 alone, same inputs
+                dist.barrier()
+                if rank == 0:
+                    with parity_engine.sequence_parallel_disabled():
+                        r1 = fn()
+                    torch.cuda.synchronize()
+                    out[name]["parity_vs_n1"] = float((res.float() - r1.float()).norm() / r1.float().norm())
+                    del r1
+                dist.barrier()
 
     # ---- configs[3]: Yume-5B 4-step distilled sampling of one FramePack chunk (5 history + 8 new latent frames) ----
     g = torch.Generator(device=dev).manual_seed(2)
@@ -299,7 +308,7 @@ def supplementary(args, dev, eng5, world, rank, peaks):
 
     def loop5(sde):
         return lambda: sampler.denoise_chunk_5b(model5, torch.cat([hist, noise], 1), hist, 8, 4, arg_c, shift=7.0, sde=sde)
-    loop_entry("5b-chunk-4step", loop5(False), 8, 4, fl5)
+    loop_entry("5b-chunk-4step", loop5(False), 8, 4, fl5, parity_engine=e5)
     loop_entry("5b-chunk-4step-sde", loop5(True), 8, 4, fl5)
     if world == 1:
         e5.use_cuda_graph = True
@@ -338,7 +347,8 @@ def supplementary(args, dev, eng5, world, rank, peaks):
         a_n = dict(context=[ctx_n], clip_fea=clip, y=[y14], seq_len=L14)
         t14 = torch.tensor([500.0], device=dev)
         e14.context_cache = False
-        loop_entry("14b-chunk", lambda: m14([x14], t=t14, rand_num_img=0.6, latent_frame_zero=8, **a_c)[0], 8, 1, fl14, reps=3)
+        loop_entry("14b-chunk", lambda: m14([x14], t=t14, rand_num_img=0.6, latent_frame_zero=8, **a_c)[0], 8, 1, fl14, reps=3,
+                   parity_engine=e14)
         out["14b-chunk"]["config"] = ("Yume-I2V-540P (14B: dim 5120, 40 heads, 40 layers) single FramePack-chunk forward, 13 latent "
                                       "frames @68x120 (5 history + 8 new), L=21930, 257 CLIP + 512 text context rows; no caching")
         e14.context_cache = True
@@ -347,6 +357,20 @@ def supplementary(args, dev, eng5, world, rank, peaks):
         out["14b-cfg-ode-5of50"]["config"] = ("BASELINE configs[2] slice: first 5 of the 50 Euler steps of sample.py:755-790 (CFG 5.0 -> "
                                               "2 forwards per step, shift 3.0); value extrapolates nothing: 8 new frames / (10 forwards)")
         out["14b-cfg-ode-5of50"]["ms_per_50_steps_extrapolated"] = out["14b-cfg-ode-5of50"]["ms_per_loop"] * 10
+        try:
+            # the full 81-frame regular grid (no FramePack packing): L = 21 x 34 x 60 = 42 840 tokens, the largest 14B forward
+            xg = torch.randn(16, 21, 68, 120, generator=g, device=dev)
+            yg = torch.randn(20, 21, 68, 120, generator=g, device=dev)
+            Lg = 42840
+            flg = cfg["num_layers"] * block_flops(Lg, cfg["dim"], cfg["ffn_dim"], S14)
+            e14.context_cache = False
+            a_g = dict(context=[ctx_c], clip_fea=clip, y=[yg], seq_len=Lg)
+            loop_entry("14b-grid-81f", lambda: m14([xg], t=t14, rand_num_img=0.3, **a_g)[0], 21, 1, flg, reps=2, parity_engine=e14)
+            out["14b-grid-81f"]["config"] = ("Yume-I2V-540P (14B) single forward on the full 81-frame 544x960 grid, latent [16,21,68,120], "
+                                             "L=42840 (regular-grid RoPE path, rand_num_img < 0.4), 257 CLIP + 512 text context rows; no caching")
+            del xg, yg
+        except Exception as e:   # never lose the other entries to the largest one
+            out["14b-grid-81f"] = {"error": f"{type(e).__name__}: {e}"[:500]}
         del m14, e14
         torch.cuda.empty_cache()
 

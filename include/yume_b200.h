@@ -67,8 +67,20 @@ typedef struct yb_gemm_args {
   long long a_split_stride;
   const void* res;  /* YB_EPI_RES_BF16: bf16 [M, N] residual, row stride res_ld */
   long long res_ld;
+  /* Tail split-K (SM-pair kernel, YB_EPI_GATE_RES): when the last wave of output tiles fills at most part of the SM pairs (the
+   * per-rank shapes of 4- / 8-GPU Ulysses: 228 / 120 tiles on 74 pairs), its tiles are cut into K segments that run as separate work
+   * items and leave fp32 partials in `ws`; a second kernel adds them and applies the epilogue. split_k: 0 = automatic,
+   * 1 = never, 2..12 = force that many segments on the last wave (tests). ws / ws_bytes: CALLER-owned workspace of at least
+   * yb_gemm_workspace_bytes(...) bytes, 16-byte aligned; NULL or too small = the launch is simply not split (same result up to
+   * fp32 summation order). The library never allocates. */
+  int split_k;
+  void* ws;
+  long long ws_bytes;
 } yb_gemm_args;
 int yb_gemm_bf16(const yb_gemm_args* args, void* stream);
+long long yb_gemm_workspace_bytes(int M, int N, int K, int epilogue, int cta_pair, int split_k);
+/* Host-only: out3 = {whole tiles, K segments per tail tile (1 = no split), 64-column K blocks per segment}. */
+int yb_gemm_splitk_plan(int tiles, int num_kb, int clusters, int split_k, int* out3);
 /* Host-only: the kernel / tiling yb_gemm_bf16 picks for an [M, N] output on a GPU with `sms` SMs (no device access).
  * out4 = {1 if the SM-pair kernel, N tile, M tiles (of 256 rows for the pair kernel, 128 otherwise), N tiles}. */
 int yb_gemm_plan(int M, int N, int sms, int* out4);

@@ -23,7 +23,7 @@ def test_library_exports_every_header_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/yume_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), "ctypes signature table and header disagree"
-    assert lib.yb_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.yb_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_ops_have_no_cpu_path():
@@ -406,3 +406,30 @@ def test_gemm_plan_kernel_choice():
     assert plan(512, 3072) == (0, 256, 4, 12)            # context rows: 1-CTA kernel
     assert plan(257, 96) == (0, 128, 3, 1)
     assert lib.yb_gemm_plan(0, 128, 148, out) != 0
+
+
+def test_gemm_tail_split_k_plan():
+    """The split-K chooser of the SM-pair gate+residual GEMM (host arithmetic, no GPU): splits the per-rank shapes of 4- / 8-GPU
+    Ulysses whose last wave is mostly idle, leaves full last waves and short-K launches alone, and every segment owns K blocks."""
+    import ctypes as C
+    lib = yume_b200.load()
+    out = (C.c_int * 3)()
+
+    def plan(tiles, num_kb, clusters=74, force=0):
+        assert lib.yb_gemm_splitk_plan(tiles, num_kb, clusters, force, out) == 0
+        return tuple(out)
+
+    assert plan(120, 224) == (74, 3, 75)          # 8 GPUs, FFN-down: 46 tail tiles x 3 segments = 2 sub-waves of 1/3
+    assert plan(120, 48)[1] == 1                  # 8 GPUs, o-projection: the combine launch costs more than the idle tail
+    full, ns, per = plan(228, 224)                # 4 GPUs, FFN-down: 6 tail tiles spread over the 74 pairs
+    assert full == 222 and ns >= 6 and 6 * ns <= 74 and (ns - 1) * per < 224 <= ns * per
+    assert plan(876, 224)[1] == 1 and plan(444, 224)[1] == 1     # 1 / 2 GPUs: last wave (nearly) full
+    assert plan(74, 224) == (74, 1, 224) and plan(50, 224)[1] == 1
+    assert plan(100, 224, force=2) == (74, 2, 112) and plan(100, 224, force=1)[1] == 1
+    assert plan(5, 8, force=2) == (0, 2, 4) and plan(5, 3, force=2)[1] == 1
+    for tiles in range(1, 400, 7):
+        for num_kb in (8, 48, 80, 224):
+            full, ns, per = plan(tiles, num_kb)
+            assert 0 <= full <= tiles and 1 <= ns <= 12
+            if ns > 1:
+                assert full % 74 == 0 and (ns - 1) * per < num_kb <= ns * per and per >= 8

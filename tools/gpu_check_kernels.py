@@ -299,6 +299,28 @@ def sec_gemmpair():
             print(line, flush=True)
 
 
+def sec_gemmsplit():
+    """Tail split-K of the SM-pair gate+residual GEMM at the per-rank shapes of 8-, 4- and 2-GPU Ulysses (and the full shape)."""
+    C, F = 3072, 14336
+    for L in (2310, 4620, 9240, 18480):
+        for name, (M, N, K) in (("o", (L, C, C)), ("ffn2", (L, C, F))):
+            a = torch.randn(M, K, device=dev).bfloat16()
+            w = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
+            x = torch.randn(M, N, device=dev); gate = torch.randn(1, N, device=dev)
+            fl = 2.0 * M * N * K
+            ws = _lib_ws(M, N, K)
+            t0 = min(timeit(lambda: ops.gemm(a, w, None, x, ops.YB_EPI_GATE_RES, gate=gate, cta_pair=2, split_k=1), 10) for _ in range(3))
+            t1 = min(timeit(lambda: ops.gemm(a, w, None, x, ops.YB_EPI_GATE_RES, gate=gate, cta_pair=2, split_k=0), 10) for _ in range(3))
+            t3 = timeit(lambda: torch.matmul(a, w.t()), 10)
+            print(f"gemmsplit L={L} {name}: unsplit {t0*1e3:.1f} us ({fl/t0/1e9:.0f} TF/s)  auto {t1*1e3:.1f} us ({fl/t1/1e9:.0f} TF/s, workspace {ws/1e6:.1f} MB)  "
+                  f"cuBLAS plain {t3*1e3:.1f} us ({fl/t3/1e9:.0f})", flush=True)
+
+
+def _lib_ws(M, N, K):
+    from yume_b200 import _lib
+    return _lib.load().yb_gemm_workspace_bytes(M, N, K, ops.YB_EPI_GATE_RES, 2, 0)
+
+
 def sec_convpair():
     """Causal conv as implicit GEMM: 1-CTA un-fused / 1-CTA kw-fused / SM-pair kernel on the widths of the three VAE decoders."""
     shapes = [("hy 128->128 @17x256x256", 17, 256, 256, 128, 128), ("hy 256->256 @17x128x128", 17, 128, 128, 256, 256),
@@ -354,9 +376,9 @@ def _trace_one(lib, q, k, v, out, tr, L, heads, emu):
     print("raw rows 0..2:", (t[:3] - base).tolist())
 
 
-SECTIONS = {"attmodes": sec_attmodes, "gemmpair": sec_gemmpair, "convpair": sec_convpair, "attsplit": sec_attsplit, "atttrace": sec_atttrace, "atttune": sec_atttune, "probe": sec_probe, "gemm": sec_gemm, "attention": sec_attention, "elementwise": sec_elementwise}
+SECTIONS = {"attmodes": sec_attmodes, "gemmpair": sec_gemmpair, "gemmsplit": sec_gemmsplit, "convpair": sec_convpair, "attsplit": sec_attsplit, "atttrace": sec_atttrace, "atttune": sec_atttune, "probe": sec_probe, "gemm": sec_gemm, "attention": sec_attention, "elementwise": sec_elementwise}
 if __name__ == "__main__":
-    names = sys.argv[1:] or [n for n in SECTIONS if n not in ("gemmpair", "attmodes", "convpair")]   # experimental sections only on request
+    names = sys.argv[1:] or [n for n in SECTIONS if n not in ("gemmpair", "attmodes", "convpair", "gemmsplit")]   # experimental sections only on request
     print(torch.cuda.get_device_name(0))
     for n in names:
         print(f"===== {n} =====", flush=True)

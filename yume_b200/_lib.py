@@ -9,7 +9,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libyume_b200.so"
 
 YB_EPI_BF16, YB_EPI_GELU_BF16, YB_EPI_F32, YB_EPI_GATE_RES, YB_EPI_GELU_ERF_BF16, YB_EPI_RES_BF16 = 0, 1, 2, 3, 4, 5
 YB_ATT_P_SMEM, YB_ATT_ACCUMULATE = 1, 2
-ABI_VERSION = 3   # yb_abi_version() of the library this binding was written against
+ABI_VERSION = 4   # yb_abi_version() of the library this binding was written against
 YB_ATT_EMU_SHIFT, YB_ATT_SPLIT_SHIFT = 2, 4
 
 _ERRORS = {
@@ -37,6 +37,7 @@ class GemmArgs(C.Structure):
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("epilogue", C.c_int), ("block_n", C.c_int),
         ("n_split", C.c_int), ("split_stride", C.c_longlong), ("a_split", C.c_int), ("a_split_stride", C.c_longlong),
         ("res", C.c_void_p), ("res_ld", C.c_longlong),
+        ("split_k", C.c_int), ("ws", C.c_void_p), ("ws_bytes", C.c_longlong),
     ]
 
 
@@ -65,6 +66,8 @@ SIGNATURES = {
     "yb_nchw_to_nhwc_bf16": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
     "yb_nhwc_to_nchw_f32": (_i, [_vp, _ll, _vp, _ll, _i, _vp]),
     "yb_gemm_plan": (_i, [_i, _i, _i, C.POINTER(C.c_int)]),
+    "yb_gemm_workspace_bytes": (_ll, [_i, _i, _i, _i, _i, _i]),
+    "yb_gemm_splitk_plan": (_i, [_i, _i, _i, _i, C.POINTER(C.c_int)]),
     "yb_conv3d_plan": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(C.c_int)]),
     "yb_attention_plan": (_i, [_i, _i, _i, _i, _i, C.POINTER(C.c_int)]),
     "yb_nhwc_to_nchw_f32_clamp": (_i, [_vp, _ll, _vp, _ll, _i, C.c_float, C.c_float, _vp]),

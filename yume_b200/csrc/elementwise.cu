@@ -667,7 +667,7 @@ extern "C" int yb_bcast_add(const void* a, const void* b, void* out, int R1, int
   return check_launch("bcast_add");
 }
 
-extern "C" int yb_abi_version(void) { return 3; }
+extern "C" int yb_abi_version(void) { return 4; }
 
 extern "C" int yb_ln_modulate(const void* x, long long ldx, void* out, long long ldo, int out_f32, const void* scale,
                               const void* shift, long long mod_ld, const void* tok_idx, const void* weight,

@@ -55,6 +55,11 @@ struct GemmParams {
                                 // still lands as 128 dense rows; cT/cH/cW are OUTPUT extents, the tile origin scales by the stride
   int num_m_tiles, num_n_tiles;
   int block_n, stages;          // SM-pair kernel (gemm_pair_kernel): runtime N tile (multiple of 32, <= 256) and ring depth
+  // Tail split-K of the SM-pair kernel (GATE_RES launches): work items [0, sk_full) are whole tiles; item sk_full + u is K segment
+  // u % sk_ns (sk_per 64-column blocks) of tile sk_full + u / sk_ns and leaves its raw fp32 accumulator in sk_ws[u][256][block_n]
+  // for gemm_splitk_combine_kernel. sk_ns == 1: no split (sk_full == number of tiles).
+  int sk_full, sk_ns, sk_per;
+  float* sk_ws;
   // YB_EPI_SP_QKV (internal): the fused q|k|v projection of a Ulysses rank whose epilogue IS the all-to-all — column
   // (part, head h, d) of local token t is stored into the receive buffer of the rank that owns head h (NVLink peer pointer),
   // layout [P(src), Lp, q|k|v of heads/P]; and the per-row sums of squares of the q and k parts (WanRMSNorm spans all heads)
@@ -526,6 +531,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int tile_first = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;            // tiles of 256 x block_n
   const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  const int num_work = p.sk_full + (num_tiles - p.sk_full) * p.sk_ns;   // == num_tiles without a split tail
+  // work item -> (tile, K-block range, partial slot or -1); every role walks the same sequence
+  auto decode_work = [&](int w, int& tile, int& kb0, int& kb1, int& part) {
+    tile = w; kb0 = 0; kb1 = num_kb; part = -1;
+    if (w >= p.sk_full) {
+      const int u = w - p.sk_full;
+      tile = p.sk_full + u / p.sk_ns;
+      kb0 = (u % p.sk_ns) * p.sk_per;
+      kb1 = min(num_kb, kb0 + p.sk_per);
+      part = u;
+    }
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -551,10 +568,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
-        int m_tile, n_tile;
+      for (int w = tile_first; w < num_work; w += tile_step) {
+        int tile, kb0, kb1, part, m_tile, n_tile;
+        decode_work(w, tile, kb0, kb1, part);
         tile_coords(tile, p.num_m_tiles, p.num_n_tiles, m_tile, n_tile);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
@@ -585,19 +603,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t idesc = make_idesc_bf16(256, block_n, 0, 0);
       int stage = 0, local = 0;
       uint32_t phase = 0;
-      for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++local) {
+      for (int w = tile_first; w < num_work; w += tile_step, ++local) {
+        int tile, kb0, kb1, part;
+        decode_work(w, tile, kb0, kb1, part);
         const int acc = local & 1;
         mbar_wait_cluster(&tmem_empty[acc], ((local >> 1) & 1) ^ 1);   // arrivals come from both CTAs
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t bdesc = make_smem_desc_sw128(sa + GEMM_BLOCK_M * GEMM_BLOCK_K * 2, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) umma_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) umma_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
           umma_commit_2cta(&empty_bar[stage]);        // frees the slot in BOTH CTAs
           if (++stage == stages) {
             stage = 0;
@@ -611,11 +631,31 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quad = warp & 3;
     float* stage = reinterpret_cast<float*>(smem + pair_bar_off(block_n, stages) + 256) + quad * (32 * 36);
     int local = 0;
-    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++local) {
-      int m_tile, n_tile;
+    for (int w = tile_first; w < num_work; w += tile_step, ++local) {
+      int tile, kb0, kb1, part, m_tile, n_tile;
+      decode_work(w, tile, kb0, kb1, part);
       tile_coords(tile, p.num_m_tiles, p.num_n_tiles, m_tile, n_tile);
       const int acc = local & 1;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
+      if (part >= 0) {
+        // K segment of a split tail tile: the raw fp32 accumulator goes to the workspace, row-major [256][block_n]; the fused
+        // epilogue runs in gemm_splitk_combine_kernel over the sum of the segments
+        float* wrow = p.sk_ws + (static_cast<long long>(part) * 256 + rank * GEMM_BLOCK_M + quad * 32 + lane) * block_n;
+        mbar_wait(&tmem_full[acc], (local >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < block_n / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<uint4*>(wrow + c * 32 + 4 * i) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+        }
+        tc_fence_before();
+        mbar_arrive_leader(&tmem_empty[acc]);
+        continue;
+      }
       int my_row;
       if (p.conv) {   // tile row -> voxel of this CTA's TT x TH x TW box -> output row (see gemm_kernel)
         const int r = quad * 32 + lane, mt = m_tile * 2 + rank, per_t = p.tiles_h * p.tiles_w;
@@ -749,6 +789,71 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// Fused epilogue of the split tail tiles (YB_EPI_GATE_RES): x[row, col] += (sum of the K-segment partials + bias[col]) * gate[tok, col],
+// segments added in index order (deterministic). One thread per 4 columns of one tile row.
+__global__ void __launch_bounds__(256) gemm_splitk_combine_kernel(const GemmParams p, int tail_tiles) {
+  const int block_n = p.block_n, quads = block_n >> 2;
+  const long long total = static_cast<long long>(tail_tiles) * 256 * quads;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cq = static_cast<int>(i % quads) * 4;
+    const long long rr = i / quads;
+    const int r = static_cast<int>(rr & 255);
+    const int t = static_cast<int>(rr >> 8);
+    int m_tile, n_tile;
+    tile_coords(p.sk_full + t, p.num_m_tiles, p.num_n_tiles, m_tile, n_tile);
+    const int row = m_tile * 256 + r, col = n_tile * block_n + cq;
+    if (row >= p.M || col >= p.N) continue;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sg = 0; sg < p.sk_ns; ++sg) {
+      const float4 v = *reinterpret_cast<const float4*>(p.sk_ws + ((static_cast<long long>(t) * p.sk_ns + sg) * 256 + r) * block_n + cq);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    if (p.bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.gate) {
+      const long long tok = p.tok_idx ? p.tok_idx[row] : 0;
+      g = __ldg(reinterpret_cast<const float4*>(p.gate + tok * p.gate_ld + col));
+    }
+    float4* xp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col);
+    float4 x = *xp;
+    x.x += a.x * g.x; x.y += a.y * g.y; x.z += a.z * g.z; x.w += a.w * g.w;
+    *xp = x;
+  }
+}
+
+// Tail split-K plan (host arithmetic, exported through yb_gemm_splitk_plan): `tiles` output tiles on `clusters` SM pairs leave a
+// last wave of r = tiles % clusters tiles; cutting each of them into ns K segments costs ceil(r * ns / clusters) sub-waves of
+// 1 / ns of a tile, plus the partial round trip and the combine launch (~6 us, i.e. 13.6 / num_kb of a tile, + 1 % per segment).
+// Taken only when that beats the idle tail by 15 %: 8-GPU FFN-down (120 tiles, K = 14336): 3 segments, 2.0 -> 1.73 tile times;
+// 4-GPU (228 tiles): 12 segments, 4.0 -> 3.2; never at 1 or 2 GPUs (876 / 444 tiles fill their last wave).
+static void gemm_splitk_plan(int tiles, int num_kb, int clusters, int force_ns, int* full, int* ns, int* per) {
+  *full = tiles; *ns = 1; *per = num_kb;
+  if (clusters <= 0 || force_ns == 1) return;
+  int r = tiles % clusters;
+  if (force_ns >= 2) {
+    if (num_kb < 2 * force_ns) return;
+    if (tiles <= clusters || r == 0) r = tiles < clusters ? tiles : clusters;   // tests: split the last wave whatever its fill
+    *ns = force_ns;
+  } else {
+    if (tiles <= clusters || r == 0) return;
+    double best = 0.85;
+    for (int n = 2; n <= 12 && num_kb / n >= 8; ++n) {
+      const int pr = (num_kb + n - 1) / n;
+      const double cost = static_cast<double>((r * n + clusters - 1) / clusters) * pr / num_kb + 13.6 / num_kb + 0.01 * n;
+      if (cost < best) { best = cost; *ns = n; }
+    }
+    if (*ns == 1) return;
+  }
+  *per = (num_kb + *ns - 1) / *ns;
+  while (*ns > 1 && (*ns - 1) * *per >= num_kb) --*ns;   // every segment owns at least one K block
+  if (*ns == 1) { *per = num_kb; return; }
+  *full = tiles - r;
+}
+
 // N tile of the SM-pair kernel: 256 (N itself, rounded up to 32, for narrower outputs). The kernel takes any multiple of 32 and
 // a waves-x-width cost model was tried: on the 8-GPU o-projection (M = 2310, N = 3072) 224-wide tiles fill two waves exactly
 // where 256-wide ones need 1.62, but measured 0.045 ms vs 0.043 ms (ffn1: 0.196 vs 0.176): narrower MMAs and more B re-reads cost
@@ -759,8 +864,32 @@ static int pair_block_n(int M, int N, int clusters) {
   return N >= 256 ? 256 : ((N + 31) / 32) * 32;
 }
 
+// CTA pairs the device holds at once (GPCs with an odd SM count leave an SM unpaired): asked of the driver, SM count / 2 if the
+// query is unavailable
+template <typename Kern>
+static int pair_max_clusters(Kern kern) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (sm_count() / 2));
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = 227 * 1024;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+    (void)cudaGetLastError();
+    n = sm_count() / 2;
+  }
+  return n;
+}
+
 template <int EPI>
-static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
+static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream, int split_k = 1,
+                            void* ws = nullptr, long long ws_bytes = 0) {
   auto kern = gemm_pair_kernel<EPI>;
   static bool attr_set[kMaxDevices] = {false};
   if (int rc = ensure_dynamic_smem(kern, 227 * 1024, attr_set, "gemm_pair")) return rc;
@@ -773,28 +902,27 @@ static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, Gemm
   // asked of the driver once per device, the SM count / 2 if the query is unavailable)
   static int max_clusters[kMaxDevices] = {0};
   const int dev = current_device();
-  if (max_clusters[dev] == 0) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * (sm_count() / 2));
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = 227 * 1024;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
-      (void)cudaGetLastError();
-      n = sm_count() / 2;
+  if (max_clusters[dev] == 0) max_clusters[dev] = pair_max_clusters(kern);
+  p.sk_full = tiles; p.sk_ns = 1; p.sk_per = 0; p.sk_ws = nullptr;
+  int tail = 0;
+  if (EPI == YB_EPI_GATE_RES && !p.conv && ws != nullptr && split_k != 1) {
+    const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+    gemm_splitk_plan(tiles, num_kb, max_clusters[dev], split_k, &p.sk_full, &p.sk_ns, &p.sk_per);
+    tail = tiles - p.sk_full;
+    const long long need = static_cast<long long>(tail) * p.sk_ns * 256 * p.block_n * 4;
+    if (tail > 0 && (ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 0xF))) {   // workspace too small: unsplit, same result
+      p.sk_full = tiles; p.sk_ns = 1; tail = 0;
     }
-    max_clusters[dev] = n;
+    if (tail > 0) p.sk_ws = static_cast<float*>(ws);
   }
-  const int clusters = tiles < max_clusters[dev] ? tiles : max_clusters[dev];
+  const int work = p.sk_full + tail * p.sk_ns;
+  const int clusters = work < max_clusters[dev] ? work : max_clusters[dev];
   kern<<<2 * clusters, GEMM_THREADS, pair_smem_bytes(p.block_n, p.stages), stream>>>(tmA, tmB, p);
-  return check_launch("gemm_pair");
+  int rc = check_launch("gemm_pair");
+  if (rc || tail == 0) return rc;
+  const long long total = static_cast<long long>(tail) * 256 * (p.block_n / 4);
+  gemm_splitk_combine_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(p, tail);
+  return check_launch("gemm_splitk_combine");
 }
 
 template <int BLOCK_N, int EPI, int CONVW = 0>
@@ -889,6 +1017,30 @@ extern "C" int yb_conv3d_plan(int T, int H, int W, int Cout, int kw, int fuse_w,
   return YB_OK;
 }
 
+// Tail split-K plan of the SM-pair GATE_RES GEMM (host arithmetic only; pins the chooser in the CPU test-suite).
+// out3 = {whole tiles, K segments per tail tile (1 = no split), K blocks of 64 per segment}
+extern "C" int yb_gemm_splitk_plan(int tiles, int num_kb, int clusters, int split_k, int* out3) {
+  if (tiles <= 0 || num_kb <= 0 || clusters <= 0 || split_k < 0 || split_k > 12 || !out3) return YB_ERR_ARG;
+  yb::gemm_splitk_plan(tiles, num_kb, clusters, split_k, &out3[0], &out3[1], &out3[2]);
+  return YB_OK;
+}
+
+// Bytes of caller-owned workspace yb_gemm_bf16 needs to split the tail of this launch (0 = it will not split). Asks the driver for
+// the number of resident CTA pairs, so it needs a current device.
+extern "C" long long yb_gemm_workspace_bytes(int M, int N, int K, int epilogue, int cta_pair, int split_k) {
+  using namespace yb;
+  if (M <= 0 || N <= 0 || K <= 0 || epilogue != YB_EPI_GATE_RES || split_k == 1 || split_k < 0 || split_k > 12) return 0;
+  if (!(cta_pair == 2 || (cta_pair == 0 && M >= 1024 && N >= 128))) return 0;
+  static int max_clusters[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (max_clusters[dev] == 0) max_clusters[dev] = pair_max_clusters(gemm_pair_kernel<YB_EPI_GATE_RES>);
+  const int bn = pair_block_n(M, N, max_clusters[dev]);
+  const int tiles = ((M + 255) / 256) * ((N + bn - 1) / bn);
+  int full, ns, per;
+  gemm_splitk_plan(tiles, (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K, max_clusters[dev], split_k, &full, &ns, &per);
+  return static_cast<long long>(tiles - full) * ns * 256 * bn * 4;
+}
+
 extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
   using namespace yb;
   if (!a || !a->A || !a->B || !a->out) return YB_ERR_ARG;
@@ -899,7 +1051,7 @@ extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
   if ((a->lda % 8) || (a->ldb % 8) || (a->ldo % 8) || (reinterpret_cast<uintptr_t>(a->out) & 0xF)) return YB_ERR_ALIGNMENT;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (a->struct_bytes != sizeof(yb_gemm_args)) return YB_ERR_ARG;   // caller compiled against another layout of the struct
-  if (a->cta_pair < 0 || a->cta_pair > 2) return YB_ERR_ARG;
+  if (a->cta_pair < 0 || a->cta_pair > 2 || a->split_k < 0 || a->split_k > 12) return YB_ERR_ARG;
   int a_split = a->K;
   long long a_chunk_ld = 0;
   if (a->a_split > 0) {
@@ -947,7 +1099,7 @@ extern "C" int yb_gemm_bf16(const yb_gemm_args* a, void* stream_) {
       case YB_EPI_F32: return launch_gemm_pair<YB_EPI_F32>(tmA, tmB, p, stream);
       case YB_EPI_GELU_ERF_BF16: return launch_gemm_pair<YB_EPI_GELU_ERF_BF16>(tmA, tmB, p, stream);
       case YB_EPI_RES_BF16: return launch_gemm_pair<YB_EPI_RES_BF16>(tmA, tmB, p, stream);
-      default: return launch_gemm_pair<YB_EPI_GATE_RES>(tmA, tmB, p, stream);
+      default: return launch_gemm_pair<YB_EPI_GATE_RES>(tmA, tmB, p, stream, a->split_k, a->ws, a->ws_bytes);
     }
   }
   const int block_n = (a->block_n == 128 || a->block_n == 256) ? a->block_n : ((a->N % 256 == 0 || a->N > 1024) ? 256 : 128);

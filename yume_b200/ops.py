@@ -60,9 +60,10 @@ def _need(t: torch.Tensor, dtype, name: str) -> None:
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, epilogue: int,
          gate: Optional[torch.Tensor] = None, tok_idx: Optional[torch.Tensor] = None, block_n: int = 0,
          n_split: int = 0, split_stride: int = 0, a_split: int = 0, a_split_stride: int = 0,
-         shape: Optional[tuple] = None, res: Optional[torch.Tensor] = None, cta_pair: int = 0) -> torch.Tensor:
+         shape: Optional[tuple] = None, res: Optional[torch.Tensor] = None, cta_pair: int = 0, split_k: int = 0) -> torch.Tensor:
     """out = epi(a[M,K] @ w[N,K]^T + bias). a, w bf16 (2-D, row stride arbitrary); see include/yume_b200.h.
-    cta_pair: 0 automatic, 1 force the 1-CTA kernel, 2 force the SM-pair (cta_group::2) kernel."""
+    cta_pair: 0 automatic, 1 force the 1-CTA kernel, 2 force the SM-pair (cta_group::2) kernel.
+    split_k (SM-pair GATE_RES launches): 0 automatic tail split-K, 1 never, 2..12 force that many K segments on the last wave."""
     global _launches, _flops
     _need(a, torch.bfloat16, "a")
     _need(w, torch.bfloat16, "w")
@@ -85,12 +86,19 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
         _need(gate, torch.float32, "gate")
     if tok_idx is not None:
         _need(tok_idx, torch.int32, "tok_idx")
+    ws, ws_bytes = None, 0
+    if epilogue == YB_EPI_GATE_RES and split_k != 1 and cta_pair != 1:
+        # caller-owned workspace of the tail split-K (the library never allocates): a stream-ordered allocation from torch's
+        # caching allocator, only for launches the planner actually splits
+        ws_bytes = _lib.load().yb_gemm_workspace_bytes(M, N, K, epilogue, cta_pair, split_k)
+        if ws_bytes > 0:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
     args = GemmArgs(
         struct_bytes=C.sizeof(GemmArgs), cta_pair=cta_pair, A=a.data_ptr(), B=w.data_ptr(), bias=_ptr(bias), out=out.data_ptr(), gate=_ptr(gate), tok_idx=_ptr(tok_idx),
         lda=a.stride(-2), ldb=w.stride(0), ldo=out.stride(-2), gate_ld=(gate.stride(0) if gate is not None else 0),
         M=M, N=N, K=K, epilogue=epilogue, block_n=block_n, n_split=n_split, split_stride=split_stride,
         a_split=a_split, a_split_stride=a_split_stride, res=_ptr(res),
-        res_ld=(res.stride(-2) if res is not None else 0))
+        res_ld=(res.stride(-2) if res is not None else 0), split_k=split_k, ws=_ptr(ws), ws_bytes=ws_bytes)
     check(_lib.load().yb_gemm_bf16(C.byref(args), _stream()), "yb_gemm_bf16")
     _launches += 1
     _flops += 2.0 * M * N * K
