@@ -419,7 +419,8 @@ def test_gemm_tail_split_k_plan():
         assert lib.yb_gemm_splitk_plan(tiles, num_kb, clusters, force, out) == 0
         return tuple(out)
 
-    assert plan(120, 224) == (74, 3, 75)          # 8 GPUs, FFN-down: 46 tail tiles x 3 segments = 2 sub-waves of 1/3
+    assert plan(120, 224)[1] == 1                 # 8 GPUs, FFN-down: 46 tail tiles need two sub-waves; measured gain 1 %: left alone
+    assert plan(120, 224, force=3) == (74, 3, 75)
     assert plan(120, 48)[1] == 1                  # 8 GPUs, o-projection: the combine launch costs more than the idle tail
     full, ns, per = plan(228, 224)                # 4 GPUs, FFN-down: 6 tail tiles spread over the 74 pairs
     assert full == 222 and ns >= 6 and 6 * ns <= 74 and (ns - 1) * per < 224 <= ns * per

@@ -826,10 +826,11 @@ __global__ void __launch_bounds__(256) gemm_splitk_combine_kernel(const GemmPara
 }
 
 // Tail split-K plan (host arithmetic, exported through yb_gemm_splitk_plan): `tiles` output tiles on `clusters` SM pairs leave a
-// last wave of r = tiles % clusters tiles; cutting each of them into ns K segments costs ceil(r * ns / clusters) sub-waves of
-// 1 / ns of a tile, plus the partial round trip and the combine launch (~6 us, i.e. 13.6 / num_kb of a tile, + 1 % per segment).
-// Taken only when that beats the idle tail by 15 %: 8-GPU FFN-down (120 tiles, K = 14336): 3 segments, 2.0 -> 1.73 tile times;
-// 4-GPU (228 tiles): 12 segments, 4.0 -> 3.2; never at 1 or 2 GPUs (876 / 444 tiles fill their last wave).
+// last wave of r = tiles % clusters tiles; cutting each of them into ns K segments costs ceil(r * ns / clusters) sub-waves, each
+// 1 / ns of a tile plus a fixed ~6 us (pipeline fill + fp32 dump of the partial; a 64-column K block takes ~0.4 us, so 15 / num_kb
+// of a tile), plus the combine launch (13.6 / num_kb) and 1 % per segment of workspace traffic. Calibrated on
+// profiles/r02_gemm_splitk.md: 4-GPU FFN-down (228 tiles, K = 14336) 338 -> 305 us, 4-GPU o-projection 89 -> 86 us; the 8-GPU
+// FFN-down (120 tiles, 46 in the tail) gains 1 % with 3 segments and is left alone; never at 1 or 2 GPUs (full last waves).
 static void gemm_splitk_plan(int tiles, int num_kb, int clusters, int force_ns, int* full, int* ns, int* per) {
   *full = tiles; *ns = 1; *per = num_kb;
   if (clusters <= 0 || force_ns == 1) return;
@@ -843,7 +844,7 @@ static void gemm_splitk_plan(int tiles, int num_kb, int clusters, int force_ns, 
     double best = 0.85;
     for (int n = 2; n <= 12 && num_kb / n >= 8; ++n) {
       const int pr = (num_kb + n - 1) / n;
-      const double cost = static_cast<double>((r * n + clusters - 1) / clusters) * pr / num_kb + 13.6 / num_kb + 0.01 * n;
+      const double cost = static_cast<double>((r * n + clusters - 1) / clusters) * (pr + 15.0) / num_kb + 13.6 / num_kb + 0.01 * n;
       if (cost < best) { best = cost; *ns = n; }
     }
     if (*ns == 1) return;
