@@ -782,8 +782,12 @@ def main():
     ap.add_argument("--no-14b", action="store_true", help="supplementary: skip the 14B runs")
     ap.add_argument("--no-vae", action="store_true", help="supplementary: skip the VAE decodes")
     ap.add_argument("--sp-transport", default="auto", choices=["auto", "p2p", "p2p_gemm", "nccl"])
+    ap.add_argument("--gemm-split-k", type=int, default=0, choices=[0, 1], help="tail split-K of the gate+residual GEMMs: 0 automatic, 1 never (A/B)")
     ap.add_argument("--quick", action="store_true", help="profiling runs: exact --warmup, no e2e leg, no CPU baseline")
     args = ap.parse_args()
+    if args.gemm_split_k:
+        from yume_b200 import ops as _ops
+        _ops.GEMM_SPLIT_K = args.gemm_split_k
     if args.workload == "vae":
         vae_arm(args)
     elif args.workload in ("vae22", "vae21"):

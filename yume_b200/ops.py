@@ -60,7 +60,7 @@ def _need(t: torch.Tensor, dtype, name: str) -> None:
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, epilogue: int,
          gate: Optional[torch.Tensor] = None, tok_idx: Optional[torch.Tensor] = None, block_n: int = 0,
          n_split: int = 0, split_stride: int = 0, a_split: int = 0, a_split_stride: int = 0,
-         shape: Optional[tuple] = None, res: Optional[torch.Tensor] = None, cta_pair: int = 0, split_k: int = 0) -> torch.Tensor:
+         shape: Optional[tuple] = None, res: Optional[torch.Tensor] = None, cta_pair: int = 0, split_k: Optional[int] = None) -> torch.Tensor:
     """out = epi(a[M,K] @ w[N,K]^T + bias). a, w bf16 (2-D, row stride arbitrary); see include/yume_b200.h.
     cta_pair: 0 automatic, 1 force the 1-CTA kernel, 2 force the SM-pair (cta_group::2) kernel.
     split_k (SM-pair GATE_RES launches): 0 automatic tail split-K, 1 never, 2..12 force that many K segments on the last wave."""
@@ -86,6 +86,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: to
         _need(gate, torch.float32, "gate")
     if tok_idx is not None:
         _need(tok_idx, torch.int32, "tok_idx")
+    if split_k is None:
+        split_k = GEMM_SPLIT_K
     ws, ws_bytes = None, 0
     if epilogue == YB_EPI_GATE_RES and split_k != 1 and cta_pair != 1:
         # caller-owned workspace of the tail split-K (the library never allocates): a stream-ordered allocation from torch's
@@ -325,6 +327,7 @@ YB_EPI_RES_BF16 = YB_EPI_RES_BF16
 # kernel choice of conv3d_causal when the caller does not say (0 = 1-CTA kernel, 1 = SM-pair kernel); set per engine after the
 # per-width crossover measurement (profiles/README.md)
 CONV_CTA_PAIR = 0
+GEMM_SPLIT_K = 0     # tail split-K policy of the SM-pair gate+residual GEMM for callers that do not pass one: 0 automatic, 1 never
 
 
 def conv3d_causal(xpad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, T: int, H: int,
