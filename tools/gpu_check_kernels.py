@@ -351,10 +351,10 @@ def sec_atttrace():
     _trace_one(lib, q, k, v, out, tr, L, heads, 0)
 
 
-def _trace_one(lib, q, k, v, out, tr, L, heads, emu):
+def _trace_one(lib, q, k, v, out, tr, L, heads, flags=0):
     for _ in range(3):
         rc = lib.yb_attention_ex(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(),
-                                 out.stride(0), L, L, heads, 1.0 / math.sqrt(128.0), ((emu & 3) << 2) | (128 if emu & 4 else 0), None, 0, tr.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                                 out.stride(0), L, L, heads, 1.0 / math.sqrt(128.0), flags, None, 0, tr.data_ptr(), torch.cuda.current_stream().cuda_stream)
         assert rc == 0
     torch.cuda.synchronize()
     t = tr.view(32, 32).cpu()

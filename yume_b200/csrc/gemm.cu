@@ -1033,8 +1033,12 @@ extern "C" long long yb_gemm_workspace_bytes(int M, int N, int K, int epilogue, 
   if (M <= 0 || N <= 0 || K <= 0 || epilogue != YB_EPI_GATE_RES || split_k == 1 || split_k < 0 || split_k > 12) return 0;
   if (!(cta_pair == 2 || (cta_pair == 0 && M >= 1024 && N >= 128))) return 0;
   static int max_clusters[kMaxDevices] = {0};
+  static bool attr_set[kMaxDevices] = {false};
   const int dev = current_device();
-  if (max_clusters[dev] == 0) max_clusters[dev] = pair_max_clusters(gemm_pair_kernel<YB_EPI_GATE_RES>);
+  if (max_clusters[dev] == 0) {   // same query, same kernel attributes as the launch path: the two plans must agree
+    if (ensure_dynamic_smem(gemm_pair_kernel<YB_EPI_GATE_RES>, 227 * 1024, attr_set, "gemm_pair")) return 0;
+    max_clusters[dev] = pair_max_clusters(gemm_pair_kernel<YB_EPI_GATE_RES>);
+  }
   const int bn = pair_block_n(M, N, max_clusters[dev]);
   const int tiles = ((M + 255) / 256) * ((N + bn - 1) / bn);
   int full, ns, per;
