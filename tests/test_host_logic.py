@@ -434,3 +434,13 @@ def test_gemm_tail_split_k_plan():
             assert 0 <= full <= tiles and 1 <= ns <= 12
             if ns > 1:
                 assert full % 74 == 0 and (ns - 1) * per < num_kb <= ns * per and per >= 8
+
+
+def test_graft_entry_build_runs():
+    """The driver's CPU-side build check: __graft_entry__.build() compiles (no-op when the library is current), loads the
+    library and checks the ABI version against the binding."""
+    import importlib
+    import sys
+    sys.path.insert(0, str(ROOT))
+    entry = importlib.import_module("__graft_entry__")
+    entry.build()
