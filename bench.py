@@ -102,13 +102,13 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------------------
 # CPU reference arm (the one place bench.py executes oracle/ on the CPU): bounded, FIXED sample of the same workload
 # ------------------------------------------------------------------------------------------------------------
-CPU_SAMPLE_L, CPU_SAMPLE_GRID, CPU_SAMPLE_REPS = 2310, (21, 11, 10), 3
+CPU_SAMPLE_L, CPU_SAMPLE_GRID, CPU_SAMPLE_REPS = 2310, (21, 11, 10), 5
 
 
 def cpu_reference_sample():
     """Times the oracle port of WanAttentionBlock.forward (oracle/wan_dit.py <- wan23/modules/model.py:272-316) at the
     real 5B width on the host cores. The sample is FIXED — one block at L' = 2310 tokens (1/8 of the sequence), 1 warm-up +
-    3 timed repetitions, independent of --steps / --warmup — so every invocation (product line, BENCH reference arm, SCALE
+    5 timed repetitions (best taken), independent of --steps / --warmup — so every invocation (product line, BENCH reference arm, SCALE
     reference arm) measures the same thing; it is extrapolated to the 30-block step by algorithmic FLOPs."""
     from oracle import synth
     from oracle.wan_dit import WanOracle, grid_freqs
@@ -134,12 +134,14 @@ def cpu_reference_sample():
 
     run()                                                      # first touch of weights / thread pool: discarded
     times = [run() for _ in range(CPU_SAMPLE_REPS)]
-    t_sample = sum(times) / len(times)
+    # best of the repetitions: the host is shared and noisy (2.0 - 5.5 s for the same sample on the same box); the minimum is the
+    # reproducible figure and the one most favourable to the reference arm
+    t_sample = min(times)
     step_flops = CFG_5B["num_layers"] * block_flops(SEQ_LEN, C, F, S)
     factor = step_flops / block_flops(L, C, F, S)
     return dict(t_sample_s=t_sample, t_step_s=t_sample * factor, cores=cores, L=L, times_s=times, factor=factor,
                 sample=f"1 of 30 WanAttentionBlocks (oracle port, fp32 weights, bf16 SDPA) at L={L} of 18480 tokens: "
-                       f"{CPU_SAMPLE_REPS} reps after 1 warm-up, mean {t_sample:.2f} s (min {min(times):.2f}, max {max(times):.2f}), "
+                       f"best of {CPU_SAMPLE_REPS} reps after 1 warm-up: {t_sample:.2f} s (mean {sum(times) / len(times):.2f}, max {max(times):.2f}), "
                        f"extrapolated to the 30-block step by algorithmic FLOPs (x{factor:.1f})")
 
 
