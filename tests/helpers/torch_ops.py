@@ -105,3 +105,19 @@ def vae_patchify2_bf16(video, out):
     out.zero_()
     out[:, :12] = x.permute(1, 2, 3, 0).reshape(-1, 12).to(out.dtype)
     return out
+
+
+def vae_dupup_add(main, x, dims, in_c, out_c, ft, fs):
+    """main [ft*T-(ft-1), H*fs, W*fs, out_c] += DupUp3D(x [T, H, W, in_c]) (first ft-1 duplicated frames dropped)."""
+    from oracle import wan22vae
+    T, H, W = dims
+    xn = x.float().view(T, H, W, in_c).permute(3, 0, 1, 2)[None]
+    up = wan22vae.Wan22VaeOracle.dup_up(xn, out_c, ft, fs)[0].permute(1, 2, 3, 0)          # [To, Ho, Wo, out_c]
+    main.copy_((main.float().view(up.shape) + up).reshape(main.shape).to(main.dtype))
+    return main
+
+
+def vae_unpatchify2_clamp(y, out, T, H, W):
+    v = y[:, :12].view(T, H, W, 12).permute(3, 0, 1, 2)[None]
+    out.copy_(v.reshape(1, 3, 2, 2, T, H, W).permute(0, 1, 4, 5, 3, 6, 2).reshape(3, T, 2 * H, 2 * W).clamp(-1, 1))
+    return out
