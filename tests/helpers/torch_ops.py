@@ -203,3 +203,145 @@ def vae_assemble_tiles(tiles, th, tw, tlen, tf0, out, row_limit, blend_extent, t
             pieces.append(tile[:, :t_limit + 1])
     out.copy_(torch.cat(pieces, dim=1))
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# DiT engine (yume_b200/dit.py) stand-ins
+# ------------------------------------------------------------------------------------------------------------
+def _gelu_tanh(x):
+    return F.gelu(x, approximate="tanh")
+
+
+def gemm(a, w, bias, out, epilogue=YB_EPI_BF16, gate=None, tok_idx=None, block_n=0, n_split=0, split_stride=0, a_split=0,  # noqa: F811
+         a_split_stride=0, shape=None, res=None, cta_pair=0, split_k=None):
+    """Full-featured stand-in of yb_gemm_bf16 (replaces the minimal one above): every epilogue, the gate table + token index of the
+    adaLN gate, the Ulysses layouts (n_split: column block j of the output written to chunk j; a_split: A given as K chunks)."""
+    if a_split:                                              # A[t, k] = a[k // a_split, t, k % a_split]
+        M, K = shape
+        A = a.reshape(-1)[: (K // a_split) * a_split_stride].view(K // a_split, a_split_stride)[:, : M * a_split]
+        A = A.reshape(K // a_split, M, a_split).permute(1, 0, 2).reshape(M, K).float()
+    else:
+        A = a.float()
+        M = A.shape[0]
+    y = A @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    if epilogue == YB_EPI_GELU_TANH:
+        y = _gelu_tanh(y)
+    elif epilogue == YB_EPI_GELU_ERF:
+        y = F.gelu(y)
+    elif epilogue == YB_EPI_RES_BF16:
+        y = y + res.float()
+    if epilogue == YB_EPI_GATE_RES:
+        if gate is not None:
+            rows = tok_idx.long() if tok_idx is not None else torch.zeros(M, dtype=torch.long)
+            y = y * gate[rows]
+        out.add_(y)
+        return out
+    if n_split:
+        N = w.shape[0]
+        dst = out.reshape(-1)[: (N // n_split) * split_stride].view(N // n_split, split_stride)[:, : M * n_split]
+        dst.view(N // n_split, M, n_split).copy_(y.view(M, N // n_split, n_split).permute(1, 0, 2).to(out.dtype))
+        return out
+    out.copy_(y.to(out.dtype))
+    return out
+
+
+YB_EPI_GELU_BF16, YB_EPI_GELU_ERF_BF16 = YB_EPI_GELU_TANH, YB_EPI_GELU_ERF
+
+
+def ln_modulate(x, out, scale, shift, tok_idx=None, weight=None, bias=None, eps=1e-6):
+    y = F.layer_norm(x.float(), (x.shape[1],), None, None, eps)
+    if weight is not None:
+        y = y * weight + bias
+    if scale is not None:
+        rows = tok_idx.long() if tok_idx is not None else torch.zeros(x.shape[0], dtype=torch.long)
+        sc = scale[rows] if scale.dim() == 2 else scale
+        sh = shift[rows] if shift.dim() == 2 else shift
+        y = y * (1 + sc) + sh
+    out.copy_(y.to(out.dtype))
+    return out
+
+
+def _norm_rope_rows(x, weight, rope, head_dim, eps, rope_len):
+    """x f32 [L, C] -> RMSNorm over C * weight, then 3-axis RoPE on adjacent pairs of every head for rows < rope_len."""
+    L, C = x.shape
+    y = x * torch.rsqrt(x.pow(2).mean(dim=1, keepdim=True) + eps) * weight
+    if rope is not None:
+        n = L if rope_len is None else min(rope_len, L)
+        v = y[:n].view(n, C // head_dim, head_dim // 2, 2)
+        cos, sin = rope[:n, None, :, 0], rope[:n, None, :, 1]
+        rot = torch.stack([v[..., 0] * cos - v[..., 1] * sin, v[..., 0] * sin + v[..., 1] * cos], dim=-1)
+        y = torch.cat([rot.reshape(n, C), y[n:]], dim=0)
+    return y
+
+
+def _pieces_view(qk, pieces):
+    """The peer-major Ulysses send buffer seen as [pieces, L, piece_cols]: logical column c of row t is element c % piece_cols of
+    piece c // piece_cols, pieces `piece_stride` elements apart, rows qk.stride(0) apart (yb_rmsnorm_rope_pieces)."""
+    L, C, pc, ps = pieces
+    return torch.as_strided(qk, (C // pc, L, pc), (ps, qk.stride(0), 1), qk.storage_offset())
+
+
+def rmsnorm_rope(qk, weight, rope, head_dim, eps=1e-6, rope_len=None, pieces=None):
+    if pieces is not None:
+        v = _pieces_view(qk, pieces)                                         # [P, L, pc]
+        L, C = pieces[0], pieces[1]
+        y = _norm_rope_rows(v.permute(1, 0, 2).reshape(L, C).float(), weight, rope, head_dim, eps, rope_len)
+        v.copy_(y.view(L, C // pieces[2], pieces[2]).permute(1, 0, 2).to(qk.dtype))
+        return qk
+    qk.copy_(_norm_rope_rows(qk.float(), weight, rope, head_dim, eps, rope_len).to(qk.dtype))
+    return qk
+
+
+def qk_norm_rope(q, k, wq, wk, rope, head_dim, eps=1e-6, rope_len=None, pieces=None):
+    rmsnorm_rope(q, wq, rope, head_dim, eps, rope_len, pieces)
+    rmsnorm_rope(k, wk, rope, head_dim, eps, rope_len, pieces)
+
+
+def attention(q, k, v, out, heads, scale=None, variant=0, accumulate=False, split=0):
+    Lq, Lk, d = q.shape[0], k.shape[0], 128
+    f = lambda t, L: t.float().reshape(L, heads, d).transpose(0, 1)[None]  # noqa: E731
+    o = F.scaled_dot_product_attention(f(q, Lq), f(k, Lk), f(v, Lk), scale=scale)[0].transpose(0, 1).reshape(Lq, heads * d)
+    if accumulate:
+        o = o + out.float()
+    out.copy_(o.to(out.dtype))
+    return out
+
+
+def linear_f32_small(x, w, bias, silu_in=False):
+    y = (F.silu(x) if silu_in else x) @ w.t()
+    return y + bias if bias is not None else y
+
+
+def linear_f32(x, w, bias, out):
+    out.copy_(x @ w.t() + (bias if bias is not None else 0))
+    return out
+
+
+def bcast_add(a, b):
+    return a[:, None, :] + b[None, :, :]
+
+
+def sinusoidal(t, dim):
+    half = dim // 2
+    pos = t.reshape(-1).double()
+    s = torch.outer(pos, torch.pow(10000, -torch.arange(half).double().div(half)))
+    return torch.cat([torch.cos(s), torch.sin(s)], dim=1).float()
+
+
+def patchify(x, out, ph, pw):
+    """x f32 [Cin, F, H, W] -> out bf16 [F*ceil(H/ph)*ceil(W/pw), >= Cin*ph*pw]: token order (f, hp, wp), column order (cin, i, j);
+    rows / columns past H, W read as zero (convpadd)."""
+    Cin, Fr, H, W = x.shape
+    hp, wp = -(-H // ph), -(-W // pw)
+    xp = F.pad(x.float(), (0, wp * pw - W, 0, hp * ph - H))
+    t = xp.view(Cin, Fr, hp, ph, wp, pw).permute(1, 2, 4, 0, 3, 5).reshape(Fr * hp * wp, Cin * ph * pw)
+    out[:, : Cin * ph * pw] = t.to(out.dtype)
+    return out
+
+
+def unpatchify(y, out, Fr, Hp, Wp, ph, pw):
+    Cout = out.shape[0]
+    out.copy_(y[: Fr * Hp * Wp, : ph * pw * Cout].reshape(Fr, Hp, Wp, ph, pw, Cout).permute(5, 0, 1, 3, 2, 4).reshape(Cout, Fr, Hp * ph, Wp * pw))
+    return out
