@@ -81,3 +81,39 @@ def test_wan21_wrapper_hooks_are_drop_ins(cpu_ops):
     got_mu, got_x = wrapper.encode([video]), wrapper.decode([z])
     assert got_mu[0].shape == want_mu.shape and _rel(got_mu[0], want_mu) < 3e-2
     assert got_x[0].shape == want_x.shape and _rel(got_x[0], want_x) < 3e-2
+
+
+@torch.no_grad()
+def test_hyvideo_install_vae_is_a_drop_in(monkeypatch):
+    """`install_vae` on the reference's own `AutoencoderKLCausal3D` (hyvideo/vae/autoencoder_kl_causal_3d.py, loaded with the diffusers
+    stubs of tools/make_golden_vae.py): the module's own tiled decode, then the re-bound `decode(z, return_dict=...)` — same return
+    convention, `enable_tiling()` honoured, output within the bf16 budget."""
+    import sys
+    if not (REF / "hyvideo" / "vae" / "autoencoder_kl_causal_3d.py").exists():
+        pytest.skip("reference tree not present")
+    root = Path(__file__).resolve().parents[1]
+    sys.path.insert(0, str(root / "tools"))
+    import make_golden_vae
+    from oracle import hyvae
+    from yume_b200 import vae as ybvae
+    monkeypatch.setattr(ybvae, "ops", torch_ops)
+    ak = make_golden_vae.load_reference_vae()
+    cfg = make_golden_vae.TINY
+    sd = hyvae.make_state_dict(99, **cfg)
+    ref = ak.AutoencoderKLCausal3D(in_channels=3, out_channels=3, down_block_types=("DownEncoderBlockCausal3D",) * 4,
+                                   up_block_types=("UpDecoderBlockCausal3D",) * 4, block_out_channels=cfg["block_out_channels"],
+                                   layers_per_block=2, act_fn="silu", latent_channels=16, norm_num_groups=32, sample_size=64,
+                                   sample_tsize=16, time_compression_ratio=4, spatial_compression_ratio=8, mid_block_add_attention=True)
+    ref.load_state_dict(sd, strict=False)
+    ref.eval()
+    ref.enable_tiling()
+    z = torch.randn(1, 16, 6, 10, 12, generator=torch.Generator().manual_seed(5))
+    want = ref.decode(z, return_dict=False)[0]
+    ybvae.install_vae(ref, device="cpu")
+    got = ref.decode(z, return_dict=False)
+    assert isinstance(got, tuple) and got[0].shape == want.shape and _rel(got[0], want) < 3e-2
+    out = ref.decode(z)
+    assert _rel(out.sample, want) < 3e-2
+    ref.disable_tiling()                                          # the hook follows the module's own switches
+    small = torch.randn(1, 16, 2, 4, 6, generator=torch.Generator().manual_seed(6))
+    assert ref.decode(small, return_dict=False)[0].shape == (1, 3, 5, 32, 48)
