@@ -125,9 +125,10 @@ struct AttCfg {
 // Where the time goes (profiles/r02_ncu_block.md, r02_instr_rate.md): per 128-key step a CTA spends ~3000 cycles for 2048 cycles of tensor
 // work and 2048 cycles of MUFU work; both pipes are ~67 % busy. Each query tile's chain softmax (~1720) -> P.V + next S (~1150) ->
 // hand-off (~100) is serial, the two tiles run it in ping-pong. The exponential phase of the one softmax warp per scheduler runs at
-// 10.9 cycles per MUFU.EX2 against the unit's 8: ptxas schedules the loop at 8.1, the rest are scoreboard waits of an in-order warp
-// that has nothing else to issue. Round 2 measured eleven alternatives against this kernel and kept none (profiles/r02_attention_
-// schedules.md): Q in TMEM with 64-key tiles, deferred max, packed bf16x2 exponentials, pipelined softmax, ALU-pipe packing, FMA-pipe
+// 10.9 cycles per MUFU.EX2 (21.9 per pair of scores): the unit alone issues every 8.0 cycles, every 8.5 - 9.0 while the tensor core of
+// the SM is busy, and this instruction mix on one warp takes 20.0 per pair under tensor load (ptxas schedules it at 8.1 per MUFU, the
+// rest are scoreboard waits of an in-order warp) — the phase is within 10 % of what its instruction stream can do.
+// Round 2 measured eleven alternatives against this kernel and kept none (profiles/r02_attention_schedules.md): Q in TMEM with 64-key tiles, deferred max, packed bf16x2 exponentials, pipelined softmax, ALU-pipe packing, FMA-pipe
 // polynomial exponentials, a lookahead schedule with double-buffered S, scalar instead of packed fp32 math, a deferred P store wait,
 // S(j+1) issued in two 64-key halves (N = 64 MMAs run at the N = 128 rate), and two threads per query row (16 softmax warps:
 // correct, 3.75 vs 3.13 ms). cuDNN's fused attention is 14-17 % ahead on the same tensors (profiles/r02_attention_comparators.json).
