@@ -1,7 +1,8 @@
-"""TEST INFRASTRUCTURE: a torch-CPU stand-in for the handful of `yume_b200.ops` entry points the VAE encoder engines call, with
-the same argument meaning and buffer layouts as the C ABI (include/yume_b200.h). It lets the CPU suite drive the HOST logic of
-yume_b200/vae_enc.py (weight re-packing, folded normalisation, frame bookkeeping, strides, shortcut wiring) against the
-reference-generated fixtures without a GPU. Never imported by the package; the product path has no CPU fallback."""
+"""TEST INFRASTRUCTURE: a torch-CPU stand-in for the `yume_b200.ops` entry points the engines call (DiT, the three VAE decoders, the two
+VAE encoders), with the same argument meaning and buffer layouts as the C ABI (include/yume_b200.h). It lets the CPU suite drive the HOST
+logic of the engines (weight re-packing, packer, token streams, folded normalisations, frame bookkeeping, tile plans, Ulysses layouts)
+against the reference-generated fixtures without a GPU. Tests monkeypatch it in; it is never imported by the package, and the product
+path has no CPU fallback (a missing library or a CPU tensor is an error there)."""
 import torch
 import torch.nn.functional as F
 
@@ -26,16 +27,6 @@ def nhwc_to_nchw_f32(x, out, clamp=None):
     out.copy_(x[:, :out.shape[0]].t())
     if clamp is not None:
         out.clamp_(*clamp)
-    return out
-
-
-def gemm(a, w, bias, out, epilogue=YB_EPI_BF16, res=None, **_):
-    y = a.float() @ w.float().t()
-    if bias is not None:
-        y = y + bias
-    if epilogue == YB_EPI_RES_BF16:
-        y = y + res.float()
-    out.copy_(y.to(out.dtype))
     return out
 
 
@@ -212,9 +203,9 @@ def _gelu_tanh(x):
     return F.gelu(x, approximate="tanh")
 
 
-def gemm(a, w, bias, out, epilogue=YB_EPI_BF16, gate=None, tok_idx=None, block_n=0, n_split=0, split_stride=0, a_split=0,  # noqa: F811
+def gemm(a, w, bias, out, epilogue=YB_EPI_BF16, gate=None, tok_idx=None, block_n=0, n_split=0, split_stride=0, a_split=0,
          a_split_stride=0, shape=None, res=None, cta_pair=0, split_k=None):
-    """Full-featured stand-in of yb_gemm_bf16 (replaces the minimal one above): every epilogue, the gate table + token index of the
+    """Stand-in of yb_gemm_bf16: every epilogue, the gate table + token index of the
     adaLN gate, the Ulysses layouts (n_split: column block j of the output written to chunk j; a_split: A given as K chunks)."""
     if a_split:                                              # A[t, k] = a[k // a_split, t, k % a_split]
         M, K = shape
