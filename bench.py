@@ -146,9 +146,9 @@ def cpu_reference_sample():
 
 
 def cpu_baseline_isolated() -> dict:
-    """The `cpu_baseline` object of the product line: the SAME fixed sample as `--impl reference`, run in a fresh process without a
-    CUDA context (inside this process, next to the CUDA runtime's threads and 10 GB of pinned / device state, the identical sample
-    measured 5.4 s against 2.0 - 2.8 s alone — the two arms must report one number). Falls back to the in-process sample."""
+    """The `cpu_baseline` object of the product line: the SAME fixed sample as `--impl reference`, run the same way — a fresh process
+    without a CUDA context — so that both arms measure one thing. (The shared 128-core host is noisy: 1.9 - 5.5 s for the identical
+    sample across runs on the same box; best-of-5 and process isolation remove what can be removed.) Falls back to the in-process sample."""
     import subprocess
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
     env["CUDA_VISIBLE_DEVICES"] = ""
